@@ -1,0 +1,458 @@
+// kernels.cuh -- __global__ kernels for sm_100a: BLAS build (Morton, radix sort, LBVH, wide collapse), camera +
+// routing, the persistent two-level trace kernel, framebuffer and domain-exchange helpers.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include "bvh_build.h"
+#include "gvt_device.h"
+#include "shade.h"
+#include "traverse.h"
+
+namespace cg = cooperative_groups;
+
+namespace gvt {
+
+// =========================================================================================================
+// BLAS build
+// =========================================================================================================
+__global__ void k_tri_setup(BuildCtx c) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c.n) tri_setup(c, i);
+}
+__global__ void k_leaf_setup(BuildCtx c) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c.n) leaf_setup(c, i);
+}
+__global__ void k_karras(BuildCtx c) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 < c.n) karras_node(c, (int)i);
+}
+// bottom-up refit: the second thread to reach an internal node computes its box and continues upwards
+__global__ void k_refit(BuildCtx c) {
+  unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.n) return;
+  int node = c.bn_parent[c.n - 1 + k];
+  if (c.n == 1) return;
+  while (node >= 0) {
+    __threadfence();
+    unsigned old = atomicAdd(&c.bn_flag[node], 1u);
+    if (old == 0u) return;
+    int2 ch = c.bn_child[node];
+    // children boxes were written by other threads: read through L2
+    float4 l0 = __ldcg(&c.bn_lo[ch.x]), h0 = __ldcg(&c.bn_hi[ch.x]);
+    float4 l1 = __ldcg(&c.bn_lo[ch.y]), h1 = __ldcg(&c.bn_hi[ch.y]);
+    c.bn_lo[node] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
+    c.bn_hi[node] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+    node = c.bn_parent[node];
+  }
+}
+// one thread per wide node of the current level; children tasks are appended to `out`
+__global__ void k_collapse(BuildCtx c, const CollapseTask *in, unsigned n_in, CollapseTask *out, unsigned *n_out) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_in) return;
+  CollapseTask t = in[i];
+  int slot_b[8], n_internal, n_leaf_tris;
+  uint32_t meta[8];
+  unsigned qlo[24], qhi[24];
+  float4 w0;
+  collapse_node(c, t, slot_b, n_internal, n_leaf_tris, meta, qlo, qhi, w0);
+  unsigned child_base = n_internal ? atomicAdd(c.node_count, (unsigned)n_internal) : 0u;
+  unsigned tri_base = n_leaf_tris ? atomicAdd(c.tri_count, (unsigned)n_leaf_tris) : 0u;
+  unsigned qpos = n_internal ? atomicAdd(n_out, (unsigned)n_internal) : 0u;
+  collapse_emit(c, t, slot_b, meta, qlo, qhi, w0, child_base, tri_base, out + qpos);
+}
+
+// ---- LSD radix sort, 8 bits per pass, stable; keys + values (uint32) ---------------------------------------
+#define RS_THREADS 256
+#define RS_ITEMS 8
+#define RS_TILE (RS_THREADS * RS_ITEMS)
+
+__global__ void k_rs_hist(const uint32_t *keys, unsigned n, int shift, unsigned *hist, unsigned nblocks) {
+  __shared__ unsigned h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned base = blockIdx.x * RS_TILE;
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    unsigned i = base + it * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// in-place exclusive scan of one tile per block; block totals to sums[]
+__global__ void k_scan_tile(unsigned *data, unsigned n, unsigned *sums) {
+  __shared__ unsigned warp_tot[RS_THREADS / 32];
+  unsigned base = blockIdx.x * RS_TILE + threadIdx.x * RS_ITEMS;
+  unsigned v[RS_ITEMS], tot = 0;
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    v[k] = (base + k < n) ? data[base + k] : 0u;
+    tot += v[k];
+  }
+  unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned inc = tot;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (unsigned)o) inc += t;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = lane < RS_THREADS / 32 ? warp_tot[lane] : 0u;
+    unsigned winc = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= (unsigned)o) winc += t;
+    }
+    if (lane < RS_THREADS / 32) warp_tot[lane] = winc - w;
+    if (lane == RS_THREADS / 32 - 1 && sums) sums[blockIdx.x] = winc;
+  }
+  __syncthreads();
+  unsigned run = warp_tot[warp] + inc - tot;
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    if (base + k < n) data[base + k] = run;
+    run += v[k];
+  }
+}
+__global__ void k_scan_add(unsigned *data, unsigned n, const unsigned *sums) {
+  unsigned base = blockIdx.x * RS_TILE;
+  unsigned add = sums[blockIdx.x];
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    unsigned i = base + it * RS_THREADS + threadIdx.x;
+    if (i < n) data[i] += add;
+  }
+}
+
+__global__ void k_rs_scatter(const uint32_t *keys, const uint32_t *vals, uint32_t *okeys, uint32_t *ovals, unsigned n, int shift,
+                             const unsigned *offs, unsigned nblocks) {
+  __shared__ unsigned cnt[RS_THREADS / 32][256];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int w = 0; w < RS_THREADS / 32; ++w) cnt[w][threadIdx.x] = 0;
+  __syncthreads();
+  // warp `warp` owns RS_TILE/8 consecutive keys, walked 32 at a time in order (stability)
+  const unsigned wbase = blockIdx.x * RS_TILE + warp * (RS_TILE / (RS_THREADS / 32));
+  uint32_t k[RS_ITEMS], v[RS_ITEMS];
+  const unsigned ltmask = (1u << lane) - 1u;
+#pragma unroll
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    unsigned i = wbase + it * 32 + lane;
+    bool ok = i < n;
+    k[it] = ok ? keys[i] : 0xFFFFFFFFu;
+    v[it] = ok ? vals[i] : 0u;
+    unsigned d = ok ? ((k[it] >> shift) & 255u) : 256u + lane; // invalid lanes get private "digits"
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (ok && (peers & ltmask) == 0u) cnt[warp][d] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  { // digit threadIdx.x: exclusive prefix over the warps, seeded with this block's global offset
+    unsigned d = threadIdx.x;
+    unsigned run = offs[d * nblocks + blockIdx.x];
+    for (int w = 0; w < RS_THREADS / 32; ++w) {
+      unsigned c = cnt[w][d];
+      cnt[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    unsigned i = wbase + it * 32 + lane;
+    bool ok = i < n;
+    unsigned d = ok ? ((k[it] >> shift) & 255u) : 256u + lane;
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (ok) {
+      unsigned pos = cnt[warp][d] + __popc(peers & ltmask);
+      okeys[pos] = k[it];
+      ovals[pos] = v[it];
+    }
+    __syncwarp();
+    if (ok && (peers & ltmask) == 0u) cnt[warp][d] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+// =========================================================================================================
+// Frame kernels
+// =========================================================================================================
+struct SceneDev {
+  Tlas tlas;
+  const Instance *inst;
+  const Blas *blas;
+  float *fb; // RGBA float, W*H*4
+  DevCounters *ctr;
+};
+
+// warp-aggregated append: one atomic per group of converged lanes
+__device__ __forceinline__ unsigned queue_reserve(unsigned *count) {
+  cg::coalesced_group g = cg::coalesced_threads();
+  unsigned base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(count, g.size());
+  return g.shfl(base, 0) + g.thread_rank();
+}
+__device__ __forceinline__ void count_add(unsigned long long *c, unsigned long long v) {
+  cg::coalesced_group g = cg::coalesced_threads();
+  unsigned long long s = cg::reduce(g, v, cg::plus<unsigned long long>());
+  if (g.thread_rank() == 0 && s) atomicAdd(c, s);
+}
+
+// IceTComposite::localAdd (composite/IceTComposite.cpp:111-117): += colour, alpha += 1.  The running clamp to 1 is
+// applied once at the end (k_fb_clamp): min(1, sum) == clamp-after-each-add for non-negative terms.
+__device__ __forceinline__ void fb_add(float *fb, int id, V3 c) {
+  float *p = fb + 4 * (size_t)id;
+  atomicAdd(p + 0, c.x);
+  atomicAdd(p + 1, c.y);
+  atomicAdd(p + 2, c.z);
+  atomicAdd(p + 3, 1.0f);
+}
+__global__ void k_fb_clamp(float *fb, size_t npix) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  float4 v = reinterpret_cast<float4 *>(fb)[i];
+  v.x = fminf(v.x, 1.f), v.y = fminf(v.y, 1.f), v.z = fminf(v.z, 1.f);
+  reinterpret_cast<float4 *>(fb)[i] = v;
+}
+
+// camera rays [first, first+count) -> initial routing (FilterRaysLocally: TracerBase.h:319 / DomainTracer.h:148-181)
+__global__ void k_camera_route(FrameParams fp, SceneDev sd, size_t first, size_t count, RayQueue out) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  unsigned long long routed = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) {
+    Ray r;
+    camera_ray(fp.cam, first + i, r);
+    float t;
+    int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, -1, (fp.flags & FLAG_ENTER_INSIDE) != 0, t);
+    if (next < 0) continue;
+    if (fp.world > 1 && sd.inst[next].owner != fp.rank) continue; // shuffleDropRays keeps local first hits only
+    r.o = xadd(r.o, xmul(r.d, xmul(t, 0.95f)));                   // TracerBase.h:394
+    unsigned pos = queue_reserve(out.count);
+    if (pos < out.cap) queue_store(out, pos, r, next);
+    routed++;
+  }
+  count_add(&sd.ctr->routed_initial, routed);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&sd.ctr->camera_rays, (unsigned long long)count);
+}
+
+// camera rays only (parity hook for gvtPerspectiveCamera::generateRays)
+__global__ void k_camera_only(FrameParams fp, size_t count, RayQueue out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Ray r;
+  camera_ray(fp.cam, i, r);
+  queue_store(out, (unsigned)i, r, -1);
+}
+
+// routing only (parity hook for BVH::intersect / shuffleRays)
+__global__ void k_route(FrameParams fp, SceneDev sd, RayQueue in, unsigned n, int from, int *next, float *tout) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Ray r;
+  int dummy;
+  queue_load(in, i, r, dummy);
+  float t;
+  next[i] = tlas_route(sd.tlas, r.o, r.d, r.t_max, from, from == -1 && (fp.flags & FLAG_ENTER_INSIDE) != 0, t);
+  tout[i] = t;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The hot kernel.  Persistent CTAs; each warp pulls bundles of 32 queued rays from a global counter and runs
+// every ray to the end of its current life: trace in its instance (closest hit, or any hit for shadow rays);
+// on a miss, route to the next instance (from = this one), advance the origin, continue; on a hit, shade, emit
+// shadow rays (one per light) into `shq` and, if the bounce survives, the secondary ray into `nxq`.
+// This is Adapter::trace + shuffleRays (EmbreeMeshAdapter.cpp:436-623 + TracerBase.h:325-414) fused per ray.
+//   mode 0: scheduler mode (two-level, as above)
+//   mode 1: adapter mode (Adapter::trace contract): a ray that misses is appended to `mvq` instead of being routed
+// DomainScheduler: a ray routed to an instance owned by another rank is parked in `exq` (inst column = instance).
+// ---------------------------------------------------------------------------------------------------------
+struct TraceQueues {
+  RayQueue in, shq, nxq, mvq, exq;
+  unsigned *work; // bundle counter
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace(FrameParams fp, SceneDev sd, TraceQueues q, int mode) {
+  const unsigned n = min(*q.in.count, q.in.cap);
+  const unsigned lane = threadIdx.x & 31;
+  unsigned long long c_visits = 0, c_hits = 0, c_shgen = 0, c_shok = 0, c_sec = 0, c_fb = 0, c_exp = 0;
+  TravCounters tc;
+  tc.nodes = 0, tc.tris = 0;
+  for (;;) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(q.work, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    unsigned idx = base + lane;
+    if (idx >= n) continue;
+    Ray r;
+    int inst;
+    queue_load(q.in, idx, r, inst);
+    const bool born_shadow = (r.type == RAY_SHADOW);
+    bool first = true;
+    for (;;) {
+      const Instance in = sd.inst[inst];
+      const Blas &bl = sd.blas[in.mesh];
+      V3 lo, ld;
+      to_local(in, r.o, r.d, lo, ld);
+      Hit h;
+      c_visits++;
+      // prepGVT_EMBREE_PACKET_TYPE (EmbreeMeshAdapter.cpp:269-286): tnear = RAY_EPSILON, tfar = FLT_MAX
+      bool hit = (r.type == RAY_SHADOW) ? blas_traverse<true, COUNT>(bl, lo, ld, GVT_RAY_EPSILON, FLT_MAX, h, &tc)
+                                        : blas_traverse<false, COUNT>(bl, lo, ld, GVT_RAY_EPSILON, FLT_MAX, h, &tc);
+      if (hit) {
+        if (r.type == RAY_SHADOW) break; // occluded: dropped (:487-489)
+        c_hits++;
+        r.t = h.t;
+        V3 normal;
+        Mat mat;
+        surface_at(bl, in, h, r, fp.flags, normal, mat);
+        if (r.type == RAY_SECONDARY) { // :572-575
+          float tt = (h.t > 1.f) ? xdiv(1.f, h.t) : h.t;
+          r.w = xmul(r.w, tt);
+        }
+        for (int li = 0; li < fp.n_lights; ++li) {
+          const Light &L = fp.lights[li];
+          Ray sh;
+          if (!make_shadow_ray(r, normal, mat, L, light_position(L, fp.seed, r.id, r.depth, li), sh)) continue;
+          c_shgen++;
+          unsigned pos = queue_reserve(q.shq.count);
+          if (pos < q.shq.cap) queue_store(q.shq, pos, sh, inst);
+        }
+        if (make_bounce(r, normal, fp.seed)) {
+          c_sec++;
+          unsigned pos = queue_reserve(q.nxq.count);
+          if (pos < q.nxq.cap) queue_store(q.nxq, pos, r, inst);
+        }
+        break;
+      }
+      // miss
+      if (born_shadow && first) c_shok++;
+      first = false;
+      if (mode == 1) { // adapter contract: hand the ray back (localDispatch, :604-609 / :377-381)
+        unsigned pos = queue_reserve(q.mvq.count);
+        if (pos < q.mvq.cap) queue_store(q.mvq, pos, r, inst);
+        break;
+      }
+      float t;
+      int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, inst, false, t);
+      if (next < 0) {
+        if (r.type == RAY_SHADOW && xlength(r.color) > 0.f) { // TracerBase.h:396-399
+          fb_add(sd.fb, r.id, xmul(r.color, r.w));
+          c_fb++;
+        }
+        break;
+      }
+      r.o = xadd(r.o, xmul(r.d, xmul(t, 0.95f))); // TracerBase.h:394
+      if (fp.world > 1 && sd.inst[next].owner != fp.rank) {
+        unsigned pos = queue_reserve(q.exq.count);
+        if (pos < q.exq.cap) queue_store(q.exq, pos, r, next);
+        c_exp++;
+        break;
+      }
+      inst = next;
+    }
+  }
+  count_add(&sd.ctr->instance_visits, c_visits);
+  count_add(&sd.ctr->primary_hits, c_hits);
+  count_add(&sd.ctr->shadow_generated, c_shgen);
+  count_add(&sd.ctr->shadow_unoccluded, c_shok);
+  count_add(&sd.ctr->secondary_generated, c_sec);
+  count_add(&sd.ctr->fb_adds, c_fb);
+  count_add(&sd.ctr->rays_exported, c_exp);
+  if (COUNT) {
+    count_add(&sd.ctr->nodes_visited, tc.nodes);
+    count_add(&sd.ctr->tris_tested, tc.tris);
+  }
+}
+
+// closest-hit / any-hit queries in mesh-local space (parity hooks)
+__global__ void k_intersect(Blas bl, RayQueue in, unsigned n, int any_hit, int4 *hits) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Ray r;
+  int dummy;
+  queue_load(in, i, r, dummy);
+  Hit h;
+  TravCounters tc;
+  if (any_hit)
+    blas_traverse<true, false>(bl, r.o, r.d, GVT_RAY_EPSILON, FLT_MAX, h, &tc);
+  else
+    blas_traverse<false, false>(bl, r.o, r.d, GVT_RAY_EPSILON, FLT_MAX, h, &tc);
+  hits[i] = make_int4(h.prim, (int)f2u(h.prim >= 0 ? h.t : FLT_MAX), (int)f2u(h.u), (int)f2u(h.v));
+}
+
+// AoS (80-byte host records) <-> SoA columns
+__global__ void k_aos_to_soa(const uint4 *aos, unsigned n, RayQueue q, unsigned offset, int inst) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 *p = aos + 5 * (size_t)i;
+  uint4 a = p[0], b = p[1], c = p[2], d = p[3];
+  q.c0[offset + i] = make_float4(u2f(a.x), u2f(a.y), u2f(a.z), u2f(a.w));
+  q.c1[offset + i] = make_float4(u2f(b.x), u2f(b.y), u2f(b.z), u2f(b.w));
+  q.c2[offset + i] = make_float4(u2f(c.x), u2f(c.y), u2f(c.z), u2f(c.w));
+  q.c3[offset + i] = make_int4((int)d.x, (int)d.y, (int)d.z, (int)d.w);
+  q.inst[offset + i] = inst;
+}
+__global__ void k_soa_to_aos(RayQueue q, unsigned n, uint4 *aos) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = q.c0[i], b = q.c1[i], c = q.c2[i];
+  int4 d = q.c3[i];
+  uint4 *p = aos + 5 * (size_t)i;
+  p[0] = make_uint4(f2u(a.x), f2u(a.y), f2u(a.z), f2u(a.w));
+  p[1] = make_uint4(f2u(b.x), f2u(b.y), f2u(b.z), f2u(b.w));
+  p[2] = make_uint4(f2u(c.x), f2u(c.y), f2u(c.z), f2u(c.w));
+  p[3] = make_uint4((unsigned)d.x, (unsigned)d.y, (unsigned)d.z, (unsigned)d.w);
+  p[4] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// shuffleRays on a host-provided batch (parity path): route, advance, compact survivors; finished shadow rays -> fb
+__global__ void k_shuffle(FrameParams fp, SceneDev sd, RayQueue in, unsigned n, int from, RayQueue out) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Ray r;
+  int dummy;
+  queue_load(in, i, r, dummy);
+  float t;
+  int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, from, from == -1 && (fp.flags & FLAG_ENTER_INSIDE) != 0, t);
+  if (next >= 0) {
+    r.o = xadd(r.o, xmul(r.d, xmul(t, 0.95f)));
+    unsigned pos = queue_reserve(out.count);
+    if (pos < out.cap) queue_store(out, pos, r, next);
+  } else if (r.type == RAY_SHADOW && xlength(r.color) > 0.f) {
+    fb_add(sd.fb, r.id, xmul(r.color, r.w));
+  }
+}
+
+// ---- DomainScheduler exchange helpers (replace SendRays' pack/unpack, DomainTracer.h:370-496) ---------------
+__global__ void k_export_count(RayQueue ex, const Instance *inst, unsigned *peer_counts) {
+  unsigned n = min(*ex.count, ex.cap);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    atomicAdd(&peer_counts[inst[ex.inst[i]].owner], 1u);
+}
+// pack peer-major into [column][ray] (column stride = stride rays); peer_cursor starts at the exclusive offsets
+__global__ void k_export_pack(RayQueue ex, const Instance *inst, unsigned *peer_cursor, uint4 *packed, int *packed_inst, size_t stride) {
+  unsigned n = min(*ex.count, ex.cap);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int target = ex.inst[i];
+    unsigned pos = atomicAdd(&peer_cursor[inst[target].owner], 1u);
+    const uint4 *c0 = reinterpret_cast<const uint4 *>(ex.c0), *c1 = reinterpret_cast<const uint4 *>(ex.c1),
+                *c2 = reinterpret_cast<const uint4 *>(ex.c2), *c3 = reinterpret_cast<const uint4 *>(ex.c3);
+    packed[0 * stride + pos] = c0[i];
+    packed[1 * stride + pos] = c1[i];
+    packed[2 * stride + pos] = c2[i];
+    packed[3 * stride + pos] = c3[i];
+    packed_inst[pos] = target;
+  }
+}
+__global__ void k_import(const uint4 *packed, const int *packed_inst, size_t stride, unsigned n, RayQueue q, unsigned offset) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  reinterpret_cast<uint4 *>(q.c0)[offset + i] = packed[0 * stride + i];
+  reinterpret_cast<uint4 *>(q.c1)[offset + i] = packed[1 * stride + i];
+  reinterpret_cast<uint4 *>(q.c2)[offset + i] = packed[2 * stride + i];
+  reinterpret_cast<uint4 *>(q.c3)[offset + i] = packed[3 * stride + i];
+  q.inst[offset + i] = packed_inst[i];
+}
+
+} // namespace gvt

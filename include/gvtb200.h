@@ -1,0 +1,210 @@
+/* gvtb200.h -- C ABI of the B200-native GraviT render adapter (libgvtb200.so).
+ *
+ * This is the drop-in boundary for the ray-trace hot path of TACC/GraviT.  Every entry point names the
+ * reference interface it replaces (paths relative to /root/reference/src/gvt/render/).  Plain pointers and
+ * sizes only; no C++ or torch types.  All pointers are HOST pointers unless the name starts with d_.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative gvtb200_status; gvtb200_last_error() gives the text.
+ *     Nothing calls exit() (the reference's adapters exit(1)/GVT_ASSERT: EmbreeMeshAdapter.cpp:122,128).
+ *   - there is NO CPU fallback: if no CUDA device is usable gvtb200_init fails with GVTB200_ERR_NO_DEVICE.
+ *   - one in-flight call per handle; distinct handles may be used from distinct host threads.
+ */
+#ifndef GVTB200_H
+#define GVTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVTB200_API __attribute__((visibility("default")))
+
+typedef enum {
+  GVTB200_OK = 0,
+  GVTB200_ERR_NO_DEVICE = -1,
+  GVTB200_ERR_CUDA = -2,
+  GVTB200_ERR_INVALID = -3,
+  GVTB200_ERR_CAPACITY = -4,
+  GVTB200_ERR_OOM = -5
+} gvtb200_status;
+
+/* gvt::render::actor::Ray (actor/Ray.h:45-187): 64-byte payload `rats` (:68-79) inside a 16-aligned 68-byte
+ * union (:95) => sizeof(Ray) == 80.  RayVector (:189) is a contiguous array of these. */
+typedef struct gvtb200_ray {
+  float origin[3];
+  float t_min;
+  float direction[3];
+  float t_max;
+  float color[3];
+  float t;
+  int32_t id;    /* framebuffer index j*W+i */
+  int32_t depth; /* remaining bounces */
+  float w;
+  int32_t type; /* GVTB200_RAY_* == Ray::RayType (actor/Ray.h:50-55) */
+  uint8_t pad[16];
+} gvtb200_ray;
+
+enum { GVTB200_RAY_PRIMARY = 0, GVTB200_RAY_SHADOW = 1, GVTB200_RAY_SECONDARY = 2 };
+
+/* gvt::render::data::primitives::Material (data/primitives/Material.h:59-89), LAMBERT/PHONG/BLINN fields */
+typedef struct gvtb200_material {
+  int32_t type; /* 0 LAMBERT, 1 PHONG, 2 BLINN (Material.h:50-57) */
+  float kd[3];
+  float ks[3];
+  float alpha;
+} gvtb200_material;
+
+/* gvt::render::data::scene::{PointLight,AmbientLight,AreaLight} (data/scene/Light.h) */
+typedef struct gvtb200_light {
+  int32_t type; /* 0 point, 1 ambient, 2 area */
+  float position[3];
+  float color[3];
+  float normal[3];
+  float width, height;
+} gvtb200_light;
+
+enum {
+  GVTB200_FLAG_SMOOTH = 1,       /* interpolated vertex normals (the goldens); default = HEAD's FLAT_SHADING
+                                    (adapter/embree/EmbreeMeshAdapter.cpp:75,507-524) */
+  GVTB200_FLAG_ENTER_INSIDE = 2, /* documented deviation F6: camera rays whose origin is inside an instance box
+                                    enter it at t = 0 (reference drops them: actor/RayPacket.h:194) */
+};
+
+enum { GVTB200_SCHEDULE_IMAGE = 0, GVTB200_SCHEDULE_DOMAIN = 1 }; /* scheduler::ScheduleType (Types.h:48-62) */
+
+typedef struct gvtb200_mesh_s *gvtb200_mesh;
+typedef struct gvtb200_scene_s *gvtb200_scene;
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+/* replaces api::gvtInit (api/api.cpp:76-98) for the device side: selects the CUDA device, creates streams. */
+GVTB200_API int gvtb200_init(int device);
+GVTB200_API const char *gvtb200_last_error(void);
+GVTB200_API int gvtb200_device_info(int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor);
+
+/* ---- B1: the engine adapter (Adapter.h:44-88) --------------------------------------------------------- */
+/* replaces EmbreeMeshAdapter::EmbreeMeshAdapter (adapter/embree/EmbreeMeshAdapter.cpp:125-162): takes the
+ * Mesh the host already holds (vertices, 0-based faces AFTER Mesh::addFace's filter, Mesh.cpp:102-112; vertex
+ * normals from Mesh::generateNormals, :116-154, or NULL for flat-only) and builds the BLAS on the GPU
+ * (Morton codes -> radix sort -> LBVH -> 8-wide compressed BVH).  face_mat (index into mats, or -1) and
+ * vcolors (per vertex) may be NULL (EmbreeMeshAdapter.cpp:536-569 picks vertex colour > face material > mesh). */
+GVTB200_API int gvtb200_mesh_create(const float *vertices, uint32_t n_vertices, const uint32_t *faces0, uint32_t n_faces,
+                                    const float *vertex_normals, const gvtb200_material *mesh_material,
+                                    const gvtb200_material *mats, uint32_t n_mats, const int32_t *face_mat,
+                                    const float *vcolors, gvtb200_mesh *out);
+GVTB200_API int gvtb200_mesh_destroy(gvtb200_mesh mesh);
+/* parity hooks for the BLAS build: Morton key per face (input order), the sorted face order, build stats
+ * {n_wide_nodes, n_tris, max_depth, build_us} */
+GVTB200_API int gvtb200_mesh_morton(gvtb200_mesh mesh, uint32_t *codes, uint32_t *sorted_faces);
+GVTB200_API int gvtb200_mesh_stats(gvtb200_mesh mesh, uint64_t stats[4]);
+
+/* replaces Adapter::trace (Adapter.h:82-84) == EmbreeMeshAdapter::trace (EmbreeMeshAdapter.cpp:625-660):
+ * rays[begin,end) are traced against ONE instance of the mesh (m/minv column-major mat4, normi column-major
+ * mat3, as glm::value_ptr gives them), mutated in place (bounces), and the outgoing rays -- non-shadow rays
+ * that missed, and unoccluded shadow rays carrying their shaded colour -- are APPENDED to moved[*n_moved ..].
+ * end == 0 means n_rays (EmbreeMeshAdapter.cpp:642).  GVTB200_ERR_CAPACITY if moved_cap is too small. */
+GVTB200_API int gvtb200_trace(gvtb200_mesh mesh, gvtb200_ray *rays, size_t n_rays, size_t begin, size_t end,
+                              gvtb200_ray *moved, size_t moved_cap, size_t *n_moved, const float m[16],
+                              const float minv[16], const float normi[9], const gvtb200_light *lights, int n_lights,
+                              uint32_t flags, uint32_t seed);
+
+/* closest-hit / any-hit queries in mesh-local space (what rtcIntersect8 / rtcOccluded8 return,
+ * EmbreeMeshAdapter.cpp:474,375): prim = -1 on miss.  Test hook for hit-record parity. */
+typedef struct gvtb200_hit {
+  int32_t prim;
+  float t, u, v;
+} gvtb200_hit;
+GVTB200_API int gvtb200_intersect(gvtb200_mesh mesh, const gvtb200_ray *rays, size_t n, gvtb200_hit *hits);
+GVTB200_API int gvtb200_occluded(gvtb200_mesh mesh, const gvtb200_ray *rays, size_t n, int32_t *occluded);
+
+/* ---- B2: scene / frame (api/api.h:26-263, Renderer.cpp:37-115, algorithm/*.h) -------------------------- */
+GVTB200_API int gvtb200_scene_create(gvtb200_scene *out);
+GVTB200_API int gvtb200_scene_destroy(gvtb200_scene scene);
+/* api::addInstance (api/api.cpp:292-322): the host passes what it stored in the context DB -- mat, matinv,
+ * normi and the instance box (two transformed corners, :309-312).  Returns the instance id (creation order,
+ * which is what BVH::BVH assigns, data/accel/BVH.cpp:48-51). */
+GVTB200_API int gvtb200_scene_add_instance(gvtb200_scene scene, gvtb200_mesh mesh, const float m[16], const float minv[16],
+                                           const float normi[9], const float box_min[3], const float box_max[3]);
+/* api::addPointLight / addAreaLight (api/api.cpp:329-372) */
+GVTB200_API int gvtb200_scene_set_lights(gvtb200_scene scene, const gvtb200_light *lights, int n_lights);
+/* api::addCamera (api/api.cpp:418-440) + gvtCameraBase::buildTransform (data/scene/gvtCamera.cpp:89-171) */
+GVTB200_API int gvtb200_scene_set_camera(gvtb200_scene scene, const float eye[3], const float focus[3], const float up[3],
+                                         float fov, int depth, int samples, float jitter);
+/* api::addFilm (api/api.cpp:457-468) */
+GVTB200_API int gvtb200_scene_set_film(gvtb200_scene scene, int width, int height);
+GVTB200_API int gvtb200_scene_set_flags(gvtb200_scene scene, uint32_t flags, uint32_t seed);
+/* AbstractTrace::Initialize (algorithm/TracerBase.h:247-308): builds the top-level instance BVH exactly as
+ * data/accel/BVH.cpp:44-216 does (same split search, same std::partition) and uploads it. */
+GVTB200_API int gvtb200_scene_commit(gvtb200_scene scene);
+/* parity hooks: instanceSetID order after the build (BVH.cpp:60-66) */
+GVTB200_API int gvtb200_scene_tlas_order(gvtb200_scene scene, int32_t *sorted_ids, int *n);
+
+/* gvtPerspectiveCamera::generateRays (data/scene/gvtCamera.cpp:233-312): all W*H*samples^2 rays, ray-index order */
+GVTB200_API int gvtb200_camera_rays(gvtb200_scene scene, gvtb200_ray *out, size_t cap);
+/* BVH::intersect<8> (data/accel/BVH.h:61-135): next instance + box-entry t per ray; `from` is excluded */
+GVTB200_API int gvtb200_route(gvtb200_scene scene, const gvtb200_ray *rays, size_t n, int from, int32_t *next, float *t);
+/* AbstractTrace::shuffleRays (algorithm/TracerBase.h:325-414, non-volume branch): routes `rays`, advances the
+ * origin of rays that enter an instance (:394) and returns them grouped by instance in out (out_inst[i] = next
+ * instance of out[i]); finished shadow rays are accumulated into the scene framebuffer (:396-399). */
+GVTB200_API int gvtb200_shuffle(gvtb200_scene scene, const gvtb200_ray *rays, size_t n, int from, gvtb200_ray *out,
+                                int32_t *out_inst, size_t cap, size_t *n_out);
+/* IceTComposite::reset / colorbf (composite/IceTComposite.cpp:79-82, IceTComposite.h:106) */
+GVTB200_API int gvtb200_framebuffer_clear(gvtb200_scene scene);
+GVTB200_API int gvtb200_framebuffer_read(gvtb200_scene scene, float *rgba, size_t n_floats);
+
+/* Tracer<ImageScheduler>::operator() (algorithm/ImageTracer.h:127-269) + gvtRenderer::render (Renderer.cpp:106-115)
+ * for pixel rows [row0,row1) -- the whole frame stays on the device: camera rays, routing, two-level traversal,
+ * shading, shadow rays, bounces, framebuffer.  rgba_out (W*H*4 floats) may be NULL to leave the result on the
+ * device.  counters (may be NULL) receives gvtb200_counters. */
+typedef struct gvtb200_counters {
+  uint64_t camera_rays;      /* generated */
+  uint64_t routed_initial;   /* camera rays that entered an instance */
+  uint64_t primary_hits;     /* primary + secondary closest hits shaded */
+  uint64_t shadow_generated; /* shadow rays traced */
+  uint64_t shadow_unoccluded;
+  uint64_t secondary_generated;
+  uint64_t fb_adds;
+  uint64_t instance_visits; /* (ray, instance) pairs traced == sum of the reference's queue sizes */
+  uint64_t nodes_visited;   /* only when profiling counters are enabled */
+  uint64_t tris_tested;
+  uint64_t rays_exported; /* domain scheduler: rays handed to other ranks */
+  uint64_t reserved;
+} gvtb200_counters;
+GVTB200_API int gvtb200_render_frame(gvtb200_scene scene, int row0, int row1, float *rgba_out, gvtb200_counters *counters);
+/* same, asynchronous on the scene's stream, nothing copied back (bench / multi-GPU drivers) */
+GVTB200_API int gvtb200_render_frame_async(gvtb200_scene scene, int row0, int row1);
+GVTB200_API int gvtb200_scene_sync(gvtb200_scene scene);
+GVTB200_API int gvtb200_scene_counters(gvtb200_scene scene, gvtb200_counters *out);
+GVTB200_API int gvtb200_scene_profile_counters(gvtb200_scene scene, int enable);
+/* device pointer of the RGBA float framebuffer (W*H*4) and the CUDA stream the scene launches on, so that
+ * the multi-GPU drivers can hand them to NCCL (replaces icetCompositeImage, composite/IceTComposite.cpp:96) */
+GVTB200_API int gvtb200_scene_device_framebuffer(gvtb200_scene scene, void **d_rgba, void **cuda_stream);
+/* final clamp after a cross-GPU sum (localAdd's clamp, composite/IceTComposite.cpp:113-114) */
+GVTB200_API int gvtb200_framebuffer_clamp(gvtb200_scene scene);
+/* elapsed GPU time (ms) of the last render_frame[_async] on this scene, measured with CUDA events on the
+ * scene's stream; kernel_ms[3] = {camera+route, closest-hit trace, shadow trace} of the last wave */
+GVTB200_API int gvtb200_scene_last_timing(gvtb200_scene scene, float *frame_ms, float kernel_ms[3]);
+
+/* ---- Tracer<DomainScheduler> (algorithm/DomainTracer.h:115-496) ---------------------------------------- */
+/* mpiInstanceMap (DomainTracer.h:115-144): owner rank of every instance; meshes of instances this rank does not
+ * own may be NULL in gvtb200_scene_add_instance. */
+GVTB200_API int gvtb200_domain_set_owner(gvtb200_scene scene, const int32_t *owner, int n_instances, int rank, int world_size);
+/* FilterRaysLocally/shuffleDropRays (:148-181) then the local drain loop (:222-324) until every local queue is
+ * empty.  Rays bound for instances owned by other ranks are parked in per-peer export queues. */
+GVTB200_API int gvtb200_domain_begin_frame(gvtb200_scene scene);
+GVTB200_API int gvtb200_domain_drain_local(gvtb200_scene scene);
+/* SendRays phase 1 (:409-415): counts[p] = rays parked for rank p.  phase 2 (:433-463): the rays for all peers
+ * packed peer-major as 5 SoA columns (4 x 16 B + next-instance id) in one device buffer laid out
+ * [column][ray]; *d_export points at it, column stride = *stride_rays rays. */
+GVTB200_API int gvtb200_domain_export(gvtb200_scene scene, uint32_t *counts, void **d_export, size_t *stride_rays);
+/* unpack n_rays received rays (same layout, column stride stride_rays) into the local queues */
+GVTB200_API int gvtb200_domain_import(gvtb200_scene scene, const void *d_rays, size_t n_rays, size_t stride_rays);
+/* rays still queued locally (termination test, DomainTracer.h:339-349) */
+GVTB200_API int gvtb200_domain_pending(gvtb200_scene scene, uint64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVTB200_H */
