@@ -34,6 +34,10 @@ struct BuildCtx {
   unsigned wnode_cap;
 };
 
+// absolute padding of the leaf boxes: the canonical triangle test is evaluated in fp32, so a ray can be accepted while
+// passing a few ulp (of the ray-origin-to-triangle distance) outside the exact triangle; the boxes must not cull it
+GVT_HD float blas_leaf_pad(V3 mext) { return 4e-6f * (mext.x + mext.y + mext.z) + 1e-30f; }
+
 GVT_HD uint32_t expand_bits10(uint32_t v) {
   v = (v * 0x00010001u) & 0xFF0000FFu;
   v = (v * 0x00000101u) & 0x0F00F00Fu;

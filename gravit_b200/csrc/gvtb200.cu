@@ -1,0 +1,1261 @@
+// gvtb200.cu -- the C ABI (include/gvtb200.h) over the sm_100a kernels.  Host logic only: device memory, launch
+// order, the top-level instance BVH build (a restatement of data/accel/BVH.cpp, it is O(instances) setup work) and
+// the camera basis (gvtCamera.cpp:89-171).  There is NO CPU ray-tracing path in this library.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gvtb200.h"
+#include "kernels.cuh"
+
+using namespace gvt;
+
+static_assert(sizeof(gvtb200_ray) == 80, "gvtb200_ray must match gvt::render::actor::Ray (80 bytes)");
+
+namespace {
+
+thread_local std::string t_err;
+int g_device = -1;
+int g_sms = 0;
+int g_trace_blocks_per_sm[2] = { 0, 0 };
+unsigned long long g_launches = 0; // kernels launched by this library (bench.py reports it)
+#define LAUNCHED(n) (g_launches += (n))
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_err = buf;
+  return code;
+}
+#define CU(expr)                                                                                                         \
+  do {                                                                                                                   \
+    cudaError_t e__ = (expr);                                                                                            \
+    if (e__ != cudaSuccess)                                                                                              \
+      return fail(e__ == cudaErrorMemoryAllocation ? GVTB200_ERR_OOM : GVTB200_ERR_CUDA, "%s:%d %s: %s", __FILE__,     \
+                  __LINE__, #expr, cudaGetErrorString(e__));                                                             \
+  } while (0)
+#define NEED_INIT()                                                                                                      \
+  do {                                                                                                                   \
+    if (g_device < 0) return fail(GVTB200_ERR_NO_DEVICE, "gvtb200_init has not succeeded: no CUDA device (no CPU fallback)"); \
+  } while (0)
+
+inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)std::max<size_t>(1, (n + threads - 1) / threads); }
+
+template <class T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)); }
+template <class T> void dfree(T *&p) {
+  if (p) cudaFree((void *)p);
+  p = nullptr;
+}
+
+// ---- SoA ray queue storage --------------------------------------------------------------------------------
+struct QueueMem {
+  RayQueue q;
+  void *slab = nullptr;
+  QueueMem() { memset(&q, 0, sizeof(q)); }
+  cudaError_t ensure(size_t cap) {
+    if (cap < 32) cap = 32;
+    if (slab && q.cap >= cap) return cudaSuccess;
+    release();
+    size_t bytes = cap * 68 + 256;
+    cudaError_t e = cudaMalloc(&slab, bytes);
+    if (e != cudaSuccess) {
+      slab = nullptr;
+      return e;
+    }
+    char *p = (char *)slab;
+    q.count = (unsigned *)p, p += 256;
+    q.c0 = (float4 *)p, p += cap * 16;
+    q.c1 = (float4 *)p, p += cap * 16;
+    q.c2 = (float4 *)p, p += cap * 16;
+    q.c3 = (int4 *)p, p += cap * 16;
+    q.inst = (int *)p;
+    q.cap = (unsigned)cap;
+    return cudaMemset(q.count, 0, 256);
+  }
+  void release() {
+    if (slab) cudaFree(slab);
+    slab = nullptr;
+    memset(&q, 0, sizeof(q));
+  }
+};
+
+// Box3D helpers in the reference's operation order (data/primitives/BBox.cpp:33-133)
+struct HBox {
+  float lo[3], hi[3];
+  HBox() {
+    for (int i = 0; i < 3; ++i) lo[i] = FLT_MAX, hi[i] = -FLT_MAX;
+  }
+  void merge(const HBox &o) { // BBox.cpp:55-63
+    for (int i = 0; i < 3; ++i) lo[i] = fastmin(o.lo[i], lo[i]), hi[i] = fastmax(o.hi[i], hi[i]);
+  }
+  int wideRangingBoxDir() const { // BBox.cpp:118-126
+    float dx = xsub(hi[0], lo[0]), dy = xsub(hi[1], lo[1]), dz = xsub(hi[2], lo[2]);
+    if (dx > dy && dx > dz) return 0;
+    if (dy > dz) return 1;
+    return 2;
+  }
+  float centroid(int a) const { return xadd(xmul(lo[a], 0.5f), xmul(hi[a], 0.5f)); } // BBox.cpp:128
+  float surfaceArea() const {                                                         // BBox.cpp:130-133
+    float dx = xsub(hi[0], lo[0]), dy = xsub(hi[1], lo[1]), dz = xsub(hi[2], lo[2]);
+    return xmul(2.f, xadd(xadd(xmul(dx, dy), xmul(dy, dz)), xmul(dz, dx)));
+  }
+};
+
+} // namespace
+
+// =============================================================================================================
+// handles
+// =============================================================================================================
+struct gvtb200_mesh_s {
+  unsigned nv = 0, nf = 0;
+  float4 *d_nodes = nullptr, *d_tris = nullptr, *d_normals = nullptr, *d_vcolors = nullptr, *d_mats = nullptr;
+  int4 *d_faces = nullptr;
+  uint32_t *d_keys_unsorted = nullptr, *d_sorted_faces = nullptr;
+  Blas blas;
+  uint64_t stats[4] = { 0, 0, 0, 0 };
+  // adapter-mode (B1) working set, created on first use
+  cudaStream_t stream = nullptr;
+  Instance *d_inst = nullptr;
+  Blas *d_blas = nullptr;
+  DevCounters *d_ctr = nullptr;
+  unsigned *d_work = nullptr;
+  uint4 *d_aos = nullptr;
+  size_t aos_cap = 0;
+  QueueMem q_in, q_nx, q_sh, q_mv, q_fin;
+  int4 *d_hits = nullptr;
+  size_t hits_cap = 0;
+};
+
+namespace {
+struct InstHost {
+  gvtb200_mesh mesh;
+  float m[16], minv[16], normi[9];
+  HBox box;
+  float centroid[3];
+  int owner;
+};
+struct TNodeHost {
+  HBox bbox;
+  int left = -1, right = -1, first = 0, count = 0;
+};
+} // namespace
+
+struct gvtb200_scene_s {
+  std::vector<InstHost> inst;
+  std::vector<gvtb200_light> lights;
+  float eye[3] = { 0, 0, 1 }, focus[3] = { 0, 0, 0 }, up[3] = { 0, 1, 0 };
+  float fov = 0.785398f;
+  int depth = 1, samples = 1, jitter_window = 0;
+  int W = 512, H = 512;
+  uint32_t flags = 0, seed = 0;
+  int rank = 0, world = 1;
+  bool committed = false, profile = false;
+  // TLAS
+  std::vector<TNodeHost> tnodes;
+  std::vector<int> work, sorted_ids;
+  // device
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+  Instance *d_inst = nullptr;
+  Blas *d_blas = nullptr;
+  float4 *d_tnodes = nullptr, *d_tboxes = nullptr;
+  Tlas tlas;
+  float *d_fb = nullptr;
+  size_t fb_pix = 0;
+  DevCounters *d_ctr = nullptr;
+  unsigned *d_work = nullptr, *d_peer = nullptr;
+  QueueMem q_a, q_b, q_sh, q_ex, q_tmp;
+  uint4 *d_export = nullptr;
+  size_t export_cap = 0;
+  int *d_next = nullptr;
+  float *d_t = nullptr;
+  uint4 *d_aos = nullptr;
+  size_t aos_cap = 0, route_cap = 0;
+  float last_frame_ms = 0.f, last_kernel_ms[3] = { 0, 0, 0 };
+  bool timing_valid = false;
+};
+
+namespace {
+
+// ---- device-wide scan (used by the radix sort) -------------------------------------------------------------
+int scan_inplace(unsigned *d, size_t n, std::vector<unsigned *> &levels, size_t level, cudaStream_t st) {
+  unsigned tiles = blocks_for(n, RS_TILE);
+  if (tiles == 1) {
+    k_scan_tile<<<1, RS_THREADS, 0, st>>>(d, (unsigned)n, nullptr);
+    return 0;
+  }
+  if (levels.size() <= level) {
+    unsigned *p = nullptr;
+    if (dalloc(&p, tiles) != cudaSuccess) return -1;
+    levels.push_back(p);
+  }
+  unsigned *sums = levels[level];
+  k_scan_tile<<<tiles, RS_THREADS, 0, st>>>(d, (unsigned)n, sums);
+  if (scan_inplace(sums, tiles, levels, level + 1, st)) return -1;
+  k_scan_add<<<tiles, RS_THREADS, 0, st>>>(d, (unsigned)n, sums);
+  return 0;
+}
+
+int trace_grid(bool count) {
+  int idx = count ? 1 : 0;
+  if (!g_trace_blocks_per_sm[idx]) {
+    int nb = 0;
+    if (count)
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true>, 128, 0);
+    else
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false>, 128, 0);
+    g_trace_blocks_per_sm[idx] = std::max(1, nb);
+  }
+  return g_sms * g_trace_blocks_per_sm[idx];
+}
+
+void launch_trace(bool count, const FrameParams &fp, const SceneDev &sd, const TraceQueues &tq, int mode, cudaStream_t st) {
+  int grid = trace_grid(count);
+  LAUNCHED(1);
+  if (count)
+    k_trace<true><<<grid, 128, 0, st>>>(fp, sd, tq, mode);
+  else
+    k_trace<false><<<grid, 128, 0, st>>>(fp, sd, tq, mode);
+}
+
+RayQueue null_queue(unsigned *count) {
+  RayQueue q;
+  memset(&q, 0, sizeof(q));
+  q.count = count; // cap 0: every append is counted and discarded
+  return q;
+}
+
+void pack_instance(Instance &d, const float minv[16], const float normi[9], int mesh, int owner) {
+  // column-major inputs: element (row r, col c) = a[4*c + r]
+  d.minv0 = make_float4(minv[0], minv[4], minv[8], minv[12]);
+  d.minv1 = make_float4(minv[1], minv[5], minv[9], minv[13]);
+  d.minv2 = make_float4(minv[2], minv[6], minv[10], minv[14]);
+  d.n0 = make_float4(normi[0], normi[3], normi[6], 0.f);
+  d.n1 = make_float4(normi[1], normi[4], normi[7], 0.f);
+  d.n2 = make_float4(normi[2], normi[5], normi[8], 0.f);
+  d.mesh = mesh, d.owner = owner, d.pad0 = d.pad1 = 0;
+}
+
+void pack_lights(FrameParams &fp, const gvtb200_light *lights, int n) {
+  fp.n_lights = n;
+  for (int i = 0; i < n; ++i) {
+    Light &L = fp.lights[i];
+    L.type = lights[i].type;
+    L.pos = v3(lights[i].position[0], lights[i].position[1], lights[i].position[2]);
+    L.color = v3(lights[i].color[0], lights[i].color[1], lights[i].color[2]);
+    L.normal = v3(lights[i].normal[0], lights[i].normal[1], lights[i].normal[2]);
+    L.width = lights[i].width, L.height = lights[i].height;
+  }
+}
+
+// gvtCameraBase::buildTransform (data/scene/gvtCamera.cpp:89-171, RIGHT_HAND_CAMERA gvtCamera.h:46) and the
+// per-frame constants of gvtPerspectiveCamera::generateRays (:233-260)
+void build_camera(const gvtb200_scene_s &s, Camera &c) {
+  V3 eye = v3(s.eye[0], s.eye[1], s.eye[2]), focus = v3(s.focus[0], s.focus[1], s.focus[2]), up = v3(s.up[0], s.up[1], s.up[2]);
+  V3 w = xnormalize(xsub(focus, eye));
+  V3 v = xnormalize(up);
+  V3 u;
+  u.x = xsub(xmul(w.y, v.z), xmul(w.z, v.y));
+  u.y = xsub(xmul(w.z, v.x), xmul(w.x, v.z));
+  u.z = xsub(xmul(w.x, v.y), xmul(w.y, v.x));
+  u = xnormalize(u);
+  V3 upv;
+  upv.x = xsub(xmul(u.y, w.z), xmul(w.y, u.z));
+  upv.y = xsub(xmul(u.z, w.x), xmul(w.z, u.x));
+  upv.z = xsub(xmul(u.x, w.y), xmul(w.x, u.y));
+  v = xnormalize(upv);
+  c.eye = eye, c.u = u, c.v = v, c.w = w;
+  float aspect = xdiv((float)s.W, (float)s.H);
+  c.vert = tanf((float)((double)s.fov * 0.5));
+  c.horz = xmul(tanf((float)((double)s.fov * 0.5)), aspect);
+  const float divider = (float)s.samples;
+  c.offset = (float)((1.0 / (double)divider) * (double)s.jitter_window);
+  c.wmult = xdiv(2.f, (float)(s.W - 1));
+  c.hmult = xdiv(2.f, (float)(s.H - 1));
+  c.half_sample = xmul((float)s.samples, 0.5f);
+  c.contri = xdiv(1.f, (float)(s.samples * s.samples));
+  c.W = s.W, c.H = s.H, c.samples = s.samples, c.depth = s.depth;
+}
+
+void build_frame_params(const gvtb200_scene_s &s, FrameParams &fp) {
+  memset(&fp, 0, sizeof(fp));
+  build_camera(s, fp.cam);
+  pack_lights(fp, s.lights.data(), (int)s.lights.size());
+  fp.flags = s.flags, fp.seed = s.seed, fp.rank = s.rank, fp.world = s.world;
+}
+
+SceneDev scene_dev(const gvtb200_scene_s &s) {
+  SceneDev sd;
+  sd.tlas = s.tlas;
+  sd.inst = s.d_inst;
+  sd.blas = s.d_blas;
+  sd.fb = s.d_fb;
+  sd.ctr = s.d_ctr;
+  return sd;
+}
+
+int upload_rays(const gvtb200_ray *rays, size_t n, uint4 *&d_aos, size_t &aos_cap, QueueMem &q, int inst_or_slot_mode, cudaStream_t st) {
+  // inst_or_slot_mode: >= -1 -> constant inst column; -2 -> inst column = slot index
+  if (aos_cap < n) {
+    dfree(d_aos);
+    CU(dalloc(&d_aos, 5 * n));
+    aos_cap = n;
+  }
+  CU(q.ensure(n));
+  CU(cudaMemcpyAsync(d_aos, rays, n * sizeof(gvtb200_ray), cudaMemcpyHostToDevice, st));
+  if (n) k_aos_to_soa<<<blocks_for(n, 256), 256, 0, st>>>(d_aos, (unsigned)n, q.q, 0u, inst_or_slot_mode);
+  unsigned cnt = (unsigned)n;
+  CU(cudaMemcpyAsync(q.q.count, &cnt, 4, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+// ---- top-level BVH: data/accel/BVH.cpp:44-216 -------------------------------------------------------------------
+float tlas_find_split(gvtb200_scene_s &s, int axis, int start, int end) { // BVH.cpp:173-216
+  float minCost = FLT_MAX, splitPoint = 0.f;
+  for (int i = start; i < end; ++i) {
+    const HBox &ref = s.inst[s.work[i]].box;
+    for (int e = 0; e < 2; ++e) {
+      float edge = e == 0 ? ref.lo[axis] : ref.hi[axis];
+      HBox lb, rb;
+      int lc = 0;
+      for (int j = start; j < end; ++j) {
+        const HBox &bb = s.inst[s.work[j]].box;
+        if (bb.centroid(axis) < edge) {
+          ++lc;
+          lb.merge(bb);
+        } else
+          rb.merge(bb);
+      }
+      int rc = end - start - lc;
+      // TRAVERSAL_COST is the double literal 0.5 (BVH.cpp:39): the sum is formed in double, then rounded to float
+      float la = xmul(lb.surfaceArea(), (float)lc), ra = xmul(rb.surfaceArea(), (float)rc);
+      float cost = (float)(0.5 + (double)la + (double)ra);
+      if (cost < minCost) minCost = cost, splitPoint = edge;
+    }
+  }
+  return splitPoint;
+}
+int tlas_build(gvtb200_scene_s &s, int start, int end) { // BVH.cpp:77-171
+  int id = (int)s.tnodes.size();
+  s.tnodes.push_back(TNodeHost());
+  HBox bbox;
+  for (int i = start; i < end; ++i) bbox.merge(s.inst[s.work[i]].box);
+  int count = end - start;
+  auto leaf = [&]() {
+    s.tnodes[id].bbox = bbox;
+    s.tnodes[id].first = (int)s.sorted_ids.size();
+    s.tnodes[id].count = count;
+    for (int i = start; i < end; ++i) s.sorted_ids.push_back(s.work[i]);
+    return id;
+  };
+  if (count <= 1) return leaf(); // LEAF_SIZE 1 (:40,95)
+  int axis = bbox.wideRangingBoxDir();
+  float split = tlas_find_split(s, axis, start, end);
+  auto bound = std::partition(s.work.begin() + start, s.work.begin() + end,
+                              [&](int k) { return s.inst[k].centroid[axis] < split; }); // :139-140, BVH.h:160-172
+  int mid = (int)(bound - s.work.begin());
+  if (mid == start || mid == end) return leaf(); // :144
+  int l = tlas_build(s, start, mid);
+  int r = tlas_build(s, mid, end);
+  s.tnodes[id].left = l, s.tnodes[id].right = r, s.tnodes[id].bbox = bbox, s.tnodes[id].count = 0;
+  return id;
+}
+int tlas_depth(const gvtb200_scene_s &s, int n) {
+  if (s.tnodes[n].left < 0) return 1;
+  return 1 + std::max(tlas_depth(s, s.tnodes[n].left), tlas_depth(s, s.tnodes[n].right));
+}
+
+} // namespace
+
+// =============================================================================================================
+// library
+// =============================================================================================================
+extern "C" {
+
+int gvtb200_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_device = -1;
+    return fail(GVTB200_ERR_NO_DEVICE, "no CUDA device: %s (this library has no CPU fallback)",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device < 0 || device >= n) return fail(GVTB200_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp p;
+  CU(cudaGetDeviceProperties(&p, device));
+  if (p.major < 10) return fail(GVTB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+  g_sms = p.multiProcessorCount;
+  g_device = device;
+  g_trace_blocks_per_sm[0] = g_trace_blocks_per_sm[1] = 0;
+  CU(cudaFree(0));
+  return GVTB200_OK;
+}
+
+const char *gvtb200_last_error(void) { return t_err.c_str(); }
+
+int gvtb200_device_info(int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor) {
+  NEED_INIT();
+  cudaDeviceProp p;
+  CU(cudaGetDeviceProperties(&p, g_device));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (hbm_bytes) *hbm_bytes = p.totalGlobalMem;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return GVTB200_OK;
+}
+
+// =============================================================================================================
+// B1: mesh / BLAS
+// =============================================================================================================
+int gvtb200_mesh_destroy(gvtb200_mesh m) {
+  if (!m) return GVTB200_OK;
+  dfree(m->d_nodes), dfree(m->d_tris), dfree(m->d_normals), dfree(m->d_vcolors), dfree(m->d_mats), dfree(m->d_faces);
+  dfree(m->d_keys_unsorted), dfree(m->d_sorted_faces);
+  dfree(m->d_inst), dfree(m->d_blas), dfree(m->d_ctr), dfree(m->d_work), dfree(m->d_aos), dfree(m->d_hits);
+  m->q_in.release(), m->q_nx.release(), m->q_sh.release(), m->q_mv.release(), m->q_fin.release();
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+  return GVTB200_OK;
+}
+
+static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const uint32_t *faces0, uint32_t nf) {
+  cudaStream_t st = m->stream;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  float *d_verts = nullptr;
+  uint32_t *d_faces3 = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_keys2 = nullptr, *d_vals2 = nullptr;
+  unsigned *d_hist = nullptr, *d_flag = nullptr, *d_counts = nullptr;
+  float4 *bn_lo = nullptr, *bn_hi = nullptr, *wnodes = nullptr;
+  int2 *bn_child = nullptr, *bn_range = nullptr;
+  int *bn_parent = nullptr;
+  CollapseTask *d_ta = nullptr, *d_tb = nullptr;
+  std::vector<unsigned *> scan_levels;
+  int rc = GVTB200_OK;
+  auto cleanup = [&]() {
+    dfree(d_verts), dfree(d_faces3), dfree(d_keys), dfree(d_vals), dfree(d_keys2), dfree(d_vals2), dfree(d_hist), dfree(d_flag);
+    dfree(d_counts), dfree(bn_lo), dfree(bn_hi), dfree(wnodes), dfree(bn_child), dfree(bn_range), dfree(bn_parent), dfree(d_ta), dfree(d_tb);
+    for (auto *p : scan_levels) cudaFree(p);
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+  };
+#define CUB(expr)                                                                                                        \
+  do {                                                                                                                   \
+    cudaError_t e__ = (expr);                                                                                            \
+    if (e__ != cudaSuccess) {                                                                                            \
+      rc = fail(e__ == cudaErrorMemoryAllocation ? GVTB200_ERR_OOM : GVTB200_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, \
+                #expr, cudaGetErrorString(e__));                                                                         \
+      cleanup();                                                                                                         \
+      return rc;                                                                                                         \
+    }                                                                                                                    \
+  } while (0)
+
+  const size_t n = nf;
+  CUB(dalloc(&d_verts, 3 * (size_t)nv));
+  CUB(dalloc(&d_faces3, 3 * n));
+  CUB(cudaMemcpyAsync(d_verts, vertices, 3 * (size_t)nv * 4, cudaMemcpyHostToDevice, st));
+  CUB(cudaMemcpyAsync(d_faces3, faces0, 3 * n * 4, cudaMemcpyHostToDevice, st));
+  // mesh bounds in Mesh::computeBoundingBox order (data/primitives/Mesh.cpp:186-199); min/max are exact
+  V3 lo = v3(FLT_MAX, FLT_MAX, FLT_MAX), hi = v3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+  for (uint32_t i = 0; i < nv; ++i) {
+    lo.x = fastmin(lo.x, vertices[3 * i]), lo.y = fastmin(lo.y, vertices[3 * i + 1]), lo.z = fastmin(lo.z, vertices[3 * i + 2]);
+    hi.x = fastmax(hi.x, vertices[3 * i]), hi.y = fastmax(hi.y, vertices[3 * i + 1]), hi.z = fastmax(hi.z, vertices[3 * i + 2]);
+  }
+  BuildCtx c;
+  memset(&c, 0, sizeof(c));
+  c.verts = d_verts, c.faces = d_faces3, c.n = nf;
+  c.mlo = lo, c.mext = xsub(hi, lo);
+  c.pad = blas_leaf_pad(c.mext);
+  CUB(dalloc(&d_keys, n)); CUB(dalloc(&d_vals, n)); CUB(dalloc(&d_keys2, n)); CUB(dalloc(&d_vals2, n));
+  CUB(dalloc(&m->d_keys_unsorted, n)); CUB(dalloc(&m->d_sorted_faces, n));
+  CUB(dalloc(&d_counts, 4));
+  CUB(cudaEventRecord(e0, st));
+  unsigned max_depth = 0, n_wnodes = 1, n_wtris = 0;
+  if (nf > 0) {
+    c.keys = d_keys, c.vals = d_vals;
+    k_tri_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
+    CUB(cudaMemcpyAsync(m->d_keys_unsorted, d_keys, n * 4, cudaMemcpyDeviceToDevice, st));
+    // LSD radix sort, 4 x 8 bits, stable
+    unsigned nblocks = blocks_for(n, RS_TILE);
+    CUB(dalloc(&d_hist, 256 * (size_t)nblocks));
+    uint32_t *ka = d_keys, *va = d_vals, *kb = d_keys2, *vb = d_vals2;
+    for (int pass = 0; pass < 4; ++pass) {
+      k_rs_hist<<<nblocks, RS_THREADS, 0, st>>>(ka, nf, 8 * pass, d_hist, nblocks);
+      if (scan_inplace(d_hist, 256 * (size_t)nblocks, scan_levels, 0, st)) CUB(cudaErrorMemoryAllocation);
+      k_rs_scatter<<<nblocks, RS_THREADS, 0, st>>>(ka, va, kb, vb, nf, 8 * pass, d_hist, nblocks);
+      std::swap(ka, kb), std::swap(va, vb);
+    }
+    c.keys = ka, c.vals = va; // 4 passes: back in d_keys / d_vals
+    CUB(cudaMemcpyAsync(m->d_sorted_faces, va, n * 4, cudaMemcpyDeviceToDevice, st));
+    // binary radix tree + bottom-up fit
+    CUB(dalloc(&bn_lo, 2 * n)); CUB(dalloc(&bn_hi, 2 * n)); CUB(dalloc(&bn_child, n)); CUB(dalloc(&bn_range, n));
+    CUB(dalloc(&bn_parent, 2 * n)); CUB(dalloc(&d_flag, n));
+    CUB(cudaMemsetAsync(d_flag, 0, n * 4, st));
+    CUB(cudaMemsetAsync(bn_parent, 0xFF, 2 * n * 4, st));
+    c.bn_lo = bn_lo, c.bn_hi = bn_hi, c.bn_child = bn_child, c.bn_range = bn_range, c.bn_parent = bn_parent, c.bn_flag = d_flag;
+    k_leaf_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
+    if (nf > 1) {
+      k_karras<<<blocks_for(n, 256), 256, 0, st>>>(c);
+      k_refit<<<blocks_for(n, 256), 256, 0, st>>>(c);
+    }
+    // collapse into 8-wide compressed nodes, one level per launch
+    CUB(dalloc(&wnodes, 5 * n));
+    CUB(dalloc(&m->d_tris, 3 * n));
+    CUB(dalloc(&d_ta, n)); CUB(dalloc(&d_tb, n));
+    c.wnodes = wnodes, c.wtris = m->d_tris, c.node_count = d_counts, c.tri_count = d_counts + 1, c.wnode_cap = nf;
+    unsigned init[4] = { 1u, 0u, 0u, 0u };
+    CUB(cudaMemcpyAsync(d_counts, init, 16, cudaMemcpyHostToDevice, st));
+    CollapseTask root;
+    root.bnode = 0, root.wnode = 0;
+    CUB(cudaMemcpyAsync(d_ta, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+    unsigned cur = 1;
+    while (cur) {
+      ++max_depth;
+      CUB(cudaMemsetAsync(d_counts + 2, 0, 4, st));
+      k_collapse<<<blocks_for(cur, 128), 128, 0, st>>>(c, d_ta, cur, d_tb, d_counts + 2);
+      CUB(cudaMemcpyAsync(&cur, d_counts + 2, 4, cudaMemcpyDeviceToHost, st));
+      CUB(cudaStreamSynchronize(st));
+      std::swap(d_ta, d_tb);
+    }
+    unsigned fin[2];
+    CUB(cudaMemcpyAsync(fin, d_counts, 8, cudaMemcpyDeviceToHost, st));
+    CUB(cudaStreamSynchronize(st));
+    n_wnodes = fin[0], n_wtris = fin[1];
+    CUB(dalloc(&m->d_nodes, 5 * (size_t)n_wnodes));
+    CUB(cudaMemcpyAsync(m->d_nodes, wnodes, 80 * (size_t)n_wnodes, cudaMemcpyDeviceToDevice, st));
+  } else {
+    CUB(dalloc(&m->d_nodes, 5));
+    CUB(dalloc(&m->d_tris, 3));
+    n_wnodes = 0;
+  }
+  CUB(cudaEventRecord(e1, st));
+  CUB(cudaStreamSynchronize(st));
+  CUB(cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  m->stats[0] = n_wnodes, m->stats[1] = n_wtris, m->stats[2] = max_depth, m->stats[3] = (uint64_t)(ms * 1000.f);
+  cleanup();
+#undef CUB
+  return GVTB200_OK;
+}
+
+int gvtb200_mesh_create(const float *vertices, uint32_t n_vertices, const uint32_t *faces0, uint32_t n_faces, const float *vertex_normals,
+                        const gvtb200_material *mesh_material, const gvtb200_material *mats, uint32_t n_mats, const int32_t *face_mat,
+                        const float *vcolors, gvtb200_mesh *out) {
+  NEED_INIT();
+  if (!out) return fail(GVTB200_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if ((n_vertices && !vertices) || (n_faces && !faces0)) return fail(GVTB200_ERR_INVALID, "NULL vertex/face array");
+  if (n_faces >= 0x7FFFFFFFu / 4) return fail(GVTB200_ERR_INVALID, "too many faces");
+  for (size_t i = 0; i < 3 * (size_t)n_faces; ++i)
+    if (faces0[i] >= n_vertices) return fail(GVTB200_ERR_INVALID, "face %zu references vertex %u >= %u", i / 3, faces0[i], n_vertices);
+  if (face_mat)
+    for (uint32_t i = 0; i < n_faces; ++i)
+      if (face_mat[i] >= (int32_t)n_mats) return fail(GVTB200_ERR_INVALID, "face %u references material %d >= %u", i, face_mat[i], n_mats);
+  CU(cudaSetDevice(g_device));
+  gvtb200_mesh m = new gvtb200_mesh_s();
+  memset(&m->blas, 0, sizeof(Blas));
+  m->nv = n_vertices, m->nf = n_faces;
+  int rc;
+#define CUM(expr)                                                                                                        \
+  do {                                                                                                                   \
+    cudaError_t e__ = (expr);                                                                                            \
+    if (e__ != cudaSuccess) {                                                                                            \
+      rc = fail(e__ == cudaErrorMemoryAllocation ? GVTB200_ERR_OOM : GVTB200_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, \
+                #expr, cudaGetErrorString(e__));                                                                         \
+      gvtb200_mesh_destroy(m);                                                                                           \
+      return rc;                                                                                                         \
+    }                                                                                                                    \
+  } while (0)
+  CUM(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  rc = mesh_build(m, vertices, n_vertices, faces0, n_faces);
+  if (rc) {
+    gvtb200_mesh_destroy(m);
+    return rc;
+  }
+  { // shading tables
+    std::vector<int4> f4(std::max<size_t>(1, n_faces));
+    for (uint32_t i = 0; i < n_faces; ++i)
+      f4[i] = make_int4((int)faces0[3 * i], (int)faces0[3 * i + 1], (int)faces0[3 * i + 2], face_mat ? face_mat[i] : -1);
+    CUM(dalloc(&m->d_faces, f4.size()));
+    CUM(cudaMemcpy(m->d_faces, f4.data(), f4.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    auto up3 = [&](const float *src, float4 *&dst) -> cudaError_t {
+      std::vector<float4> t(std::max<size_t>(1, n_vertices));
+      for (uint32_t i = 0; i < n_vertices; ++i) t[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+      cudaError_t e = dalloc(&dst, t.size());
+      if (e != cudaSuccess) return e;
+      return cudaMemcpy(dst, t.data(), t.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    };
+    if (vertex_normals) CUM(up3(vertex_normals, m->d_normals));
+    if (vcolors) CUM(up3(vcolors, m->d_vcolors));
+    auto packm = [](const gvtb200_material &a, float4 &p0, float4 &p1) {
+      p0 = make_float4(u2f((uint32_t)a.type), a.kd[0], a.kd[1], a.kd[2]);
+      p1 = make_float4(a.ks[0], a.ks[1], a.ks[2], a.alpha);
+    };
+    gvtb200_material def; // Material.h:62-75 defaults
+    def.type = 0, def.kd[0] = def.kd[1] = def.kd[2] = .5f, def.ks[0] = def.ks[1] = def.ks[2] = .5f, def.alpha = 1.f;
+    packm(mesh_material ? *mesh_material : def, m->blas.mat0, m->blas.mat1);
+    if (mats && n_mats && face_mat) {
+      std::vector<float4> t(2 * (size_t)n_mats);
+      for (uint32_t i = 0; i < n_mats; ++i) packm(mats[i], t[2 * i], t[2 * i + 1]);
+      CUM(dalloc(&m->d_mats, t.size()));
+      CUM(cudaMemcpy(m->d_mats, t.data(), t.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+  }
+#undef CUM
+  m->blas.nodes = m->d_nodes, m->blas.tris = m->d_tris, m->blas.faces = m->d_faces, m->blas.normals = m->d_normals;
+  m->blas.vcolors = m->d_vcolors, m->blas.mats = m->d_mats;
+  m->blas.n_tris = n_faces, m->blas.n_nodes = (unsigned)m->stats[0];
+  *out = m;
+  return GVTB200_OK;
+}
+
+int gvtb200_mesh_morton(gvtb200_mesh m, uint32_t *codes, uint32_t *sorted_faces) {
+  NEED_INIT();
+  if (!m) return fail(GVTB200_ERR_INVALID, "mesh is NULL");
+  if (codes && m->nf) CU(cudaMemcpy(codes, m->d_keys_unsorted, (size_t)m->nf * 4, cudaMemcpyDeviceToHost));
+  if (sorted_faces && m->nf) CU(cudaMemcpy(sorted_faces, m->d_sorted_faces, (size_t)m->nf * 4, cudaMemcpyDeviceToHost));
+  return GVTB200_OK;
+}
+int gvtb200_mesh_stats(gvtb200_mesh m, uint64_t stats[4]) {
+  if (!m) return fail(GVTB200_ERR_INVALID, "mesh is NULL");
+  memcpy(stats, m->stats, sizeof(m->stats));
+  return GVTB200_OK;
+}
+
+static int mesh_adapter_ctx(gvtb200_mesh m) {
+  if (!m->d_inst) {
+    CU(dalloc(&m->d_inst, 1));
+    CU(dalloc(&m->d_blas, 1));
+    CU(dalloc(&m->d_ctr, 1));
+    CU(dalloc(&m->d_work, 64));
+    CU(cudaMemcpy(m->d_blas, &m->blas, sizeof(Blas), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+static int gvtb200_intersect_impl(gvtb200_mesh m, const gvtb200_ray *rays, size_t n, int any, int4 *hits_host) {
+  NEED_INIT();
+  if (!m) return fail(GVTB200_ERR_INVALID, "mesh is NULL");
+  if (n == 0) return GVTB200_OK;
+  if (n > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "too many rays");
+  CU(cudaSetDevice(g_device));
+  if (int rc = mesh_adapter_ctx(m)) return rc;
+  if (int rc = upload_rays(rays, n, m->d_aos, m->aos_cap, m->q_in, 0, m->stream)) return rc;
+  if (m->hits_cap < n) {
+    dfree(m->d_hits);
+    CU(dalloc(&m->d_hits, n));
+    m->hits_cap = n;
+  }
+  k_intersect<<<blocks_for(n, 128), 128, 0, m->stream>>>(m->blas, m->q_in.q, (unsigned)n, any, m->d_hits);
+  CU(cudaMemcpyAsync(hits_host, m->d_hits, n * sizeof(int4), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  CU(cudaGetLastError());
+  return GVTB200_OK;
+}
+
+int gvtb200_intersect(gvtb200_mesh m, const gvtb200_ray *rays, size_t n, gvtb200_hit *hits) {
+  static_assert(sizeof(gvtb200_hit) == sizeof(int4), "hit record is 16 bytes");
+  if (n && (!rays || !hits)) return fail(GVTB200_ERR_INVALID, "NULL rays/hits");
+  return gvtb200_intersect_impl(m, rays, n, 0, reinterpret_cast<int4 *>(hits));
+}
+int gvtb200_occluded(gvtb200_mesh m, const gvtb200_ray *rays, size_t n, int32_t *occluded) {
+  if (n && (!rays || !occluded)) return fail(GVTB200_ERR_INVALID, "NULL rays/occluded");
+  std::vector<int4> h(n);
+  int rc = gvtb200_intersect_impl(m, rays, n, 1, h.data());
+  if (rc) return rc;
+  for (size_t i = 0; i < n; ++i) occluded[i] = h[i].x >= 0 ? 1 : 0;
+  return GVTB200_OK;
+}
+
+int gvtb200_trace(gvtb200_mesh m, gvtb200_ray *rays, size_t n_rays, size_t begin, size_t end, gvtb200_ray *moved, size_t moved_cap,
+                  size_t *n_moved, const float mat[16], const float minv[16], const float normi[9], const gvtb200_light *lights,
+                  int n_lights, uint32_t flags, uint32_t seed) {
+  NEED_INIT();
+  if (!m || !n_moved || !minv || !normi || (n_lights && !lights)) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  (void)mat; // the instance matrix itself is not needed: rays are taken to mesh space with minv, normals back with normi
+  if (n_lights < 0 || n_lights > GVT_MAX_LIGHTS) return fail(GVTB200_ERR_INVALID, "at most %d lights", GVT_MAX_LIGHTS);
+  if (end == 0) end = n_rays; // EmbreeMeshAdapter.cpp:642
+  if (begin > end || end > n_rays) return fail(GVTB200_ERR_INVALID, "bad range [%zu,%zu) of %zu", begin, end, n_rays);
+  const size_t n = end - begin;
+  if (n == 0) return GVTB200_OK;
+  if (!rays || (moved_cap && !moved)) return fail(GVTB200_ERR_INVALID, "NULL rays/moved");
+  if (n * (size_t)(1 + n_lights) > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "too many rays in one call");
+  CU(cudaSetDevice(g_device));
+  if (int rc = mesh_adapter_ctx(m)) return rc;
+  cudaStream_t st = m->stream;
+  int max_depth = 1;
+  for (size_t i = begin; i < end; ++i) max_depth = std::max(max_depth, rays[i].depth);
+  Instance in;
+  pack_instance(in, minv, normi, 0, 0);
+  CU(cudaMemcpyAsync(m->d_inst, &in, sizeof(in), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(m->d_ctr, 0, sizeof(DevCounters), st));
+  FrameParams fp;
+  memset(&fp, 0, sizeof(fp));
+  pack_lights(fp, lights, n_lights);
+  fp.flags = flags, fp.seed = seed, fp.rank = 0, fp.world = 1;
+  SceneDev sd;
+  memset(&sd, 0, sizeof(sd));
+  sd.inst = m->d_inst, sd.blas = m->d_blas, sd.ctr = m->d_ctr;
+  if (int rc = upload_rays(rays + begin, n, m->d_aos, m->aos_cap, m->q_in, -2, st)) return rc;
+  CU(m->q_fin.ensure(n));
+  k_aos_to_soa<<<blocks_for(n, 256), 256, 0, st>>>(m->d_aos, (unsigned)n, m->q_fin.q, 0u, -2);
+  CU(m->q_nx.ensure(n));
+  CU(m->q_sh.ensure(n * (size_t)std::max(1, n_lights)));
+  // every input ray can be handed back, every hit can emit one unoccluded shadow ray per light per bounce
+  const size_t mv_need = n * (size_t)(1 + n_lights * max_depth);
+  CU(m->q_mv.ensure(std::min<size_t>(mv_need, std::max<size_t>(moved_cap, n))));
+  CU(cudaMemsetAsync(m->q_mv.q.count, 0, 4, st));
+  TraceQueues tq;
+  QueueMem *qa = &m->q_in, *qb = &m->q_nx;
+  for (int wave = 0; wave < max_depth; ++wave) {
+    CU(cudaMemsetAsync(m->d_work, 0, 8, st));
+    CU(cudaMemsetAsync(qb->q.count, 0, 4, st));
+    CU(cudaMemsetAsync(m->q_sh.q.count, 0, 4, st));
+    tq.in = qa->q, tq.shq = m->q_sh.q, tq.nxq = qb->q, tq.mvq = m->q_mv.q, tq.exq = null_queue(m->d_work + 2), tq.fin = m->q_fin.q;
+    tq.work = m->d_work;
+    launch_trace(false, fp, sd, tq, 1, st);
+    tq.in = m->q_sh.q, tq.shq = null_queue(m->d_work + 3), tq.nxq = null_queue(m->d_work + 4), tq.work = m->d_work + 1;
+    launch_trace(false, fp, sd, tq, 1, st);
+    std::swap(qa, qb);
+  }
+  unsigned n_mv = 0;
+  CU(cudaMemcpyAsync(&n_mv, m->q_mv.q.count, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  if (n_mv > m->q_mv.q.cap || *n_moved + n_mv > moved_cap)
+    return fail(GVTB200_ERR_CAPACITY, "moved_rays capacity %zu too small: %zu + %u outgoing rays", moved_cap, *n_moved, n_mv);
+  // rays back (mutated in place) and moved rays appended
+  size_t need = std::max<size_t>(n, n_mv);
+  if (m->aos_cap < need) {
+    dfree(m->d_aos);
+    CU(dalloc(&m->d_aos, 5 * need));
+    m->aos_cap = need;
+  }
+  k_soa_to_aos<<<blocks_for(n, 256), 256, 0, st>>>(m->q_fin.q, (unsigned)n, m->d_aos);
+  CU(cudaMemcpyAsync(rays + begin, m->d_aos, n * sizeof(gvtb200_ray), cudaMemcpyDeviceToHost, st));
+  if (n_mv) {
+    CU(cudaStreamSynchronize(st));
+    k_soa_to_aos<<<blocks_for(n_mv, 256), 256, 0, st>>>(m->q_mv.q, n_mv, m->d_aos);
+    CU(cudaMemcpyAsync(moved + *n_moved, m->d_aos, (size_t)n_mv * sizeof(gvtb200_ray), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  *n_moved += n_mv;
+  return GVTB200_OK;
+}
+
+// =============================================================================================================
+// B2: scene / frame
+// =============================================================================================================
+int gvtb200_scene_create(gvtb200_scene *out) {
+  NEED_INIT();
+  if (!out) return fail(GVTB200_ERR_INVALID, "out is NULL");
+  CU(cudaSetDevice(g_device));
+  gvtb200_scene s = new gvtb200_scene_s();
+  memset(&s->tlas, 0, sizeof(Tlas));
+  cudaError_t e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+  s->stream = s->own_stream;
+  for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
+  if (e == cudaSuccess) e = dalloc(&s->d_ctr, 1);
+  if (e == cudaSuccess) e = dalloc(&s->d_work, 64);
+  if (e == cudaSuccess) e = dalloc(&s->d_peer, 1024);
+  if (e == cudaSuccess) e = cudaMemset(s->d_ctr, 0, sizeof(DevCounters));
+  if (e != cudaSuccess) {
+    gvtb200_scene_destroy(s);
+    return fail(GVTB200_ERR_CUDA, "scene_create: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return GVTB200_OK;
+}
+int gvtb200_scene_destroy(gvtb200_scene s) {
+  if (!s) return GVTB200_OK;
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  dfree(s->d_inst), dfree(s->d_blas), dfree(s->d_tnodes), dfree(s->d_tboxes), dfree(s->d_fb), dfree(s->d_ctr), dfree(s->d_work), dfree(s->d_peer);
+  dfree(s->d_export), dfree(s->d_next), dfree(s->d_t), dfree(s->d_aos);
+  s->q_a.release(), s->q_b.release(), s->q_sh.release(), s->q_ex.release(), s->q_tmp.release();
+  for (auto &e : s->ev)
+    if (e) cudaEventDestroy(e);
+  if (s->own_stream) cudaStreamDestroy(s->own_stream);
+  delete s;
+  return GVTB200_OK;
+}
+int gvtb200_scene_add_instance(gvtb200_scene s, gvtb200_mesh mesh, const float m[16], const float minv[16], const float normi[9],
+                               const float box_min[3], const float box_max[3]) {
+  if (!s || !m || !minv || !normi || !box_min || !box_max) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  InstHost in;
+  in.mesh = mesh;
+  memcpy(in.m, m, 64), memcpy(in.minv, minv, 64), memcpy(in.normi, normi, 36);
+  for (int i = 0; i < 3; ++i) in.box.lo[i] = box_min[i], in.box.hi[i] = box_max[i];
+  for (int i = 0; i < 3; ++i) in.centroid[i] = in.box.centroid(i); // api.cpp:321
+  in.owner = 0;
+  s->inst.push_back(in);
+  s->committed = false;
+  return (int)s->inst.size() - 1;
+}
+int gvtb200_scene_set_lights(gvtb200_scene s, const gvtb200_light *lights, int n) {
+  if (!s || (n && !lights)) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  if (n < 0 || n > GVT_MAX_LIGHTS) return fail(GVTB200_ERR_INVALID, "at most %d lights", GVT_MAX_LIGHTS);
+  s->lights.assign(lights, lights + n);
+  return GVTB200_OK;
+}
+int gvtb200_scene_set_camera(gvtb200_scene s, const float eye[3], const float focus[3], const float up[3], float fov, int depth,
+                             int samples, float jitter) {
+  if (!s || !eye || !focus || !up) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  if (samples < 1 || depth < 0) return fail(GVTB200_ERR_INVALID, "samples must be >= 1 and depth >= 0");
+  memcpy(s->eye, eye, 12), memcpy(s->focus, focus, 12), memcpy(s->up, up, 12);
+  s->fov = fov, s->depth = depth, s->samples = samples;
+  s->jitter_window = (int)jitter; // gvtCamera.h:136 / gvtCamera.cpp:202: an int
+  return GVTB200_OK;
+}
+int gvtb200_scene_set_film(gvtb200_scene s, int w, int h) {
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  if (w < 2 || h < 2 || (size_t)w * h > 0x40000000u) return fail(GVTB200_ERR_INVALID, "film %dx%d not supported", w, h);
+  s->W = w, s->H = h;
+  return GVTB200_OK;
+}
+int gvtb200_scene_set_flags(gvtb200_scene s, uint32_t flags, uint32_t seed) {
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  s->flags = flags, s->seed = seed;
+  return GVTB200_OK;
+}
+
+int gvtb200_scene_commit(gvtb200_scene s) {
+  NEED_INIT();
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  CU(cudaSetDevice(g_device));
+  const int n = (int)s->inst.size();
+  s->tnodes.clear(), s->sorted_ids.clear();
+  s->work.resize(n);
+  for (int i = 0; i < n; ++i) s->work[i] = i; // ids 0..n-1 in creation order (BVH.cpp:48-51)
+  if (n) tlas_build(*s, 0, n);
+  if (n && tlas_depth(*s, 0) > GVT_TLAS_STACK) return fail(GVTB200_ERR_CAPACITY, "top-level BVH deeper than %d", GVT_TLAS_STACK);
+  // flatten
+  std::vector<float4> tn(2 * std::max<size_t>(1, s->tnodes.size())), tb(2 * std::max<size_t>(1, (size_t)n));
+  for (size_t i = 0; i < s->tnodes.size(); ++i) {
+    const TNodeHost &t = s->tnodes[i];
+    int a = t.left >= 0 ? t.left : ~t.first, b = t.left >= 0 ? t.right : t.count;
+    tn[2 * i] = make_float4(t.bbox.lo[0], t.bbox.lo[1], t.bbox.lo[2], u2f((uint32_t)a));
+    tn[2 * i + 1] = make_float4(t.bbox.hi[0], t.bbox.hi[1], t.bbox.hi[2], u2f((uint32_t)b));
+  }
+  for (int i = 0; i < n; ++i) {
+    const InstHost &in = s->inst[s->sorted_ids[i]];
+    tb[2 * i] = make_float4(in.box.lo[0], in.box.lo[1], in.box.lo[2], u2f((uint32_t)s->sorted_ids[i]));
+    tb[2 * i + 1] = make_float4(in.box.hi[0], in.box.hi[1], in.box.hi[2], 0.f);
+  }
+  dfree(s->d_tnodes), dfree(s->d_tboxes), dfree(s->d_inst), dfree(s->d_blas);
+  CU(dalloc(&s->d_tnodes, tn.size()));
+  CU(dalloc(&s->d_tboxes, tb.size()));
+  CU(cudaMemcpy(s->d_tnodes, tn.data(), tn.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(s->d_tboxes, tb.data(), tb.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  s->tlas.nodes = s->d_tnodes, s->tlas.boxes = s->d_tboxes, s->tlas.n_nodes = (int)s->tnodes.size(), s->tlas.n_inst = n;
+  // instance + BLAS tables
+  std::map<gvtb200_mesh, int> mesh_index;
+  std::vector<Blas> blas;
+  std::vector<Instance> di(std::max(1, n));
+  for (int i = 0; i < n; ++i) {
+    const InstHost &in = s->inst[i];
+    int mi = -1;
+    if (in.mesh) {
+      auto it = mesh_index.find(in.mesh);
+      if (it == mesh_index.end()) {
+        mi = (int)blas.size();
+        mesh_index[in.mesh] = mi;
+        blas.push_back(in.mesh->blas);
+      } else
+        mi = it->second;
+    } else if (s->world == 1 || in.owner == s->rank)
+      return fail(GVTB200_ERR_INVALID, "instance %d has no mesh but is owned by this rank", i);
+    pack_instance(di[i], in.minv, in.normi, mi, in.owner);
+  }
+  if (blas.empty()) {
+    Blas b;
+    memset(&b, 0, sizeof(b));
+    blas.push_back(b);
+  }
+  CU(dalloc(&s->d_inst, di.size()));
+  CU(dalloc(&s->d_blas, blas.size()));
+  CU(cudaMemcpy(s->d_inst, di.data(), di.size() * sizeof(Instance), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(s->d_blas, blas.data(), blas.size() * sizeof(Blas), cudaMemcpyHostToDevice));
+  s->committed = true;
+  return GVTB200_OK;
+}
+
+int gvtb200_scene_tlas_order(gvtb200_scene s, int32_t *sorted_ids, int *n) {
+  if (!s || !s->committed) return fail(GVTB200_ERR_INVALID, "scene not committed");
+  if (sorted_ids) memcpy(sorted_ids, s->sorted_ids.data(), s->sorted_ids.size() * 4);
+  if (n) *n = (int)s->tnodes.size();
+  return GVTB200_OK;
+}
+
+static int scene_fb(gvtb200_scene s) {
+  size_t npix = (size_t)s->W * s->H;
+  if (s->fb_pix != npix) {
+    dfree(s->d_fb);
+    CU(dalloc(&s->d_fb, npix * 4));
+    s->fb_pix = npix;
+    CU(cudaMemsetAsync(s->d_fb, 0, npix * 16, s->stream));
+  }
+  return 0;
+}
+#define NEED_SCENE()                                                                                                     \
+  do {                                                                                                                   \
+    NEED_INIT();                                                                                                         \
+    if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");                                                          \
+    if (!s->committed) return fail(GVTB200_ERR_INVALID, "scene not committed (gvtb200_scene_commit)");                  \
+    CU(cudaSetDevice(g_device));                                                                                         \
+  } while (0)
+
+int gvtb200_camera_rays(gvtb200_scene s, gvtb200_ray *out, size_t cap) {
+  NEED_INIT();
+  if (!s || !out) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(g_device));
+  size_t n = (size_t)s->W * s->H * s->samples * s->samples;
+  if (cap < n) return fail(GVTB200_ERR_CAPACITY, "need room for %zu rays", n);
+  if (n > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "too many rays");
+  FrameParams fp;
+  build_frame_params(*s, fp);
+  CU(s->q_tmp.ensure(n));
+  if (s->aos_cap < n) {
+    dfree(s->d_aos);
+    CU(dalloc(&s->d_aos, 5 * n));
+    s->aos_cap = n;
+  }
+  k_camera_only<<<blocks_for(n, 256), 256, 0, s->stream>>>(fp, n, s->q_tmp.q);
+  k_soa_to_aos<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->q_tmp.q, (unsigned)n, s->d_aos);
+  CU(cudaMemcpyAsync(out, s->d_aos, n * sizeof(gvtb200_ray), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  return GVTB200_OK;
+}
+
+int gvtb200_route(gvtb200_scene s, const gvtb200_ray *rays, size_t n, int from, int32_t *next, float *t) {
+  NEED_SCENE();
+  if (n == 0) return GVTB200_OK;
+  if (!rays || !next || !t) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  if (n > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "too many rays");
+  if (int rc = upload_rays(rays, n, s->d_aos, s->aos_cap, s->q_tmp, -1, s->stream)) return rc;
+  if (s->route_cap < n) {
+    dfree(s->d_next), dfree(s->d_t);
+    CU(dalloc(&s->d_next, n));
+    CU(dalloc(&s->d_t, n));
+    s->route_cap = n;
+  }
+  FrameParams fp;
+  build_frame_params(*s, fp);
+  k_route<<<blocks_for(n, 128), 128, 0, s->stream>>>(fp, scene_dev(*s), s->q_tmp.q, (unsigned)n, from, s->d_next, s->d_t);
+  CU(cudaMemcpyAsync(next, s->d_next, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(t, s->d_t, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  return GVTB200_OK;
+}
+
+int gvtb200_shuffle(gvtb200_scene s, const gvtb200_ray *rays, size_t n, int from, gvtb200_ray *out, int32_t *out_inst, size_t cap,
+                    size_t *n_out) {
+  NEED_SCENE();
+  if (!n_out) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  *n_out = 0;
+  if (n == 0) return GVTB200_OK;
+  if (!rays || !out || !out_inst) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  if (n > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "too many rays");
+  if (int rc = scene_fb(s)) return rc;
+  if (int rc = upload_rays(rays, n, s->d_aos, s->aos_cap, s->q_tmp, -1, s->stream)) return rc;
+  CU(s->q_a.ensure(n));
+  CU(cudaMemsetAsync(s->q_a.q.count, 0, 4, s->stream));
+  FrameParams fp;
+  build_frame_params(*s, fp);
+  k_shuffle<<<blocks_for(n, 128), 128, 0, s->stream>>>(fp, scene_dev(*s), s->q_tmp.q, (unsigned)n, from, s->q_a.q);
+  unsigned cnt = 0;
+  CU(cudaMemcpyAsync(&cnt, s->q_a.q.count, 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  if (cnt > cap) return fail(GVTB200_ERR_CAPACITY, "need room for %u rays", cnt);
+  if (cnt) {
+    std::vector<gvtb200_ray> tmp(cnt);
+    std::vector<int> ti(cnt);
+    k_soa_to_aos<<<blocks_for(cnt, 256), 256, 0, s->stream>>>(s->q_a.q, cnt, s->d_aos);
+    CU(cudaMemcpyAsync(tmp.data(), s->d_aos, (size_t)cnt * sizeof(gvtb200_ray), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(ti.data(), s->q_a.q.inst, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    // group by target instance (the reference keeps one queue per instance, TracerBase.h:403-409)
+    std::vector<unsigned> order(cnt);
+    for (unsigned i = 0; i < cnt; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return ti[a] < ti[b]; });
+    for (unsigned i = 0; i < cnt; ++i) out[i] = tmp[order[i]], out_inst[i] = ti[order[i]];
+  }
+  *n_out = cnt;
+  return GVTB200_OK;
+}
+
+int gvtb200_framebuffer_clear(gvtb200_scene s) {
+  NEED_INIT();
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  CU(cudaSetDevice(g_device));
+  if (int rc = scene_fb(s)) return rc;
+  CU(cudaMemsetAsync(s->d_fb, 0, s->fb_pix * 16, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return GVTB200_OK;
+}
+int gvtb200_framebuffer_clamp(gvtb200_scene s) {
+  NEED_INIT();
+  if (!s || !s->d_fb) return fail(GVTB200_ERR_INVALID, "no framebuffer");
+  CU(cudaSetDevice(g_device));
+  k_fb_clamp<<<blocks_for(s->fb_pix, 256), 256, 0, s->stream>>>(s->d_fb, s->fb_pix);
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  return GVTB200_OK;
+}
+int gvtb200_framebuffer_read(gvtb200_scene s, float *rgba, size_t n_floats) {
+  NEED_INIT();
+  if (!s || !s->d_fb || !rgba) return fail(GVTB200_ERR_INVALID, "no framebuffer / NULL argument");
+  if (n_floats < s->fb_pix * 4) return fail(GVTB200_ERR_CAPACITY, "need %zu floats", s->fb_pix * 4);
+  CU(cudaSetDevice(g_device));
+  CU(cudaMemcpyAsync(rgba, s->d_fb, s->fb_pix * 16, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return GVTB200_OK;
+}
+
+// one wave = Adapter::trace on every queued ray + the shadow rays it generated; `depth` waves drain a frame
+static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool timed) {
+  SceneDev sd = scene_dev(*s);
+  TraceQueues tq;
+  for (int wave = 0; wave < waves; ++wave) {
+    CU(cudaMemsetAsync(s->d_work, 0, 32, s->stream));
+    CU(cudaMemsetAsync(s->q_b.q.count, 0, 4, s->stream));
+    CU(cudaMemsetAsync(s->q_sh.q.count, 0, 4, s->stream));
+    tq.in = s->q_a.q, tq.shq = s->q_sh.q, tq.nxq = s->q_b.q, tq.mvq = null_queue(s->d_work + 2), tq.exq = s->q_ex.q;
+    tq.fin = null_queue(s->d_work + 5), tq.work = s->d_work;
+    if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[2], s->stream));
+    launch_trace(s->profile, fp, sd, tq, 0, s->stream);
+    if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[3], s->stream));
+    tq.in = s->q_sh.q, tq.shq = null_queue(s->d_work + 3), tq.nxq = null_queue(s->d_work + 4), tq.work = s->d_work + 1;
+    launch_trace(s->profile, fp, sd, tq, 0, s->stream);
+    if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[4], s->stream));
+    std::swap(s->q_a, s->q_b);
+  }
+  return 0;
+}
+
+static int frame_queues(gvtb200_scene s, size_t count) {
+  size_t nl = std::max<size_t>(1, s->lights.size());
+  if (count * nl > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "frame has too many rays for one queue");
+  CU(s->q_a.ensure(count));
+  CU(s->q_b.ensure(s->depth > 1 ? count : 32));
+  CU(s->q_sh.ensure(count * nl));
+  CU(s->q_ex.ensure(s->world > 1 ? count : 32));
+  return 0;
+}
+
+int gvtb200_render_frame_tiles(gvtb200_scene s, int row0, int row1, int tile_rows, int tile_index, int tile_stride) {
+  NEED_SCENE();
+  if (s->world > 1) return fail(GVTB200_ERR_INVALID, "domain-partitioned scene: use the gvtb200_domain_* calls");
+  if (row0 < 0 || row1 > s->H || row0 > row1) return fail(GVTB200_ERR_INVALID, "bad row range [%d,%d) of %d", row0, row1, s->H);
+  if (tile_rows < 1 || tile_stride < 1 || tile_index < 0 || tile_index >= tile_stride)
+    return fail(GVTB200_ERR_INVALID, "bad tiling rows=%d index=%d stride=%d", tile_rows, tile_index, tile_stride);
+  if (int rc = scene_fb(s)) return rc;
+  RowTiles tiles;
+  tiles.row0 = row0, tiles.row1 = row1, tiles.tile_rows = tile_rows, tiles.index = tile_index, tiles.stride = tile_stride;
+  const size_t s2 = (size_t)s->samples * s->samples;
+  const size_t count = tiles_local_rows(tiles) * s->W * s2;
+  if (int rc = frame_queues(s, count)) return rc;
+  FrameParams fp;
+  build_frame_params(*s, fp);
+  cudaStream_t st = s->stream;
+  CU(cudaEventRecord(s->ev[0], st));
+  CU(cudaMemsetAsync(s->d_fb, 0, s->fb_pix * 16, st)); // clearBuffer, TracerBase.h:310
+  CU(cudaMemsetAsync(s->d_ctr, 0, sizeof(DevCounters), st));
+  CU(cudaMemsetAsync(s->q_a.q.count, 0, 4, st));
+  CU(cudaMemsetAsync(s->q_ex.q.count, 0, 4, st));
+  if (count) {
+    k_camera_route<<<g_sms * 8, 256, 0, st>>>(fp, scene_dev(*s), tiles, count, s->q_a.q);
+    LAUNCHED(1);
+    if (int rc = run_waves(s, fp, std::max(1, s->depth), true)) return rc;
+  }
+  k_fb_clamp<<<blocks_for(s->fb_pix, 256), 256, 0, st>>>(s->d_fb, s->fb_pix);
+  LAUNCHED(1);
+  CU(cudaEventRecord(s->ev[1], st));
+  CU(cudaGetLastError());
+  s->timing_valid = count > 0;
+  return GVTB200_OK;
+}
+int gvtb200_render_frame_async(gvtb200_scene s, int row0, int row1) { return gvtb200_render_frame_tiles(s, row0, row1, 1, 0, 1); }
+// run the scene's work on a caller-owned CUDA stream (e.g. the stream NCCL collectives are enqueued on); NULL restores
+// the scene's own stream
+int gvtb200_scene_set_stream(gvtb200_scene s, void *cuda_stream) {
+  NEED_INIT();
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  CU(cudaStreamSynchronize(s->stream));
+  s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
+  return GVTB200_OK;
+}
+unsigned long long gvtb200_launch_count(void) { return g_launches; }
+int gvtb200_scene_sync(gvtb200_scene s) {
+  NEED_INIT();
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  return GVTB200_OK;
+}
+int gvtb200_scene_counters(gvtb200_scene s, gvtb200_counters *out) {
+  static_assert(sizeof(gvtb200_counters) == sizeof(DevCounters), "counter layouts must match");
+  NEED_INIT();
+  if (!s || !out) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  CU(cudaMemcpyAsync(out, s->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return GVTB200_OK;
+}
+int gvtb200_render_frame(gvtb200_scene s, int row0, int row1, float *rgba_out, gvtb200_counters *counters) {
+  int rc = gvtb200_render_frame_async(s, row0, row1);
+  if (rc) return rc;
+  if (rgba_out) CU(cudaMemcpyAsync(rgba_out, s->d_fb, s->fb_pix * 16, cudaMemcpyDeviceToHost, s->stream));
+  if (counters) CU(cudaMemcpyAsync(counters, s->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  return GVTB200_OK;
+}
+int gvtb200_scene_profile_counters(gvtb200_scene s, int enable) {
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  s->profile = enable != 0;
+  return GVTB200_OK;
+}
+int gvtb200_scene_device_framebuffer(gvtb200_scene s, void **d_rgba, void **cuda_stream) {
+  NEED_INIT();
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  CU(cudaSetDevice(g_device));
+  if (int rc = scene_fb(s)) return rc;
+  if (d_rgba) *d_rgba = s->d_fb;
+  if (cuda_stream) *cuda_stream = (void *)s->stream;
+  return GVTB200_OK;
+}
+int gvtb200_scene_last_timing(gvtb200_scene s, float *frame_ms, float kernel_ms[3]) {
+  NEED_INIT();
+  if (!s || !s->timing_valid) return fail(GVTB200_ERR_INVALID, "no timed frame");
+  CU(cudaEventSynchronize(s->ev[1]));
+  float a = 0, b = 0, c = 0, d = 0;
+  CU(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
+  CU(cudaEventElapsedTime(&b, s->ev[0], s->ev[2]));
+  CU(cudaEventElapsedTime(&c, s->ev[2], s->ev[3]));
+  CU(cudaEventElapsedTime(&d, s->ev[3], s->ev[4]));
+  if (frame_ms) *frame_ms = a;
+  if (kernel_ms) kernel_ms[0] = b, kernel_ms[1] = c, kernel_ms[2] = d;
+  return GVTB200_OK;
+}
+
+// =============================================================================================================
+// Tracer<DomainScheduler>
+// =============================================================================================================
+int gvtb200_domain_set_owner(gvtb200_scene s, const int32_t *owner, int n, int rank, int world) {
+  if (!s || !owner) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  if (n != (int)s->inst.size()) return fail(GVTB200_ERR_INVALID, "owner table has %d entries, scene has %zu instances", n, s->inst.size());
+  if (world < 1 || world > 1024 || rank < 0 || rank >= world) return fail(GVTB200_ERR_INVALID, "bad rank/world %d/%d", rank, world);
+  for (int i = 0; i < n; ++i) {
+    if (owner[i] < 0 || owner[i] >= world) return fail(GVTB200_ERR_INVALID, "owner[%d] = %d outside 0..%d", i, owner[i], world - 1);
+    s->inst[i].owner = owner[i];
+  }
+  s->rank = rank, s->world = world;
+  s->committed = false;
+  return GVTB200_OK;
+}
+int gvtb200_domain_begin_frame(gvtb200_scene s) {
+  NEED_SCENE();
+  if (int rc = scene_fb(s)) return rc;
+  const size_t count = (size_t)s->W * s->H * s->samples * s->samples;
+  if (int rc = frame_queues(s, count)) return rc;
+  FrameParams fp;
+  build_frame_params(*s, fp);
+  cudaStream_t st = s->stream;
+  CU(cudaMemsetAsync(s->d_fb, 0, s->fb_pix * 16, st));
+  CU(cudaMemsetAsync(s->d_ctr, 0, sizeof(DevCounters), st));
+  CU(cudaMemsetAsync(s->q_a.q.count, 0, 4, st));
+  CU(cudaMemsetAsync(s->q_ex.q.count, 0, 4, st));
+  // every rank generates all camera rays and keeps those whose first instance it owns (DomainTracer.h:148-181)
+  RowTiles tiles;
+  tiles.row0 = 0, tiles.row1 = s->H, tiles.tile_rows = 1, tiles.index = 0, tiles.stride = 1;
+  k_camera_route<<<g_sms * 8, 256, 0, st>>>(fp, scene_dev(*s), tiles, count, s->q_a.q);
+  LAUNCHED(1);
+  CU(cudaGetLastError());
+  s->timing_valid = false;
+  return GVTB200_OK;
+}
+int gvtb200_domain_drain_local(gvtb200_scene s) {
+  NEED_SCENE();
+  FrameParams fp;
+  build_frame_params(*s, fp);
+  if (int rc = run_waves(s, fp, std::max(1, s->depth), false)) return rc;
+  CU(cudaGetLastError());
+  return GVTB200_OK;
+}
+int gvtb200_domain_export(gvtb200_scene s, uint32_t *counts, void **d_export, size_t *n_total) {
+  NEED_SCENE();
+  if (!counts || !d_export || !n_total) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  cudaStream_t st = s->stream;
+  const int P = s->world;
+  unsigned n_ex = 0;
+  CU(cudaMemcpyAsync(&n_ex, s->q_ex.q.count, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemsetAsync(s->d_peer, 0, 4 * (size_t)P, st));
+  CU(cudaStreamSynchronize(st));
+  if (n_ex > s->q_ex.q.cap) return fail(GVTB200_ERR_CAPACITY, "export queue overflow (%u > %u)", n_ex, s->q_ex.q.cap);
+  std::vector<unsigned> c(P, 0), off(P, 0);
+  if (n_ex) {
+    k_export_count<<<g_sms * 4, 256, 0, st>>>(s->q_ex.q, s->d_inst, s->d_peer);
+    CU(cudaMemcpyAsync(c.data(), s->d_peer, 4 * (size_t)P, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int p = 1; p < P; ++p) off[p] = off[p - 1] + c[p - 1];
+    if (s->export_cap < n_ex) {
+      dfree(s->d_export);
+      CU(dalloc(&s->d_export, 5 * (size_t)n_ex));
+      s->export_cap = n_ex;
+    }
+    CU(cudaMemcpyAsync(s->d_peer, off.data(), 4 * (size_t)P, cudaMemcpyHostToDevice, st));
+    k_export_pack<<<g_sms * 4, 256, 0, st>>>(s->q_ex.q, s->d_inst, s->d_peer, s->d_export);
+    CU(cudaMemsetAsync(s->q_ex.q.count, 0, 4, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+  }
+  for (int p = 0; p < P; ++p) counts[p] = c[p];
+  *d_export = s->d_export;
+  *n_total = n_ex;
+  return GVTB200_OK;
+}
+int gvtb200_domain_import(gvtb200_scene s, const void *d_rays, size_t n_rays) {
+  NEED_SCENE();
+  if (n_rays == 0) return GVTB200_OK;
+  if (!d_rays) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  cudaStream_t st = s->stream;
+  unsigned have = 0;
+  CU(cudaMemcpyAsync(&have, s->q_a.q.count, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  have = std::min(have, s->q_a.q.cap);
+  if ((size_t)have + n_rays > s->q_a.q.cap) {
+    if (have) return fail(GVTB200_ERR_CAPACITY, "local queue full (%u + %zu > %u)", have, n_rays, s->q_a.q.cap);
+    CU(s->q_a.ensure(n_rays));
+    CU(s->q_b.ensure(s->depth > 1 ? n_rays : 32));
+    CU(s->q_sh.ensure(n_rays * std::max<size_t>(1, s->lights.size())));
+  }
+  k_import<<<blocks_for(n_rays, 256), 256, 0, st>>>((const uint4 *)d_rays, (unsigned)n_rays, s->q_a.q, have);
+  unsigned total = have + (unsigned)n_rays;
+  CU(cudaMemcpyAsync(s->q_a.q.count, &total, 4, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  return GVTB200_OK;
+}
+int gvtb200_domain_pending(gvtb200_scene s, uint64_t *n) {
+  NEED_SCENE();
+  if (!n) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  unsigned a = 0, e = 0;
+  CU(cudaMemcpyAsync(&a, s->q_a.q.count, 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(&e, s->q_ex.q.count, 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  *n = (uint64_t)a + e;
+  return GVTB200_OK;
+}
+
+} // extern "C"

@@ -2,6 +2,7 @@
 // routing, the persistent two-level trace kernel, framebuffer and domain-exchange helpers.
 #pragma once
 #include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
 #include <cuda_runtime.h>
 
 #include "bvh_build.h"
@@ -200,11 +201,7 @@ __device__ __forceinline__ void count_add(unsigned long long *c, unsigned long l
 // IceTComposite::localAdd (composite/IceTComposite.cpp:111-117): += colour, alpha += 1.  The running clamp to 1 is
 // applied once at the end (k_fb_clamp): min(1, sum) == clamp-after-each-add for non-negative terms.
 __device__ __forceinline__ void fb_add(float *fb, int id, V3 c) {
-  float *p = fb + 4 * (size_t)id;
-  atomicAdd(p + 0, c.x);
-  atomicAdd(p + 1, c.y);
-  atomicAdd(p + 2, c.z);
-  atomicAdd(p + 3, 1.0f);
+  atomicAdd(reinterpret_cast<float4 *>(fb) + id, make_float4(c.x, c.y, c.z, 1.0f)); // one 16-byte RED (sm_90+)
 }
 __global__ void k_fb_clamp(float *fb, size_t npix) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -214,13 +211,33 @@ __global__ void k_fb_clamp(float *fb, size_t npix) {
   reinterpret_cast<float4 *>(fb)[i] = v;
 }
 
-// camera rays [first, first+count) -> initial routing (FilterRaysLocally: TracerBase.h:319 / DomainTracer.h:148-181)
-__global__ void k_camera_route(FrameParams fp, SceneDev sd, size_t first, size_t count, RayQueue out) {
+// Which film rows a frame call covers (ImageScheduler sharding, ImageTracer.h:111-125): rows
+//   row0 + (b * stride + index) * tile_rows + k,  k < tile_rows, b = 0,1,...   clipped to [row0, row1).
+// stride == 1 gives the contiguous block [row0, row1).
+struct RowTiles {
+  int row0, row1, tile_rows, index, stride;
+};
+__host__ __device__ inline size_t tiles_local_rows(const RowTiles &t) { // rows this shard owns
+  int span = t.row1 - t.row0;
+  if (span <= 0) return 0;
+  int period = t.tile_rows * t.stride;
+  int full = span / period, rem = span - full * period;
+  int extra = rem - t.index * t.tile_rows;
+  extra = extra < 0 ? 0 : (extra > t.tile_rows ? t.tile_rows : extra);
+  return (size_t)full * t.tile_rows + extra;
+}
+
+// camera rays of this shard's rows -> initial routing (FilterRaysLocally: TracerBase.h:319 / DomainTracer.h:148-181)
+__global__ void k_camera_route(FrameParams fp, SceneDev sd, RowTiles tiles, size_t count, RayQueue out) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
   unsigned long long routed = 0;
+  const size_t per_row = (size_t)fp.cam.W * fp.cam.samples * fp.cam.samples;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) {
+    size_t lr = i / per_row, within = i - lr * per_row;
+    size_t b = lr / tiles.tile_rows, k = lr - b * tiles.tile_rows;
+    size_t row = (size_t)tiles.row0 + (b * tiles.stride + tiles.index) * tiles.tile_rows + k;
     Ray r;
-    camera_ray(fp.cam, first + i, r);
+    camera_ray(fp.cam, row * per_row + within, r);
     float t;
     int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, -1, (fp.flags & FLAG_ENTER_INSIDE) != 0, t);
     if (next < 0) continue;
@@ -267,6 +284,7 @@ __global__ void k_route(FrameParams fp, SceneDev sd, RayQueue in, unsigned n, in
 // ---------------------------------------------------------------------------------------------------------
 struct TraceQueues {
   RayQueue in, shq, nxq, mvq, exq;
+  RayQueue fin;   // adapter mode: final state of every input ray, by input slot (Adapter::trace mutates rayList in place)
   unsigned *work; // bundle counter
 };
 
@@ -289,6 +307,8 @@ __global__ void __launch_bounds__(128) k_trace(FrameParams fp, SceneDev sd, Trac
     queue_load(q.in, idx, r, inst);
     const bool born_shadow = (r.type == RAY_SHADOW);
     bool first = true;
+    const int slot = inst; // adapter mode only
+    if (mode == 1) inst = 0;
     for (;;) {
       const Instance in = sd.inst[inst];
       const Blas &bl = sd.blas[in.mesh];
@@ -316,12 +336,14 @@ __global__ void __launch_bounds__(128) k_trace(FrameParams fp, SceneDev sd, Trac
           if (!make_shadow_ray(r, normal, mat, L, light_position(L, fp.seed, r.id, r.depth, li), sh)) continue;
           c_shgen++;
           unsigned pos = queue_reserve(q.shq.count);
-          if (pos < q.shq.cap) queue_store(q.shq, pos, sh, inst);
+          if (pos < q.shq.cap) queue_store(q.shq, pos, sh, mode == 1 ? -1 : inst);
         }
         if (make_bounce(r, normal, fp.seed)) {
           c_sec++;
           unsigned pos = queue_reserve(q.nxq.count);
-          if (pos < q.nxq.cap) queue_store(q.nxq, pos, r, inst);
+          if (pos < q.nxq.cap) queue_store(q.nxq, pos, r, mode == 1 ? slot : inst);
+        } else if (mode == 1 && slot >= 0) {
+          queue_store(q.fin, (unsigned)slot, r, slot);
         }
         break;
       }
@@ -330,7 +352,8 @@ __global__ void __launch_bounds__(128) k_trace(FrameParams fp, SceneDev sd, Trac
       first = false;
       if (mode == 1) { // adapter contract: hand the ray back (localDispatch, :604-609 / :377-381)
         unsigned pos = queue_reserve(q.mvq.count);
-        if (pos < q.mvq.cap) queue_store(q.mvq, pos, r, inst);
+        if (pos < q.mvq.cap) queue_store(q.mvq, pos, r, slot);
+        if (r.type != RAY_SHADOW && slot >= 0) queue_store(q.fin, (unsigned)slot, r, slot);
         break;
       }
       float t;
@@ -391,7 +414,7 @@ __global__ void k_aos_to_soa(const uint4 *aos, unsigned n, RayQueue q, unsigned 
   q.c1[offset + i] = make_float4(u2f(b.x), u2f(b.y), u2f(b.z), u2f(b.w));
   q.c2[offset + i] = make_float4(u2f(c.x), u2f(c.y), u2f(c.z), u2f(c.w));
   q.c3[offset + i] = make_int4((int)d.x, (int)d.y, (int)d.z, (int)d.w);
-  q.inst[offset + i] = inst;
+  q.inst[offset + i] = (inst == -2) ? (int)i : inst; // -2: the column carries the caller's slot index (adapter mode)
 }
 __global__ void k_soa_to_aos(RayQueue q, unsigned n, uint4 *aos) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -425,34 +448,37 @@ __global__ void k_shuffle(FrameParams fp, SceneDev sd, RayQueue in, unsigned n, 
 }
 
 // ---- DomainScheduler exchange helpers (replace SendRays' pack/unpack, DomainTracer.h:370-496) ---------------
+// Wire record = the reference's 80-byte Ray (64-byte payload + 16 pad bytes, DomainTracer.h:444-451); the first pad
+// word carries the target instance id (the reference sends it once per queue as `int queue_id`).
 __global__ void k_export_count(RayQueue ex, const Instance *inst, unsigned *peer_counts) {
   unsigned n = min(*ex.count, ex.cap);
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     atomicAdd(&peer_counts[inst[ex.inst[i]].owner], 1u);
 }
-// pack peer-major into [column][ray] (column stride = stride rays); peer_cursor starts at the exclusive offsets
-__global__ void k_export_pack(RayQueue ex, const Instance *inst, unsigned *peer_cursor, uint4 *packed, int *packed_inst, size_t stride) {
+// pack peer-major; peer_cursor starts at the exclusive offsets of the peer counts
+__global__ void k_export_pack(RayQueue ex, const Instance *inst, unsigned *peer_cursor, uint4 *packed) {
   unsigned n = min(*ex.count, ex.cap);
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int target = ex.inst[i];
     unsigned pos = atomicAdd(&peer_cursor[inst[target].owner], 1u);
-    const uint4 *c0 = reinterpret_cast<const uint4 *>(ex.c0), *c1 = reinterpret_cast<const uint4 *>(ex.c1),
-                *c2 = reinterpret_cast<const uint4 *>(ex.c2), *c3 = reinterpret_cast<const uint4 *>(ex.c3);
-    packed[0 * stride + pos] = c0[i];
-    packed[1 * stride + pos] = c1[i];
-    packed[2 * stride + pos] = c2[i];
-    packed[3 * stride + pos] = c3[i];
-    packed_inst[pos] = target;
+    uint4 *p = packed + 5 * (size_t)pos;
+    p[0] = reinterpret_cast<const uint4 *>(ex.c0)[i];
+    p[1] = reinterpret_cast<const uint4 *>(ex.c1)[i];
+    p[2] = reinterpret_cast<const uint4 *>(ex.c2)[i];
+    p[3] = reinterpret_cast<const uint4 *>(ex.c3)[i];
+    p[4] = make_uint4((unsigned)target, 0u, 0u, 0u);
   }
 }
-__global__ void k_import(const uint4 *packed, const int *packed_inst, size_t stride, unsigned n, RayQueue q, unsigned offset) {
+// unpack n wire records into the queue at [offset, offset+n)
+__global__ void k_import(const uint4 *packed, unsigned n, RayQueue q, unsigned offset) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  reinterpret_cast<uint4 *>(q.c0)[offset + i] = packed[0 * stride + i];
-  reinterpret_cast<uint4 *>(q.c1)[offset + i] = packed[1 * stride + i];
-  reinterpret_cast<uint4 *>(q.c2)[offset + i] = packed[2 * stride + i];
-  reinterpret_cast<uint4 *>(q.c3)[offset + i] = packed[3 * stride + i];
-  q.inst[offset + i] = packed_inst[i];
+  const uint4 *p = packed + 5 * (size_t)i;
+  reinterpret_cast<uint4 *>(q.c0)[offset + i] = p[0];
+  reinterpret_cast<uint4 *>(q.c1)[offset + i] = p[1];
+  reinterpret_cast<uint4 *>(q.c2)[offset + i] = p[2];
+  reinterpret_cast<uint4 *>(q.c3)[offset + i] = p[3];
+  q.inst[offset + i] = (int)p[4].x;
 }
 
 } // namespace gvt

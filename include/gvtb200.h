@@ -119,7 +119,7 @@ typedef struct gvtb200_hit {
 GVTB200_API int gvtb200_intersect(gvtb200_mesh mesh, const gvtb200_ray *rays, size_t n, gvtb200_hit *hits);
 GVTB200_API int gvtb200_occluded(gvtb200_mesh mesh, const gvtb200_ray *rays, size_t n, int32_t *occluded);
 
-/* ---- B2: scene / frame (api/api.h:26-263, Renderer.cpp:37-115, algorithm/*.h) -------------------------- */
+/* ---- B2: scene / frame (api/api.h:26-263, Renderer.cpp:37-115, algorithm/ *.h) -------------------------- */
 GVTB200_API int gvtb200_scene_create(gvtb200_scene *out);
 GVTB200_API int gvtb200_scene_destroy(gvtb200_scene scene);
 /* api::addInstance (api/api.cpp:292-322): the host passes what it stored in the context DB -- mat, matinv,
@@ -175,7 +175,15 @@ typedef struct gvtb200_counters {
 GVTB200_API int gvtb200_render_frame(gvtb200_scene scene, int row0, int row1, float *rgba_out, gvtb200_counters *counters);
 /* same, asynchronous on the scene's stream, nothing copied back (bench / multi-GPU drivers) */
 GVTB200_API int gvtb200_render_frame_async(gvtb200_scene scene, int row0, int row1);
+/* same, for one shard of the film rows (ImageScheduler, algorithm/ImageTracer.h:111-125 slices the ray array per rank):
+ * rows row0 + (b*tile_stride + tile_index)*tile_rows + k, k < tile_rows, b = 0,1,..., clipped to [row0,row1).
+ * tile_stride == 1 is the reference's contiguous slice; interleaved tiles balance the load across GPUs. */
+GVTB200_API int gvtb200_render_frame_tiles(gvtb200_scene scene, int row0, int row1, int tile_rows, int tile_index, int tile_stride);
 GVTB200_API int gvtb200_scene_sync(gvtb200_scene scene);
+/* enqueue the scene's work on a caller-owned CUDA stream (the one NCCL collectives use); NULL = the scene's own */
+GVTB200_API int gvtb200_scene_set_stream(gvtb200_scene scene, void *cuda_stream);
+/* number of kernels this library has launched so far in this process (measurement hook) */
+GVTB200_API unsigned long long gvtb200_launch_count(void);
 GVTB200_API int gvtb200_scene_counters(gvtb200_scene scene, gvtb200_counters *out);
 GVTB200_API int gvtb200_scene_profile_counters(gvtb200_scene scene, int enable);
 /* device pointer of the RGBA float framebuffer (W*H*4) and the CUDA stream the scene launches on, so that
@@ -195,12 +203,13 @@ GVTB200_API int gvtb200_domain_set_owner(gvtb200_scene scene, const int32_t *own
  * empty.  Rays bound for instances owned by other ranks are parked in per-peer export queues. */
 GVTB200_API int gvtb200_domain_begin_frame(gvtb200_scene scene);
 GVTB200_API int gvtb200_domain_drain_local(gvtb200_scene scene);
-/* SendRays phase 1 (:409-415): counts[p] = rays parked for rank p.  phase 2 (:433-463): the rays for all peers
- * packed peer-major as 5 SoA columns (4 x 16 B + next-instance id) in one device buffer laid out
- * [column][ray]; *d_export points at it, column stride = *stride_rays rays. */
-GVTB200_API int gvtb200_domain_export(gvtb200_scene scene, uint32_t *counts, void **d_export, size_t *stride_rays);
-/* unpack n_rays received rays (same layout, column stride stride_rays) into the local queues */
-GVTB200_API int gvtb200_domain_import(gvtb200_scene scene, const void *d_rays, size_t n_rays, size_t stride_rays);
+/* SendRays phase 1 (:409-415): counts[p] = rays parked for rank p (world_size entries).  phase 2 (:433-463): the
+ * parked rays packed peer-major in one DEVICE buffer of 80-byte wire records -- the reference's Ray record
+ * (:444-451) whose first pad word carries the target instance id.  *d_export points at it, *n_total = sum(counts).
+ * The export queue is emptied. */
+GVTB200_API int gvtb200_domain_export(gvtb200_scene scene, uint32_t *counts, void **d_export, size_t *n_total);
+/* unpack n_rays received wire records (device pointer) into the local queues */
+GVTB200_API int gvtb200_domain_import(gvtb200_scene scene, const void *d_rays, size_t n_rays);
 /* rays still queued locally (termination test, DomainTracer.h:339-349) */
 GVTB200_API int gvtb200_domain_pending(gvtb200_scene scene, uint64_t *n);
 

@@ -1,0 +1,183 @@
+// emul_blas.cpp -- TEST INFRASTRUCTURE.  Compiles the product's per-thread device bodies (gravit_b200/csrc/*.h)
+// with g++ (GVT_HD = inline, -ffp-contract=off) and drives them sequentially, so that the BLAS build LOGIC
+// (Morton keys, Karras tree, refit, wide collapse) and the compressed-wide-BVH traversal can be checked against
+// the oracle on a box without a GPU.  Never linked into libgvtb200.so; the product has no CPU path.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../gravit_b200/csrc/bvh_build.h"
+#include "../../gravit_b200/csrc/gvt_device.h"
+#include "../../gravit_b200/csrc/shade.h"
+#include "../../gravit_b200/csrc/traverse.h"
+
+using namespace gvt;
+
+struct EmulMesh {
+  std::vector<float> verts;
+  std::vector<uint32_t> faces;
+  std::vector<uint32_t> keys_unsorted, keys, vals;
+  std::vector<float4> bn_lo, bn_hi;
+  std::vector<int2> bn_child, bn_range;
+  std::vector<int> bn_parent;
+  std::vector<float4> wnodes, wtris;
+  unsigned n_wnodes = 0, n_wtris = 0, depth = 0;
+  Blas blas;
+};
+
+#define EM_API extern "C" __attribute__((visibility("default")))
+
+EM_API void *emul_build(const float *verts, unsigned nv, const uint32_t *faces, unsigned nf) {
+  EmulMesh *m = new EmulMesh();
+  m->verts.assign(verts, verts + 3 * (size_t)nv);
+  m->faces.assign(faces, faces + 3 * (size_t)nf);
+  BuildCtx c;
+  memset(&c, 0, sizeof(c));
+  c.verts = m->verts.data();
+  c.faces = m->faces.data();
+  c.n = nf;
+  V3 lo = v3(FLT_MAX, FLT_MAX, FLT_MAX), hi = v3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+  for (unsigned i = 0; i < nv; ++i) {
+    lo.x = fastmin(lo.x, verts[3 * i]), lo.y = fastmin(lo.y, verts[3 * i + 1]), lo.z = fastmin(lo.z, verts[3 * i + 2]);
+    hi.x = fastmax(hi.x, verts[3 * i]), hi.y = fastmax(hi.y, verts[3 * i + 1]), hi.z = fastmax(hi.z, verts[3 * i + 2]);
+  }
+  c.mlo = lo;
+  c.mext = xsub(hi, lo);
+  c.pad = blas_leaf_pad(c.mext);
+  m->keys.resize(nf), m->vals.resize(nf);
+  c.keys = m->keys.data(), c.vals = m->vals.data();
+  for (unsigned f = 0; f < nf; ++f) tri_setup(c, f);
+  m->keys_unsorted = m->keys;
+  { // stable sort by key (what the LSD radix sort does)
+    std::vector<uint32_t> order(nf);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return m->keys_unsorted[a] < m->keys_unsorted[b]; });
+    for (unsigned i = 0; i < nf; ++i) m->keys[i] = m->keys_unsorted[order[i]], m->vals[i] = order[i];
+  }
+  size_t nb = 2 * (size_t)nf;
+  m->bn_lo.resize(nb), m->bn_hi.resize(nb), m->bn_child.resize(nb), m->bn_range.resize(nb), m->bn_parent.assign(nb, -1);
+  c.bn_lo = m->bn_lo.data(), c.bn_hi = m->bn_hi.data(), c.bn_child = m->bn_child.data(), c.bn_range = m->bn_range.data();
+  c.bn_parent = m->bn_parent.data();
+  for (unsigned k = 0; k < nf; ++k) leaf_setup(c, k);
+  for (unsigned i = 0; i + 1 < nf; ++i) karras_node(c, (int)i);
+  // refit: post-order
+  if (nf > 1) {
+    std::vector<int> stack, order;
+    stack.push_back(0);
+    while (!stack.empty()) {
+      int b = stack.back();
+      stack.pop_back();
+      order.push_back(b);
+      int2 ch = c.bn_child[b];
+      if (ch.x < (int)nf - 1) stack.push_back(ch.x);
+      if (ch.y < (int)nf - 1) stack.push_back(ch.y);
+    }
+    for (size_t i = order.size(); i-- > 0;) {
+      int b = order[i];
+      int2 ch = c.bn_child[b];
+      float4 l0 = c.bn_lo[ch.x], h0 = c.bn_hi[ch.x], l1 = c.bn_lo[ch.y], h1 = c.bn_hi[ch.y];
+      c.bn_lo[b] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
+      c.bn_hi[b] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+    }
+  }
+  // collapse, level by level
+  m->wnodes.assign(5 * (size_t)std::max(1u, nf), make_float4(0, 0, 0, 0));
+  m->wtris.assign(3 * (size_t)std::max(1u, nf), make_float4(0, 0, 0, 0));
+  c.wnodes = m->wnodes.data(), c.wtris = m->wtris.data();
+  unsigned node_count = 1, tri_count = 0;
+  if (nf > 0) {
+    std::vector<CollapseTask> cur, next;
+    CollapseTask root;
+    root.bnode = (nf == 1) ? 0 /* leaf id n-1+0 == 0 */ : 0;
+    root.wnode = 0;
+    cur.push_back(root);
+    while (!cur.empty()) {
+      m->depth++;
+      next.clear();
+      for (auto &t : cur) {
+        int slot_b[8], n_internal, n_leaf_tris;
+        uint32_t meta[8];
+        unsigned qlo[24], qhi[24];
+        float4 w0;
+        collapse_node(c, t, slot_b, n_internal, n_leaf_tris, meta, qlo, qhi, w0);
+        unsigned child_base = node_count, tri_base = tri_count;
+        node_count += n_internal, tri_count += n_leaf_tris;
+        size_t q = next.size();
+        next.resize(q + n_internal);
+        collapse_emit(c, t, slot_b, meta, qlo, qhi, w0, child_base, tri_base, next.data() + q);
+      }
+      cur.swap(next);
+    }
+  }
+  m->n_wnodes = node_count, m->n_wtris = tri_count;
+  memset(&m->blas, 0, sizeof(Blas));
+  m->blas.nodes = m->wnodes.data();
+  m->blas.tris = m->wtris.data();
+  m->blas.n_tris = nf;
+  m->blas.n_nodes = node_count;
+  return m;
+}
+EM_API void emul_destroy(void *p) { delete (EmulMesh *)p; }
+EM_API void emul_morton(void *p, uint32_t *codes, uint32_t *sorted_faces) {
+  EmulMesh *m = (EmulMesh *)p;
+  if (codes) memcpy(codes, m->keys_unsorted.data(), m->keys_unsorted.size() * 4);
+  if (sorted_faces) memcpy(sorted_faces, m->vals.data(), m->vals.size() * 4);
+}
+EM_API void emul_stats(void *p, uint64_t *st) {
+  EmulMesh *m = (EmulMesh *)p;
+  st[0] = m->n_wnodes, st[1] = m->n_wtris, st[2] = m->depth, st[3] = 0;
+}
+struct Ray80 {
+  float o[3], t_min, d[3], t_max, color[3], t;
+  int id, depth;
+  float w;
+  int type;
+  unsigned char pad[16];
+};
+struct HitRec {
+  int prim;
+  float t, u, v;
+};
+// closest hit (any = 0) or any hit (any = 1) of local-space rays; counts[0..1] += nodes visited / triangles tested
+EM_API void emul_intersect(void *p, const void *rays, size_t n, int any, void *hits, uint64_t *counts) {
+  EmulMesh *m = (EmulMesh *)p;
+  const Ray80 *r = (const Ray80 *)rays;
+  HitRec *h = (HitRec *)hits;
+  TravCounters tc;
+  tc.nodes = tc.tris = 0;
+  uint64_t cn = 0, ct = 0;
+  for (size_t i = 0; i < n; ++i) {
+    Hit hit;
+    V3 o = v3(r[i].o[0], r[i].o[1], r[i].o[2]), d = v3(r[i].d[0], r[i].d[1], r[i].d[2]);
+    tc.nodes = tc.tris = 0;
+    if (any)
+      blas_traverse<true, true>(m->blas, o, d, GVT_RAY_EPSILON, FLT_MAX, hit, &tc);
+    else
+      blas_traverse<false, true>(m->blas, o, d, GVT_RAY_EPSILON, FLT_MAX, hit, &tc);
+    cn += tc.nodes, ct += tc.tris;
+    h[i].prim = hit.prim, h[i].t = hit.prim >= 0 ? hit.t : FLT_MAX, h[i].u = hit.u, h[i].v = hit.v;
+  }
+  if (counts) counts[0] += cn, counts[1] += ct;
+}
+
+// camera rays through the product's camera_ray body
+EM_API void emul_camera_rays(const float *eye, const float *u, const float *v, const float *w, const float *scal7, int W, int H,
+                             int samples, int depth, void *out) {
+  Camera c;
+  c.eye = v3(eye[0], eye[1], eye[2]), c.u = v3(u[0], u[1], u[2]), c.v = v3(v[0], v[1], v[2]), c.w = v3(w[0], w[1], w[2]);
+  c.horz = scal7[0], c.vert = scal7[1], c.wmult = scal7[2], c.hmult = scal7[3], c.half_sample = scal7[4], c.offset = scal7[5],
+  c.contri = scal7[6];
+  c.W = W, c.H = H, c.samples = samples, c.depth = depth;
+  Ray80 *o = (Ray80 *)out;
+  size_t n = (size_t)W * H * samples * samples;
+  for (size_t i = 0; i < n; ++i) {
+    Ray r;
+    camera_ray(c, i, r);
+    memset(&o[i], 0, sizeof(Ray80));
+    o[i].o[0] = r.o.x, o[i].o[1] = r.o.y, o[i].o[2] = r.o.z, o[i].t_min = r.t_min;
+    o[i].d[0] = r.d.x, o[i].d[1] = r.d.y, o[i].d[2] = r.d.z, o[i].t_max = r.t_max;
+    o[i].t = r.t, o[i].id = r.id, o[i].depth = r.depth, o[i].w = r.w, o[i].type = r.type;
+  }
+}

@@ -1,0 +1,84 @@
+"""The product's per-thread device bodies (gravit_b200/csrc/*.h) compiled with g++ and driven sequentially
+(tests/emul): Morton keys, LBVH + wide collapse, compressed-wide-BVH traversal and camera rays are checked against the
+oracle on a box without a GPU.  The same checks run against the real kernels in test_gpu_parity.py."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from scenes import library
+from tests.scene_util import oracle_scene, random_rays
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def E(built):
+    L = C.CDLL(os.path.join(HERE, "emul", "libgvt_emul.so"))
+    L.emul_build.restype = C.c_void_p
+    L.emul_build.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
+    L.emul_destroy.argtypes = [C.c_void_p]
+    L.emul_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+    L.emul_morton.argtypes = [C.c_void_p] * 3
+    L.emul_stats.argtypes = [C.c_void_p] * 2
+    return L
+
+
+def _mesh(E, o, d, k=0):
+    nv = len(np.asarray(d.meshes[k].verts).reshape(-1, 3))
+    faces, _, bbox = o.mesh_get(k, nv)
+    v = po.f32(d.meshes[k].verts).reshape(-1, 3)
+    f = np.ascontiguousarray(faces, np.uint32)
+    return C.c_void_p(E.emul_build(po._fp(v), len(v), po._fp(f), len(f))), len(f), bbox
+
+
+@pytest.mark.parametrize("name", ["simple", "bunny_obj", "bunny70k", "sibenik"])
+def test_blas_build_and_traversal_bit_exact(E, name):
+    d = {
+        "simple": lambda: library.simple_scene(96, 96),
+        "bunny_obj": lambda: library.bunny_obj_scene(160, 160),
+        "bunny70k": lambda: library.bunny_scene(160, 90),
+        "sibenik": lambda: library.sibenik_scene(96, 54),
+    }[name]()
+    o = oracle_scene(d)
+    for k in range(len(d.meshes)):
+        h, nf, bbox = _mesh(E, o, d, k)
+        codes, order = np.zeros(nf, np.uint32), np.zeros(nf, np.uint32)
+        E.emul_morton(h, po._fp(codes), po._fp(order))
+        assert np.array_equal(codes, o.morton(k))  # Morton keys bit-exact
+        assert np.array_equal(np.sort(order), np.arange(nf))  # the sort is a permutation ...
+        assert np.all(np.diff(codes[order].astype(np.int64)) >= 0)  # ... into key order
+        st = np.zeros(4, np.uint64)
+        E.emul_stats(h, po._fp(st))
+        assert st[1] == nf  # every triangle is referenced exactly once
+        rays = np.concatenate([o.camera_rays(), random_rays(bbox, 4000, seed=k + 1)])
+        ho = o.intersect(k, rays, threads=4)
+        he = np.zeros(len(rays), po.HIT_DTYPE)
+        E.emul_intersect(h, po._fp(rays), len(rays), 0, po._fp(he), None)
+        assert np.array_equal(ho, he)  # prim, t, u, v bit for bit
+        occ = o.occluded(k, rays, threads=4)
+        ha = np.zeros(len(rays), po.HIT_DTYPE)
+        E.emul_intersect(h, po._fp(rays), len(rays), 1, po._fp(ha), None)
+        assert np.array_equal((ha["prim"] >= 0).astype(np.int32), occ)
+        E.emul_destroy(h)
+
+
+def test_edge_cases(E):
+    # empty mesh, one triangle, two coincident triangles (tie -> smaller primitive id), axis-parallel rays
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], np.float32)
+    rays = np.zeros(4, po.RAY_DTYPE)
+    rays["origin"] = [[0.2, 0.2, 1], [0.2, 0.2, -1], [2, 2, 1], [0.25, 0.25, 1]]
+    rays["direction"] = [[0, 0, -1], [0, 0, 1], [0, 0, -1], [0, 0, -1]]
+    for faces, expect in (
+        (np.zeros((0, 3), np.uint32), [-1, -1, -1, -1]),
+        (np.array([[0, 1, 2]], np.uint32), [0, 0, -1, 0]),
+        (np.array([[0, 1, 2], [0, 1, 2], [0, 1, 2]], np.uint32), [0, 0, -1, 0]),
+        (np.array([[0, 1, 2], [1, 3, 2]], np.uint32), [0, 0, -1, 0]),
+    ):
+        h = C.c_void_p(E.emul_build(po._fp(v), len(v), po._fp(np.ascontiguousarray(faces)), len(faces)))
+        he = np.zeros(len(rays), po.HIT_DTYPE)
+        E.emul_intersect(h, po._fp(rays), len(rays), 0, po._fp(he), None)
+        assert he["prim"].tolist() == expect
+        E.emul_destroy(h)
