@@ -44,7 +44,7 @@ COUNTER_FIELDS = (
 ).split()
 
 PRIMARY, SHADOW, SECONDARY = 0, 1, 2
-FLAG_SMOOTH, FLAG_ENTER_INSIDE = 1, 2
+FLAG_SMOOTH, FLAG_ENTER_INSIDE, FLAG_SHADOW_TO_LIGHT = 1, 2, 8
 SCHEDULE_IMAGE, SCHEDULE_DOMAIN = 0, 1
 ADAPTER_B200 = 8  # gvt::render::adapter::B200 (gravit_b200/host/api.h)
 

@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(128) k_trace(FrameParams fp, SceneDev sd, Trac
       Hit h;
       c_visits++;
       // prepGVT_EMBREE_PACKET_TYPE (EmbreeMeshAdapter.cpp:269-286): tnear = RAY_EPSILON, tfar = FLT_MAX
-      bool hit = (r.type == RAY_SHADOW) ? blas_traverse<true, COUNT>(bl, lo, ld, GVT_RAY_EPSILON, FLT_MAX, h, &tc)
+      const bool to_light = (fp.flags & FLAG_SHADOW_TO_LIGHT) != 0;
+      bool hit = (r.type == RAY_SHADOW) ? blas_traverse<true, COUNT>(bl, lo, ld, GVT_RAY_EPSILON, to_light ? r.t_max : FLT_MAX, h, &tc)
                                         : blas_traverse<false, COUNT>(bl, lo, ld, GVT_RAY_EPSILON, FLT_MAX, h, &tc);
       if (hit) {
         if (r.type == RAY_SHADOW) break; // occluded: dropped (:487-489)
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(128) k_trace(FrameParams fp, SceneDev sd, Trac
         for (int li = 0; li < fp.n_lights; ++li) {
           const Light &L = fp.lights[li];
           Ray sh;
-          if (!make_shadow_ray(r, normal, mat, L, light_position(L, fp.seed, r.id, r.depth, li), sh)) continue;
+          if (!make_shadow_ray(r, normal, mat, L, light_position(L, fp.seed, r.id, r.depth, li), to_light, sh)) continue;
           c_shgen++;
           unsigned pos = queue_reserve(q.shq.count);
           if (pos < q.shq.cap) queue_store(q.shq, pos, sh, mode == 1 ? -1 : inst);

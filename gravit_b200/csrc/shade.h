@@ -143,7 +143,7 @@ GVT_HD void surface_at(const Blas &bl, const Instance &in, const Hit &h, const R
 }
 
 // generateShadowRays for one light (EmbreeMeshAdapter.cpp:320-358).  false = Shade() rejected the light.
-GVT_HD bool make_shadow_ray(const Ray &r, V3 normal, const Mat &mat, const Light &L, V3 lightPos, Ray &sh) {
+GVT_HD bool make_shadow_ray(const Ray &r, V3 normal, const Mat &mat, const Light &L, V3 lightPos, bool to_light, Ray &sh) {
   V3 c;
   if (!shade(mat, r, normal, L, lightPos, c)) return false;
   const float multiplier = xsub(1.0f, xmul(GVT_RAY_EPSILON, 16.f));
@@ -153,7 +153,7 @@ GVT_HD bool make_shadow_ray(const Ray &r, V3 normal, const Mat &mat, const Light
   sh.o = origin;
   sh.d = xnormalize(dir); // Ray ctor, actor/Ray.h:109
   sh.t_min = GVT_RAY_EPSILON;
-  sh.t_max = 3.0f; // glm::vec3::length() == 3 (:347,355)
+  sh.t_max = to_light ? xlength(dir) : 3.0f; // glm::vec3::length() == 3 (:347,355); FLAG_SHADOW_TO_LIGHT: the distance
   sh.t = r.t;
   sh.id = r.id;
   sh.w = r.w;

@@ -71,6 +71,10 @@ enum {
                                     (adapter/embree/EmbreeMeshAdapter.cpp:75,507-524) */
   GVTB200_FLAG_ENTER_INSIDE = 2, /* documented deviation F6: camera rays whose origin is inside an instance box
                                     enter it at t = 0 (reference drops them: actor/RayPacket.h:194) */
+  GVTB200_FLAG_SHADOW_TO_LIGHT = 8, /* documented deviation: shadow rays carry t_max = |light - origin| (what
+                                    EmbreeMeshAdapter.cpp:347 meant; glm::vec3::length() made it 3) and occlusion is tested up
+                                    to the light instead of to infinity (:279).  Off = reference behaviour, under which a
+                                    closed interior such as Sibenik is entirely in shadow. */
 };
 
 enum { GVTB200_SCHEDULE_IMAGE = 0, GVTB200_SCHEDULE_DOMAIN = 1 }; /* scheduler::ScheduleType (Types.h:48-62) */

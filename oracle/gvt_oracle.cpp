@@ -485,7 +485,7 @@ struct TNode {
   int instanceSetIdx = 0, numInstances = 0;
 };
 
-enum { FLAG_SMOOTH = 1, FLAG_ENTER_INSIDE = 2, FLAG_BRUTE = 4 };
+enum { FLAG_SMOOTH = 1, FLAG_ENTER_INSIDE = 2, FLAG_BRUTE = 4, FLAG_SHADOW_TO_LIGHT = 8 };
 
 struct Stats {
   long long camera_rays, routed_initial, adapter_calls, rays_traced, primary_hits, shadow_generated, shadow_unoccluded,
@@ -757,6 +757,9 @@ void traceRange(const Scene &s, int instId, Ray80 *rays, size_t begin, size_t en
   const Mesh &mesh = *s.meshes[in.mesh];
   const bool brute = s.flags & FLAG_BRUTE;
   const bool smooth = s.flags & FLAG_SMOOTH;
+  // documented deviation: occlusion is tested up to the light (t_max = |light - origin|, what
+  // EmbreeMeshAdapter.cpp:347 meant to compute) instead of to infinity; off by default = reference behaviour
+  const bool to_light = s.flags & FLAG_SHADOW_TO_LIGHT;
   for (size_t ri = begin; ri < end; ++ri) {
     Ray80 &r = rays[ri];
     bool first = true;
@@ -764,7 +767,7 @@ void traceRange(const Scene &s, int instId, Ray80 *rays, size_t begin, size_t en
       V3 lo, ld;
       toLocal(in.minv, r.o, r.d, lo, ld);
       // prepGVT_EMBREE_PACKET_TYPE :269-286: tnear=RAY_EPSILON, tfar=FLT_MAX, ray's own t_min/t_max ignored
-      LocalHit h = intersectClosest(mesh, lo, ld, RAY_EPSILON, FLT_MAX, brute);
+      LocalHit h = intersectClosest(mesh, lo, ld, RAY_EPSILON, (to_light && r.type == RAY_SHADOW) ? r.t_max : FLT_MAX, brute);
       if (first && hits) {
         hits[ri].prim = h.prim;
         hits[ri].t = h.prim >= 0 ? h.t : FLT_MAX;
@@ -834,7 +837,7 @@ void traceRange(const Scene &s, int instId, Ray80 *rays, size_t begin, size_t en
         sh.o = origin;
         sh.d = normalize(dir); // Ray ctor actor/Ray.h:109
         sh.t_min = RAY_EPSILON;
-        sh.t_max = 3.0f; // glm::vec3::length() == 3 (Q2), EmbreeMeshAdapter.cpp:347,355
+        sh.t_max = to_light ? length(dir) : 3.0f; // glm::vec3::length() == 3 (Q2), EmbreeMeshAdapter.cpp:347,355
         sh.t = r.t;
         sh.id = r.id;
         sh.w = r.w;
@@ -844,7 +847,7 @@ void traceRange(const Scene &s, int instId, Ray80 *rays, size_t begin, size_t en
         out.shadow_gen++;
         V3 slo, sld;
         toLocal(in.minv, sh.o, sh.d, slo, sld);
-        if (!intersectAny(mesh, slo, sld, RAY_EPSILON, FLT_MAX, brute)) {
+        if (!intersectAny(mesh, slo, sld, RAY_EPSILON, to_light ? sh.t_max : FLT_MAX, brute)) {
           out.shadow_ok++;
           out.moved.push_back(sh);
         }

@@ -30,7 +30,7 @@ assert RAY_DTYPE.itemsize == 80
 HIT_DTYPE = np.dtype([("prim", "<i4"), ("t", "<f4"), ("u", "<f4"), ("v", "<f4")])
 
 PRIMARY, SHADOW, SECONDARY = 0, 1, 2
-FLAG_SMOOTH, FLAG_ENTER_INSIDE, FLAG_BRUTE = 1, 2, 4
+FLAG_SMOOTH, FLAG_ENTER_INSIDE, FLAG_BRUTE, FLAG_SHADOW_TO_LIGHT = 1, 2, 4, 8
 STATS_FIELDS = (
     "camera_rays routed_initial adapter_calls rays_traced primary_hits shadow_generated shadow_unoccluded "
     "secondary_generated fb_adds rounds rays_sent"

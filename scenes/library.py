@@ -132,7 +132,8 @@ def bunny_scene(width=1920, height=1080):
 
 def sibenik_scene(width=1920, height=1080, depth=2, samples=1):
     """BASELINE configs 2/5: sibenik.obj, data/sibenik.conf:2-5 camera; light chosen.
-    The eye is inside the cathedral's box, so FLAG_ENTER_INSIDE (deviation F6) is part of the scene."""
+    The eye is inside the cathedral's box, so FLAG_ENTER_INSIDE (deviation F6) is part of the scene, and so is
+    FLAG_SHADOW_TO_LIGHT: with the reference's occlusion-to-infinity a closed interior is all shadow."""
     a = np.load(os.path.join(ASSETS, "sibenik.npz"))
     d = SceneDesc("sibenik", width=width, height=height)
     d.meshes = [MeshDesc(a["verts"], a["faces"], False, None, a["mats"], a["face_mat"])]
@@ -143,7 +144,7 @@ def sibenik_scene(width=1920, height=1080, depth=2, samples=1):
     d.up = (-0.0997908, 0.995004, 0.00291497)
     d.fov = float(np.float32(60.0 * math.pi / 180.0))
     d.depth, d.samples, d.jitter = depth, samples, 0.0
-    d.flags = 2  # FLAG_ENTER_INSIDE
+    d.flags = 2 | 8  # FLAG_ENTER_INSIDE | FLAG_SHADOW_TO_LIGHT (closed interior: reference semantics leave it black)
     return d
 
 

@@ -185,9 +185,12 @@ def test_frame_multi_light_multi_sample(gpu):
     assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref)) >= 50.0
 
 
-def test_frame_sibenik_inside_box_and_bounces(gpu):
-    """Config 2: camera inside the instance box (deviation F6), per-face materials, shadow + 1 bounce."""
+@pytest.mark.parametrize("flags", [2, 2 | 8])
+def test_frame_sibenik_inside_box_and_bounces(gpu, flags):
+    """Config 2: camera inside the instance box (deviation F6), per-face materials, shadow + 1 bounce; with the
+    reference's occlusion-to-infinity (flags 2: the closed interior is all shadow) and with FLAG_SHADOW_TO_LIGHT."""
     d = library.sibenik_scene(384, 216, depth=2)
+    d.flags = flags
     o, s, e = _pair(gpu, d)
     ref, st = o.render(threads=8)
     fb = s.render()
@@ -196,7 +199,11 @@ def test_frame_sibenik_inside_box_and_bounces(gpu):
     assert abs(ctr["primary_hits"] - st["primary_hits"]) <= 1e-3 * st["primary_hits"]
     assert abs(ctr["secondary_generated"] - st["secondary_generated"]) <= 1e-3 * st["secondary_generated"] + 2  # same counter-based RNG
     assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref)) >= 50.0
+    assert abs(ctr["shadow_unoccluded"] - st["shadow_unoccluded"]) <= 1e-3 * st["shadow_unoccluded"] + 2
+    if flags & 8:
+        assert st["shadow_unoccluded"] > 0.2 * st["shadow_generated"]
     d1 = library.sibenik_scene(384, 216, depth=1)
+    d1.flags = flags
     o1, s1, e1 = _pair(gpu, d1)
     ref1, _ = o1.render(threads=8)
     assert np.array_equal(s1.render(), ref1)
