@@ -91,3 +91,16 @@ def test_degenerate_faces_are_dropped(built):
     s.add_mesh(v, t)
     faces, _, _ = s.mesh_get(0, 4)
     assert faces.tolist() == [[0, 1, 2]]  # faces 2 and 3 have two identical positions (Mesh.cpp:107-109)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present on this box")
+def test_reference_side_adapter_shim_compiles_against_gravit_headers(tmp_path):
+    """B200MeshAdapter.h is written against GraviT's own Adapter.h / Mesh.h / Light.h."""
+    import subprocess
+
+    src = tmp_path / "shim_check.cpp"
+    src.write_text('#include "B200MeshAdapter.h"\nint main() { return 0; }\n')
+    cmd = ["g++", "-std=c++11", "-fsyntax-only", "-w", "-I/root/reference/src", "-I/root/reference/third-party/glm",
+           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "gravit_b200", "host", "gvt_shim"), str(src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[:2000]

@@ -1,0 +1,95 @@
+"""Host logic of the multi-GPU drivers on CPU: world_size 2, gloo backend, no GPU.
+
+Covers the ImageScheduler row sharding (every film row owned exactly once, matches the kernel's RowTiles arithmetic),
+the DomainScheduler ownership map, and the SendRays replacement (count exchange, 80-byte wire-record exchange,
+termination all-reduce) with synthetic ray records standing in for the engine's export/import buffers."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gravit_b200 import schedulers
+
+
+def test_row_shards_partition_the_film():
+    for H, world, tile in ((1080, 8, 8), (1080, 3, 16), (17, 4, 8), (5, 8, 8), (2160, 2, 1)):
+        seen = np.zeros(H, np.int32)
+        for r in range(world):
+            rows = schedulers.shard_rows(H, r, world, tile)
+            seen[rows] += 1
+            # the kernel's closed form (kernels.cuh tiles_local_rows)
+            period, full, rem = tile * world, H // (tile * world), H % (tile * world)
+            extra = min(tile, max(0, rem - r * tile))
+            assert len(rows) == full * tile + extra
+        assert np.all(seen == 1)
+
+
+def test_domain_owner_round_robin():
+    assert schedulers.domain_owner(8, 8).tolist() == list(range(8))
+    assert schedulers.domain_owner(5, 2).tolist() == [0, 1, 0, 1, 0]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(100 + rank)
+        # three exchange rounds with shrinking traffic, then termination
+        inbox_total = 0
+        rounds = 0
+        n_out = [7 + 3 * rank, 2, 0]
+        for k in range(10):
+            n = n_out[k] if k < len(n_out) else 0
+            dest = rng.integers(0, world, n)
+            dest = dest[dest != rank] if n else dest
+            recs = np.zeros((len(dest), schedulers.WIRE_BYTES), np.uint8)
+            recs[:, 0] = rank  # sender tag
+            recs[:, 1] = dest
+            recs[:, 64] = 40 + dest  # "target instance id" in the first pad word
+            order = np.argsort(dest, kind="stable")  # peer-major, as gvtb200_domain_export packs them
+            recs, dest = recs[order], dest[order]
+            counts = np.bincount(dest, minlength=world)
+            recv_counts = schedulers.exchange_counts(dist, counts, "cpu")
+            total = torch.tensor([len(dest)], dtype=torch.int64)
+            dist.all_reduce(total)
+            if int(total) == 0:
+                break
+            got = schedulers.exchange_rays(dist, torch.from_numpy(recs), counts, recv_counts).numpy()
+            assert got.shape == (int(recv_counts.sum()), schedulers.WIRE_BYTES)
+            assert np.all(got[:, 1] == rank) and np.all(got[:, 64] == 40 + rank)  # every record reached its owner
+            # peer-major arrival order
+            assert np.all(np.diff(got[:, 0].astype(int)) >= 0)
+            inbox_total += len(got)
+            rounds += 1
+        sent = torch.tensor([sum(1 for _ in range(0))], dtype=torch.int64)
+        out.put((rank, rounds, inbox_total))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_and_termination_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1] == 2  # both ranks agree on the number of exchange rounds
+    assert res[0][2] + res[1][2] > 0
