@@ -497,3 +497,47 @@ class GvtScene:
 
     def writeimage(self, path):
         acheck(self.A.gvtapi_writeimage(b"Renderer", path.encode()))
+
+
+class StandaloneScene(EngineScene):
+    """A gvtb200_scene built directly through the C ABI (no api:: database): several of these can live in one process,
+    e.g. one per simulated DomainScheduler rank.  `meshes` are Mesh objects (None = not resident on this rank),
+    `instances` is a list of (mesh index, m16, minv16, normi9, box6) as api::addInstance stores them."""
+
+    def __init__(self, meshes, instances, lights, camera, film, flags=0, seed=0, owner=None, rank=0, world=1):
+        init(_inited if _inited is not None else 0)
+        h = C.c_void_p()
+        check(lib().gvtb200_scene_create(C.byref(h)))
+        super().__init__(h.value)
+        self._keep = meshes
+        self.n_inst = len(instances)
+        for mi, m, minv, normi, box in instances:
+            mesh = meshes[mi]
+            box = f32(box)
+            check(
+                lib().gvtb200_scene_add_instance(
+                    self.h, mesh.h if mesh is not None else None, _fp(f32(m)), _fp(f32(minv)), _fp(f32(normi)), _fp(box[:3].copy()), _fp(box[3:].copy())
+                )
+            )
+        ls = np.ascontiguousarray(lights, dtype=LIGHT_DTYPE)
+        check(lib().gvtb200_scene_set_lights(self.h, _fp(ls), len(ls)))
+        eye, focus, up, fov, depth, samples, jitter = camera
+        check(lib().gvtb200_scene_set_camera(self.h, _fp(f32(eye)), _fp(f32(focus)), _fp(f32(up)), fov, depth, samples, jitter))
+        self.W, self.H = film
+        check(lib().gvtb200_scene_set_film(self.h, self.W, self.H))
+        check(lib().gvtb200_scene_set_flags(self.h, flags, seed))
+        if owner is not None:
+            o = np.ascontiguousarray(owner, dtype=np.int32)
+            check(lib().gvtb200_domain_set_owner(self.h, _fp(o), len(o), rank, world))
+        check(lib().gvtb200_scene_commit(self.h))
+
+    def close(self):
+        if self.h:
+            lib().gvtb200_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

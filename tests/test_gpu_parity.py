@@ -265,3 +265,84 @@ def test_full_size_properties(gpu):
     assert np.array_equal(top + bot, fb) and not top[540:].any() and not bot[:540].any()
     # the 512x512 oracle-checked frame is a crop-independent check of the same mesh: hit fraction is similar
     assert 0.05 < c["primary_hits"] / c["camera_rays"] < 0.5
+
+
+def _standalone_ranks(g, d, flags, world):
+    """One engine scene per simulated rank on the same GPU: rank r holds only the meshes of the instances it owns."""
+    host = library.apply(d, g.GvtScene(flags=flags))  # host layer: Mesh::addFace filter, normals, addInstance matrices
+    owner = np.arange(len(d.instances)) % world  # DomainTracer.h:115-144 with one location per mesh
+    lights = np.array([g.point_light(p, c) for p, c in d.lights], g.LIGHT_DTYPE)
+    inst = [(mi,) + tuple(host.instance_get(i)) for i, (mi, _) in enumerate(d.instances)]
+    ranks = []
+    for r in range(world):
+        meshes = []
+        for k, m in enumerate(d.meshes):
+            needed = any(owner[i] == r and mi == k for i, (mi, _) in enumerate(d.instances))
+            if not needed:
+                meshes.append(None)
+                continue
+            nv = len(np.asarray(m.verts).reshape(-1, 3))
+            faces, normals, _ = host.mesh_get(k, nv)
+            meshes.append(g.Mesh(m.verts, faces, normals=normals, material=(0, tuple(m.kd or (0.5, 0.5, 0.5)), (0.5, 0.5, 0.5), 1.0)))
+        cam = (d.eye, d.focus, d.up, d.fov, d.depth, d.samples, d.jitter)
+        ranks.append(g.StandaloneScene(meshes, inst, lights, cam, (d.width, d.height), flags=flags, owner=owner, rank=r, world=world))
+    return ranks, owner
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_domain_scheduler_simulated_ranks(gpu, world):
+    """Tracer<DomainScheduler> (DomainTracer.h:185-496) with P ranks simulated on one GPU: per-round ray-routing count
+    matrices equal the oracle's bit for bit, and the composited image equals the single-process image."""
+    import torch
+
+    g = gpu
+    d = library.simple_scene(256, 256)
+    flags = 1
+    o = oracle_scene(d, flags)
+    o.set_owner(np.arange(len(d.instances)) % world)
+    ref, st = o.render(schedule=1, world_size=world, threads=8)
+    log_o = o.route_log(world)
+    ref1, _ = o.render(schedule=0, world_size=1, threads=8)
+    ranks, owner = _standalone_ranks(g, d, flags, world)
+    for e in ranks:
+        e.domain_begin_frame()
+    log_g = []
+    for rnd in range(100):
+        sends = []
+        for e in ranks:
+            e.domain_drain_local()
+            counts, ptr, n = e.domain_export(world)
+            # copy the wire records out before the next export reuses the buffer
+            buf = torch.empty((n, 80), dtype=torch.uint8, device="cuda")
+            if n:
+                from gravit_b200 import schedulers
+
+                buf.copy_(schedulers.device_tensor(ptr, (n, 80), "|u1"))
+            sends.append((counts, buf))
+        mat = np.stack([c for c, _ in sends]).astype(np.int64)
+        if mat.sum() == 0:
+            break
+        log_g.append(mat)
+        for dst, e in enumerate(ranks):
+            parts = []
+            for src, (counts, buf) in enumerate(sends):
+                off = int(counts[:dst].sum())
+                parts.append(buf[off : off + int(counts[dst])])
+            inbox = torch.cat(parts) if parts else None
+            torch.cuda.synchronize()
+            if inbox is not None and inbox.shape[0]:
+                inbox = inbox.contiguous()
+                e.domain_import(inbox.data_ptr(), inbox.shape[0])
+    log_o = [m for m in log_o if m.sum() > 0]  # the oracle also logs the final all-zero round (termination test)
+    assert len(log_g) == len(log_o) and len(log_g) >= 1
+    for a, b in zip(log_g, log_o):
+        assert np.array_equal(a, b)  # ray-routing counts, per round, per (src, dst)
+    fb = np.zeros((d.height, d.width, 4), np.float32)
+    for e in ranks:
+        e.sync()
+        fb += e.fb_read(d.width, d.height)
+    fb[..., :3] = np.minimum(fb[..., :3], 1.0)
+    assert np.allclose(fb, ref, atol=1e-6) and np.allclose(fb, ref1, atol=1e-6)
+    assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref1)) >= 50.0
+    for e in ranks:
+        e.close()
