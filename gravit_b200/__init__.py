@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgvtb200.so")
+LIB_PATH = os.environ.get("GVTB200_LIB_PATH") or os.path.join(HERE, "libgvtb200.so")  # the override is a measurement hook (kernel variants)
 API_PATH = os.path.join(HERE, "libgvtb200_api.so")
 
 # gvt::render::actor::Ray (actor/Ray.h:68-95): 64-byte payload in an 80-byte record
@@ -40,7 +40,7 @@ LIGHT_DTYPE = np.dtype(
 MATERIAL_DTYPE = np.dtype([("type", "<i4"), ("kd", "<f4", 3), ("ks", "<f4", 3), ("alpha", "<f4")])
 COUNTER_FIELDS = (
     "camera_rays routed_initial primary_hits shadow_generated shadow_unoccluded secondary_generated fb_adds "
-    "instance_visits nodes_visited tris_tested rays_exported reserved"
+    "instance_visits nodes_visited tris_tested rays_exported stack_overflows"
 ).split()
 
 PRIMARY, SHADOW, SECONDARY = 0, 1, 2
@@ -50,7 +50,7 @@ ADAPTER_B200 = 8  # gvt::render::adapter::B200 (gravit_b200/host/api.h)
 
 # every symbol include/gvtb200.h declares (tests check that the library exports all of them)
 C_ABI_SYMBOLS = (
-    "gvtb200_init gvtb200_last_error gvtb200_device_info gvtb200_mesh_create gvtb200_mesh_destroy gvtb200_mesh_morton "
+    "gvtb200_init gvtb200_last_error gvtb200_device_info gvtb200_set_tuning gvtb200_mesh_create gvtb200_mesh_destroy gvtb200_mesh_morton "
     "gvtb200_mesh_stats gvtb200_trace gvtb200_intersect gvtb200_occluded gvtb200_scene_create gvtb200_scene_destroy "
     "gvtb200_scene_add_instance gvtb200_scene_set_lights gvtb200_scene_set_camera gvtb200_scene_set_film "
     "gvtb200_scene_set_flags gvtb200_scene_commit gvtb200_scene_tlas_order gvtb200_camera_rays gvtb200_route "
@@ -88,6 +88,7 @@ def lib():
         vp, sz, i32, u32, f = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_float
         L.gvtb200_init.argtypes = [i32]
         L.gvtb200_device_info.argtypes = [vp, vp, vp, vp]
+        L.gvtb200_set_tuning.argtypes = [i32, i32, i32]
         L.gvtb200_mesh_create.argtypes = [vp, u32, vp, u32, vp, vp, vp, u32, vp, vp, vp]
         L.gvtb200_mesh_destroy.argtypes = [vp]
         L.gvtb200_mesh_morton.argtypes = [vp, vp, vp]

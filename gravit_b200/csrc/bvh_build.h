@@ -4,8 +4,8 @@
 //   leaf_setup  : sorted leaf boxes                                            (one thread per sorted face)
 //   karras_node : binary radix tree over the sorted keys (Karras, HPG 2012)    (one thread per internal node)
 //   refit_up    : bottom-up AABB fit with one atomic flag per internal node    (one thread per leaf)
-//   collapse    : binary tree -> 8-wide compressed nodes with quantised child boxes, surface-area-greedy child
-//                 expansion, octant-ordered slots; triangles re-laid per wide node     (one thread per wide node,
+//   collapse    : binary tree -> 8-wide compressed nodes (128 bytes, 7-bit quantised child boxes), surface-area-greedy
+//                 child expansion, octant-ordered slots; triangles re-laid per wide node  (one thread per wide node,
 //                 level by level through a task queue)
 // Replaces Embree's rtcNewTriangleMesh + rtcCommit (adapter/embree/EmbreeMeshAdapter.cpp:125-162).
 #pragma once
@@ -28,9 +28,9 @@ struct BuildCtx {
   int2 *bn_range;
   unsigned *bn_flag;
   // wide output
-  float4 *wnodes; // 5 per node
-  float4 *wtris;  // 3 per triangle
-  unsigned *node_count, *tri_count;
+  float4 *wnodes; // GVT_NODE_WORDS per node
+  float4 *wtris;  // 3 per triangle record slot (GVT_LEAF_MAX slots per leaf child)
+  unsigned *node_count, *tri_count, *tri_real; // wide nodes, triangle record slots, triangles referenced
   unsigned wnode_cap;
 };
 
@@ -119,7 +119,21 @@ GVT_HD void karras_node(const BuildCtx &c, int i) {
 }
 
 // ---- wide-node collapse ------------------------------------------------------------------------------------
-#define GVT_LEAF_MAX 3 /* triangles per leaf child (unary count in 3 meta bits) */
+// Wide node = 128 bytes = one cache line = eight 16-byte words (coalesced LDG.128 each):
+//   u0: frame origin.xyz (fp32), {ex, ey, ez, imask} bytes   e* = biased exponent of 128 * grid step; imask bit s = slot s
+//                                                            holds an internal child
+//   u1: child_base, tri_base, tmask, 0                       tmask bit 8k+s = slot s is a leaf with more than k triangles
+//   u2: x lo-planes, u3: x hi-planes, u4/u5: y, u6/u7: z     word j of a block = field(slot j) << 16 | field(slot j+4)
+// A plane is a 7-bit grid coordinate q stored as the 16-bit field 0x3F80 | q -- the upper half of the float 1 + q/128 --
+// so that the traversal gets the value of slot j for free (the word itself, read as a float; the lower field adds a known
+// 0.249 quantum) and the value of slot j+4 with one shift: no integer-to-float conversion, no byte extraction
+// (traverse.h node_step).  Internal children of a node are stored consecutively from child_base in slot order; the
+// triangles of its leaf children (at most GVT_LEAF_MAX each) are stored from tri_base, three record slots per leaf in slot
+// order.  Compressed wide BVH after Ylitie, Karras, Laine (HPG 2017), re-laid for sm_100's ALU/FMA pipe balance.
+// Triangle record = 48 bytes: {v0.xyz, prim id}, {e1.xyz, 0}, {e2.xyz, 0} with e1 = v1 - v0, e2 = v2 - v0.
+#define GVT_LEAF_MAX 3 /* triangles per leaf child */
+#define GVT_NODE_WORDS 8 /* 16-byte words per wide node */
+#define GVT_QMAX 127
 
 GVT_HD float box_area(float4 lo, float4 hi) {
   float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
@@ -135,15 +149,17 @@ GVT_HD int bnode_first(const BuildCtx &c, int b) {
   return c.bn_range[b].x;
 }
 
-// biased exponent e such that 255 * 2^(e-127) >= ext (smallest such), clamped to [1,254]
+#define GVT_QPAD 0.02f /* the node frame starts this many grid steps below the children's minimum, so that the conservative
+                          rounding margins of the planes are never eaten by the clamp to the grid */
+// biased exponent e such that (GVT_QMAX - 0.2) * 2^(e-127) >= ext (smallest such), clamped to [1,247]
 GVT_HD uint32_t quant_exponent(float ext) {
   if (!(ext > 0.f)) return 1u;
-  float s = ext * (1.0f / 255.0f) * 1.0001f; // a little slack so that ceil() never needs 256
+  float s = ext * (1.0f / ((float)GVT_QMAX - 0.2f)) * 1.0001f; // room for GVT_QPAD and the margins below GVT_QMAX
   uint32_t u = f2u(s);
   uint32_t e = (u >> 23) & 0xFFu;
   if (u & 0x7FFFFFu) e += 1u; // round up to the next power of two
   if (e < 1u) e = 1u;
-  if (e > 254u) e = 254u;
+  if (e > 247u) e = 247u;
   return e;
 }
 
@@ -152,11 +168,19 @@ struct CollapseTask {
   int wnode; // index of the wide node to write
 };
 
-// Builds wide node t.wnode from binary subtree t.bnode.  Children that stay internal are appended to `out`
-// (returns how many).  Host emulation and the device kernel share this body; the device kernel reserves the
-// output range with one atomicAdd.
-GVT_HD int collapse_node(const BuildCtx &c, CollapseTask t, int *slot_b /*[8]*/, int &n_internal, int &n_leaf_tris,
-                         uint32_t *meta /*[8]*/, unsigned *qlo /*[8][3]*/, unsigned *qhi /*[8][3]*/, float4 &w0) {
+struct WideNode { // what collapse_node decides, before the output ranges are known
+  int slot_b[8];      // binary node per slot, -1 = empty
+  int cnt[8];         // triangles of a leaf slot, 0 for internal / empty slots
+  unsigned qlo[8][3]; // quantised planes
+  unsigned qhi[8][3];
+  uint32_t imask, tmask;
+  int n_internal, n_leaves, n_tris;
+  float4 w0;
+};
+
+// Builds wide node t.wnode from binary subtree t.bnode.  Host emulation and the device kernel share this body; the
+// device kernel reserves the output ranges with atomicAdd.
+GVT_HD void collapse_node(const BuildCtx &c, CollapseTask t, WideNode &w) {
   // 1. gather up to 8 children: repeatedly open the child with the largest surface area that holds more than
   //    GVT_LEAF_MAX triangles
   int ch[8];
@@ -190,6 +214,7 @@ GVT_HD int collapse_node(const BuildCtx &c, CollapseTask t, int *slot_b /*[8]*/,
   }
   uint32_t ex = quant_exponent(hi.x - lo.x), ey = quant_exponent(hi.y - lo.y), ez = quant_exponent(hi.z - lo.z);
   float isx = 1.0f / u2f(ex << 23), isy = 1.0f / u2f(ey << 23), isz = 1.0f / u2f(ez << 23);
+  lo.x -= GVT_QPAD * u2f(ex << 23), lo.y -= GVT_QPAD * u2f(ey << 23), lo.z -= GVT_QPAD * u2f(ez << 23);
   // 3. slot assignment: slot s bit2/bit1/bit0 = child sits towards +x/+y/+z of the node centre, so that
   //    visiting slots in descending (s ^ (7 - ray octant)) order is front to back.  Greedy max-cost matching.
   float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
@@ -199,7 +224,7 @@ GVT_HD int collapse_node(const BuildCtx &c, CollapseTask t, int *slot_b /*[8]*/,
     float dx = 0.5f * (l.x + h.x) - cx, dy = 0.5f * (l.y + h.y) - cy, dz = 0.5f * (l.z + h.z) - cz;
     for (int s = 0; s < 8; ++s) cost[i][s] = ((s & 4) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 1) ? dz : -dz);
   }
-  for (int s = 0; s < 8; ++s) slot_b[s] = -1;
+  for (int s = 0; s < 8; ++s) w.slot_b[s] = -1;
   bool used[8] = { false, false, false, false, false, false, false, false };
   for (int k = 0; k < nch; ++k) {
     int bi = -1, bs = -1;
@@ -207,82 +232,79 @@ GVT_HD int collapse_node(const BuildCtx &c, CollapseTask t, int *slot_b /*[8]*/,
     for (int i = 0; i < nch; ++i) {
       if (used[i]) continue;
       for (int s = 0; s < 8; ++s) {
-        if (slot_b[s] >= 0) continue;
+        if (w.slot_b[s] >= 0) continue;
         if (cost[i][s] > bc) bc = cost[i][s], bi = i, bs = s;
       }
     }
     used[bi] = true;
-    slot_b[bs] = ch[bi];
+    w.slot_b[bs] = ch[bi];
   }
-  // 4. meta + quantised boxes
-  uint32_t imask = 0;
-  n_internal = 0, n_leaf_tris = 0;
+  // 4. masks + quantised boxes
+  w.imask = 0, w.tmask = 0;
+  w.n_internal = 0, w.n_leaves = 0, w.n_tris = 0;
   for (int s = 0; s < 8; ++s) {
-    meta[s] = 0;
-    qlo[3 * s] = qlo[3 * s + 1] = qlo[3 * s + 2] = 255u; // empty slot: inverted box
-    qhi[3 * s] = qhi[3 * s + 1] = qhi[3 * s + 2] = 0u;
-    int b = slot_b[s];
+    w.cnt[s] = 0;
+    w.qlo[s][0] = w.qlo[s][1] = w.qlo[s][2] = GVT_QMAX; // empty slot: inverted box
+    w.qhi[s][0] = w.qhi[s][1] = w.qhi[s][2] = 0u;
+    int b = w.slot_b[s];
     if (b < 0) continue;
     int cnt = bnode_count(c, b);
     if (cnt > GVT_LEAF_MAX) {
-      imask |= 1u << s;
-      meta[s] = (1u << 5) | (24u + (uint32_t)s);
-      n_internal++;
+      w.imask |= 1u << s;
+      w.n_internal++;
     } else {
-      uint32_t unary = (cnt == 1) ? 1u : (cnt == 2 ? 3u : 7u);
-      meta[s] = (unary << 5) | (uint32_t)n_leaf_tris;
-      n_leaf_tris += cnt;
+      w.cnt[s] = cnt;
+      for (int k = 0; k < cnt; ++k) w.tmask |= 1u << (8 * k + s);
+      w.n_leaves++;
+      w.n_tris += cnt;
     }
     float4 l = c.bn_lo[b], h = c.bn_hi[b];
-    // conservative: floor/ceil with a 2e-3 grid-step margin, clamped to the byte range
-    float fx = floorf((l.x - lo.x) * isx - 2e-3f), fy = floorf((l.y - lo.y) * isy - 2e-3f), fz = floorf((l.z - lo.z) * isz - 2e-3f);
-    float gx = ceilf((h.x - lo.x) * isx + 2e-3f), gy = ceilf((h.y - lo.y) * isy + 2e-3f), gz = ceilf((h.z - lo.z) * isz + 2e-3f);
-    qlo[3 * s] = (unsigned)fminf(fmaxf(fx, 0.f), 255.f), qlo[3 * s + 1] = (unsigned)fminf(fmaxf(fy, 0.f), 255.f),
-            qlo[3 * s + 2] = (unsigned)fminf(fmaxf(fz, 0.f), 255.f);
-    qhi[3 * s] = (unsigned)fminf(fmaxf(gx, 0.f), 255.f), qhi[3 * s + 1] = (unsigned)fminf(fmaxf(gy, 0.f), 255.f),
-            qhi[3 * s + 2] = (unsigned)fminf(fmaxf(gz, 0.f), 255.f);
+    // conservative: floor/ceil with a 4e-3 grid-step margin (covers the rounding of the traversal's dequantisation
+    // constants, traverse.h node_step); the clamp to the grid never binds (GVT_QPAD, quant_exponent)
+    const float qm = (float)GVT_QMAX;
+    float fx = floorf((l.x - lo.x) * isx - 4e-3f), fy = floorf((l.y - lo.y) * isy - 4e-3f), fz = floorf((l.z - lo.z) * isz - 4e-3f);
+    float gx = ceilf((h.x - lo.x) * isx + 4e-3f), gy = ceilf((h.y - lo.y) * isy + 4e-3f), gz = ceilf((h.z - lo.z) * isz + 4e-3f);
+    w.qlo[s][0] = (unsigned)fminf(fmaxf(fx, 0.f), qm), w.qlo[s][1] = (unsigned)fminf(fmaxf(fy, 0.f), qm), w.qlo[s][2] = (unsigned)fminf(fmaxf(fz, 0.f), qm);
+    w.qhi[s][0] = (unsigned)fminf(fmaxf(gx, 0.f), qm), w.qhi[s][1] = (unsigned)fminf(fmaxf(gy, 0.f), qm), w.qhi[s][2] = (unsigned)fminf(fmaxf(gz, 0.f), qm);
   }
-  w0 = make_float4(lo.x, lo.y, lo.z, u2f(ex | (ey << 8) | (ez << 16) | (imask << 24)));
-  return nch;
+  // the stored exponent is that of 128 grid steps (the traversal multiplies it with the float 1 + q/128)
+  w.w0 = make_float4(lo.x, lo.y, lo.z, u2f((ex + 7u) | ((ey + 7u) << 8) | ((ez + 7u) << 16) | (w.imask << 24)));
 }
 
-GVT_HD uint32_t pack4(const unsigned *q, int base, int comp) {
-  return (q[3 * (base + 0) + comp] & 0xFFu) | ((q[3 * (base + 1) + comp] & 0xFFu) << 8) | ((q[3 * (base + 2) + comp] & 0xFFu) << 16) |
-         ((q[3 * (base + 3) + comp] & 0xFFu) << 24);
+GVT_HD uint32_t plane_word(const unsigned q[8][3], int j, int comp) {
+  return ((0x3F80u | (q[j][comp] & 0x7Fu)) << 16) | (0x3F80u | (q[j + 4][comp] & 0x7Fu));
 }
 
 // writes the node words and this node's triangle records; child tasks go to out[0..n_internal)
-GVT_HD void collapse_emit(const BuildCtx &c, CollapseTask t, const int *slot_b, const uint32_t *meta, const unsigned *qlo,
-                          const unsigned *qhi, float4 w0, unsigned child_base, unsigned tri_base, CollapseTask *out) {
-  float4 *nd = c.wnodes + 5 * (size_t)t.wnode;
-  nd[0] = w0;
-  uint32_t m0 = meta[0] | (meta[1] << 8) | (meta[2] << 16) | (meta[3] << 24);
-  uint32_t m1 = meta[4] | (meta[5] << 8) | (meta[6] << 16) | (meta[7] << 24);
-  nd[1] = make_float4(u2f(child_base), u2f(tri_base), u2f(m0), u2f(m1));
-  nd[2] = make_float4(u2f(pack4(qlo, 0, 0)), u2f(pack4(qlo, 4, 0)), u2f(pack4(qlo, 0, 1)), u2f(pack4(qlo, 4, 1)));
-  nd[3] = make_float4(u2f(pack4(qlo, 0, 2)), u2f(pack4(qlo, 4, 2)), u2f(pack4(qhi, 0, 0)), u2f(pack4(qhi, 4, 0)));
-  nd[4] = make_float4(u2f(pack4(qhi, 0, 1)), u2f(pack4(qhi, 4, 1)), u2f(pack4(qhi, 0, 2)), u2f(pack4(qhi, 4, 2)));
-  int ki = 0;
+GVT_HD void collapse_emit(const BuildCtx &c, CollapseTask t, const WideNode &w, unsigned child_base, unsigned tri_base, CollapseTask *out) {
+  uint4 *nd = reinterpret_cast<uint4 *>(c.wnodes) + GVT_NODE_WORDS * (size_t)t.wnode;
+  nd[0] = make_uint4(f2u(w.w0.x), f2u(w.w0.y), f2u(w.w0.z), f2u(w.w0.w));
+  nd[1] = make_uint4(child_base, tri_base, w.tmask, 0u);
+  for (int comp = 0; comp < 3; ++comp) {
+    nd[2 + 2 * comp] = make_uint4(plane_word(w.qlo, 0, comp), plane_word(w.qlo, 1, comp), plane_word(w.qlo, 2, comp), plane_word(w.qlo, 3, comp));
+    nd[3 + 2 * comp] = make_uint4(plane_word(w.qhi, 0, comp), plane_word(w.qhi, 1, comp), plane_word(w.qhi, 2, comp), plane_word(w.qhi, 3, comp));
+  }
+  int ki = 0, leaf_rank = 0;
   for (int s = 0; s < 8; ++s) {
-    int b = slot_b[s];
+    int b = w.slot_b[s];
     if (b < 0) continue;
-    if (bnode_count(c, b) > GVT_LEAF_MAX) { // internal child -> next level task
+    if (w.cnt[s] == 0) { // internal child -> next level task
       out[ki].bnode = b;
       out[ki].wnode = (int)child_base + ki;
       ki++;
     } else {
-      int first = bnode_first(c, b), cnt = bnode_count(c, b);
-      unsigned off = meta[s] & 0x1Fu;
-      for (int k = 0; k < cnt; ++k) {
+      int first = bnode_first(c, b);
+      for (int k = 0; k < w.cnt[s]; ++k) {
         unsigned f = c.vals[first + k];
         V3 a, bb, d;
         tri_verts(c, f, a, bb, d);
         V3 e1 = xsub(bb, a), e2 = xsub(d, a);
-        float4 *tr = c.wtris + 3 * (size_t)(tri_base + off + k);
+        float4 *tr = c.wtris + 3 * (size_t)(tri_base + GVT_LEAF_MAX * leaf_rank + k);
         tr[0] = make_float4(a.x, a.y, a.z, u2f(f));
         tr[1] = make_float4(e1.x, e1.y, e1.z, 0.f);
         tr[2] = make_float4(e2.x, e2.y, e2.z, 0.f);
       }
+      leaf_rank++;
     }
   }
 }

@@ -57,13 +57,14 @@ template <class T> void dfree(T *&p) {
 // ---- SoA ray queue storage --------------------------------------------------------------------------------
 struct QueueMem {
   RayQueue q;
+  int4 *hit = nullptr; // extra 16-byte column (hit queues only)
   void *slab = nullptr;
   QueueMem() { memset(&q, 0, sizeof(q)); }
-  cudaError_t ensure(size_t cap) {
+  cudaError_t ensure(size_t cap, bool with_hit = false) {
     if (cap < 32) cap = 32;
-    if (slab && q.cap >= cap) return cudaSuccess;
+    if (slab && q.cap >= cap && (!with_hit || hit)) return cudaSuccess;
     release();
-    size_t bytes = cap * 68 + 256;
+    size_t bytes = cap * (with_hit ? 84 : 68) + 256;
     cudaError_t e = cudaMalloc(&slab, bytes);
     if (e != cudaSuccess) {
       slab = nullptr;
@@ -75,6 +76,7 @@ struct QueueMem {
     q.c1 = (float4 *)p, p += cap * 16;
     q.c2 = (float4 *)p, p += cap * 16;
     q.c3 = (int4 *)p, p += cap * 16;
+    if (with_hit) hit = (int4 *)p, p += cap * 16;
     q.inst = (int *)p;
     q.cap = (unsigned)cap;
     return cudaMemset(q.count, 0, 256);
@@ -82,6 +84,7 @@ struct QueueMem {
   void release() {
     if (slab) cudaFree(slab);
     slab = nullptr;
+    hit = nullptr;
     memset(&q, 0, sizeof(q));
   }
 };
@@ -120,6 +123,7 @@ struct gvtb200_mesh_s {
   uint32_t *d_keys_unsorted = nullptr, *d_sorted_faces = nullptr;
   Blas blas;
   uint64_t stats[4] = { 0, 0, 0, 0 };
+  size_t tri_slots = 0; // 48-byte triangle record slots (GVT_LEAF_MAX per leaf child)
   // adapter-mode (B1) working set, created on first use
   cudaStream_t stream = nullptr;
   Instance *d_inst = nullptr;
@@ -128,7 +132,7 @@ struct gvtb200_mesh_s {
   unsigned *d_work = nullptr;
   uint4 *d_aos = nullptr;
   size_t aos_cap = 0;
-  QueueMem q_in, q_nx, q_sh, q_mv, q_fin;
+  QueueMem q_in, q_nx, q_sh, q_mv, q_fin, q_hit;
   int4 *d_hits = nullptr;
   size_t hits_cap = 0;
 };
@@ -171,7 +175,7 @@ struct gvtb200_scene_s {
   size_t fb_pix = 0;
   DevCounters *d_ctr = nullptr;
   unsigned *d_work = nullptr, *d_peer = nullptr;
-  QueueMem q_a, q_b, q_sh, q_ex, q_tmp;
+  QueueMem q_a, q_b, q_sh, q_ex, q_tmp, q_hit;
   uint4 *d_export = nullptr;
   size_t export_cap = 0;
   int *d_next = nullptr;
@@ -203,15 +207,18 @@ int scan_inplace(unsigned *d, size_t n, std::vector<unsigned *> &levels, size_t 
   return 0;
 }
 
+TraceTune g_tune = { 8, 12, 2 };
+
 int trace_grid(bool count) {
   int idx = count ? 1 : 0;
   if (!g_trace_blocks_per_sm[idx]) {
     int nb = 0;
     if (count)
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true>, 128, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true>, TRACE_THREADS, 0);
     else
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false>, 128, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false>, TRACE_THREADS, 0);
     g_trace_blocks_per_sm[idx] = std::max(1, nb);
+    if (const char *e = getenv("GVTB200_TRACE_BLOCKS_PER_SM")) g_trace_blocks_per_sm[idx] = std::max(1, std::min(nb, atoi(e)));
   }
   return g_sms * g_trace_blocks_per_sm[idx];
 }
@@ -220,9 +227,13 @@ void launch_trace(bool count, const FrameParams &fp, const SceneDev &sd, const T
   int grid = trace_grid(count);
   LAUNCHED(1);
   if (count)
-    k_trace<true><<<grid, 128, 0, st>>>(fp, sd, tq, mode);
+    k_trace<true><<<grid, TRACE_THREADS, 0, st>>>(fp, sd, tq, mode, g_tune);
   else
-    k_trace<false><<<grid, 128, 0, st>>>(fp, sd, tq, mode);
+    k_trace<false><<<grid, TRACE_THREADS, 0, st>>>(fp, sd, tq, mode, g_tune);
+}
+void launch_shade(const FrameParams &fp, const SceneDev &sd, const ShadeQueues &sq, int mode, cudaStream_t st) {
+  LAUNCHED(1);
+  k_shade<<<g_sms * 8, 256, 0, st>>>(fp, sd, sq, mode);
 }
 
 RayQueue null_queue(unsigned *count) {
@@ -395,11 +406,22 @@ int gvtb200_init(int device) {
   g_sms = p.multiProcessorCount;
   g_device = device;
   g_trace_blocks_per_sm[0] = g_trace_blocks_per_sm[1] = 0;
+  if (const char *e = getenv("GVTB200_TUNE")) { // "refill_at,exit_at,postpone_num" (measurement hook)
+    int a = 0, b = 0, c = 0;
+    if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && gvtb200_set_tuning(a, b, c)) return GVTB200_ERR_INVALID;
+  }
   CU(cudaFree(0));
   return GVTB200_OK;
 }
 
 const char *gvtb200_last_error(void) { return t_err.c_str(); }
+
+int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num) {
+  if (refill_at < 1 || refill_at > 32 || exit_at < 1 || exit_at > 32 || postpone_num < 0 || postpone_num > 8)
+    return fail(GVTB200_ERR_INVALID, "tuning out of range: refill_at %d exit_at %d (1..32), postpone_num %d (0..8)", refill_at, exit_at, postpone_num);
+  g_tune.refill_at = refill_at, g_tune.exit_at = exit_at, g_tune.postpone_num = postpone_num;
+  return GVTB200_OK;
+}
 
 int gvtb200_device_info(int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor) {
   NEED_INIT();
@@ -420,7 +442,7 @@ int gvtb200_mesh_destroy(gvtb200_mesh m) {
   dfree(m->d_nodes), dfree(m->d_tris), dfree(m->d_normals), dfree(m->d_vcolors), dfree(m->d_mats), dfree(m->d_faces);
   dfree(m->d_keys_unsorted), dfree(m->d_sorted_faces);
   dfree(m->d_inst), dfree(m->d_blas), dfree(m->d_ctr), dfree(m->d_work), dfree(m->d_aos), dfree(m->d_hits);
-  m->q_in.release(), m->q_nx.release(), m->q_sh.release(), m->q_mv.release(), m->q_fin.release();
+  m->q_in.release(), m->q_nx.release(), m->q_sh.release(), m->q_mv.release(), m->q_fin.release(), m->q_hit.release();
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
   return GVTB200_OK;
@@ -434,7 +456,7 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
   float *d_verts = nullptr;
   uint32_t *d_faces3 = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_keys2 = nullptr, *d_vals2 = nullptr;
   unsigned *d_hist = nullptr, *d_flag = nullptr, *d_counts = nullptr;
-  float4 *bn_lo = nullptr, *bn_hi = nullptr, *wnodes = nullptr;
+  float4 *bn_lo = nullptr, *bn_hi = nullptr, *wnodes = nullptr, *wtris = nullptr;
   int2 *bn_child = nullptr, *bn_range = nullptr;
   int *bn_parent = nullptr;
   CollapseTask *d_ta = nullptr, *d_tb = nullptr;
@@ -442,7 +464,7 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
   int rc = GVTB200_OK;
   auto cleanup = [&]() {
     dfree(d_verts), dfree(d_faces3), dfree(d_keys), dfree(d_vals), dfree(d_keys2), dfree(d_vals2), dfree(d_hist), dfree(d_flag);
-    dfree(d_counts), dfree(bn_lo), dfree(bn_hi), dfree(wnodes), dfree(bn_child), dfree(bn_range), dfree(bn_parent), dfree(d_ta), dfree(d_tb);
+    dfree(d_counts), dfree(bn_lo), dfree(bn_hi), dfree(wnodes), dfree(wtris), dfree(bn_child), dfree(bn_range), dfree(bn_parent), dfree(d_ta), dfree(d_tb);
     for (auto *p : scan_levels) cudaFree(p);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
   };
@@ -506,10 +528,12 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
       k_refit<<<blocks_for(n, 256), 256, 0, st>>>(c);
     }
     // collapse into 8-wide compressed nodes, one level per launch
-    CUB(dalloc(&wnodes, 5 * n));
-    CUB(dalloc(&m->d_tris, 3 * n));
+    // worst case: one wide node per face, GVT_LEAF_MAX record slots per single-triangle leaf; shrunk below
+    CUB(dalloc(&wnodes, GVT_NODE_WORDS * n));
+    CUB(dalloc(&wtris, 3 * GVT_LEAF_MAX * n));
+    CUB(cudaMemsetAsync(wtris, 0, 3 * GVT_LEAF_MAX * n * sizeof(float4), st));
     CUB(dalloc(&d_ta, n)); CUB(dalloc(&d_tb, n));
-    c.wnodes = wnodes, c.wtris = m->d_tris, c.node_count = d_counts, c.tri_count = d_counts + 1, c.wnode_cap = nf;
+    c.wnodes = wnodes, c.wtris = wtris, c.node_count = d_counts, c.tri_count = d_counts + 1, c.tri_real = d_counts + 3, c.wnode_cap = nf;
     unsigned init[4] = { 1u, 0u, 0u, 0u };
     CUB(cudaMemcpyAsync(d_counts, init, 16, cudaMemcpyHostToDevice, st));
     CollapseTask root;
@@ -524,14 +548,18 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
       CUB(cudaStreamSynchronize(st));
       std::swap(d_ta, d_tb);
     }
-    unsigned fin[2];
-    CUB(cudaMemcpyAsync(fin, d_counts, 8, cudaMemcpyDeviceToHost, st));
+    unsigned fin[4];
+    CUB(cudaMemcpyAsync(fin, d_counts, 16, cudaMemcpyDeviceToHost, st));
     CUB(cudaStreamSynchronize(st));
-    n_wnodes = fin[0], n_wtris = fin[1];
-    CUB(dalloc(&m->d_nodes, 5 * (size_t)n_wnodes));
-    CUB(cudaMemcpyAsync(m->d_nodes, wnodes, 80 * (size_t)n_wnodes, cudaMemcpyDeviceToDevice, st));
+    n_wnodes = fin[0], n_wtris = fin[3];
+    const size_t n_slots = std::max<size_t>(fin[1], 1);
+    CUB(dalloc(&m->d_nodes, GVT_NODE_WORDS * (size_t)n_wnodes));
+    CUB(cudaMemcpyAsync(m->d_nodes, wnodes, GVT_NODE_WORDS * sizeof(float4) * (size_t)n_wnodes, cudaMemcpyDeviceToDevice, st));
+    CUB(dalloc(&m->d_tris, 3 * n_slots));
+    CUB(cudaMemcpyAsync(m->d_tris, wtris, 3 * sizeof(float4) * n_slots, cudaMemcpyDeviceToDevice, st));
+    m->tri_slots = n_slots;
   } else {
-    CUB(dalloc(&m->d_nodes, 5));
+    CUB(dalloc(&m->d_nodes, GVT_NODE_WORDS));
     CUB(dalloc(&m->d_tris, 3));
     n_wnodes = 0;
   }
@@ -713,16 +741,24 @@ int gvtb200_trace(gvtb200_mesh m, gvtb200_ray *rays, size_t n_rays, size_t begin
   const size_t mv_need = n * (size_t)(1 + n_lights * max_depth);
   CU(m->q_mv.ensure(std::min<size_t>(mv_need, std::max<size_t>(moved_cap, n))));
   CU(cudaMemsetAsync(m->q_mv.q.count, 0, 4, st));
+  CU(m->q_hit.ensure(n, true));
   TraceQueues tq;
+  ShadeQueues sq;
   QueueMem *qa = &m->q_in, *qb = &m->q_nx;
   for (int wave = 0; wave < max_depth; ++wave) {
     CU(cudaMemsetAsync(m->d_work, 0, 8, st));
     CU(cudaMemsetAsync(qb->q.count, 0, 4, st));
     CU(cudaMemsetAsync(m->q_sh.q.count, 0, 4, st));
-    tq.in = qa->q, tq.shq = m->q_sh.q, tq.nxq = qb->q, tq.mvq = m->q_mv.q, tq.exq = null_queue(m->d_work + 2), tq.fin = m->q_fin.q;
+    CU(cudaMemsetAsync(m->q_hit.q.count, 0, 4, st));
+    // closest-hit wave: misses -> moved, hits -> hit queue
+    tq.in = qa->q, tq.hq = m->q_hit.q, tq.hit = m->q_hit.hit, tq.mvq = m->q_mv.q, tq.exq = null_queue(m->d_work + 2), tq.fin = m->q_fin.q;
     tq.work = m->d_work;
     launch_trace(false, fp, sd, tq, 1, st);
-    tq.in = m->q_sh.q, tq.shq = null_queue(m->d_work + 3), tq.nxq = null_queue(m->d_work + 4), tq.work = m->d_work + 1;
+    // shading: shadow rays -> q_sh, bounces -> qb, final states -> fin
+    sq.hq = m->q_hit.q, sq.hit = m->q_hit.hit, sq.shq = m->q_sh.q, sq.nxq = qb->q, sq.fin = m->q_fin.q;
+    launch_shade(fp, sd, sq, 1, st);
+    // shadow wave: unoccluded -> moved
+    tq.in = m->q_sh.q, tq.hq = null_queue(m->d_work + 3), tq.hit = nullptr, tq.work = m->d_work + 1;
     launch_trace(false, fp, sd, tq, 1, st);
     std::swap(qa, qb);
   }
@@ -780,7 +816,7 @@ int gvtb200_scene_destroy(gvtb200_scene s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   dfree(s->d_inst), dfree(s->d_blas), dfree(s->d_tnodes), dfree(s->d_tboxes), dfree(s->d_fb), dfree(s->d_ctr), dfree(s->d_work), dfree(s->d_peer);
   dfree(s->d_export), dfree(s->d_next), dfree(s->d_t), dfree(s->d_aos);
-  s->q_a.release(), s->q_b.release(), s->q_sh.release(), s->q_ex.release(), s->q_tmp.release();
+  s->q_a.release(), s->q_b.release(), s->q_sh.release(), s->q_ex.release(), s->q_tmp.release(), s->q_hit.release();
   for (auto &e : s->ev)
     if (e) cudaEventDestroy(e);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -1027,16 +1063,20 @@ int gvtb200_framebuffer_read(gvtb200_scene s, float *rgba, size_t n_floats) {
 static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool timed) {
   SceneDev sd = scene_dev(*s);
   TraceQueues tq;
+  ShadeQueues sq;
   for (int wave = 0; wave < waves; ++wave) {
     CU(cudaMemsetAsync(s->d_work, 0, 32, s->stream));
     CU(cudaMemsetAsync(s->q_b.q.count, 0, 4, s->stream));
     CU(cudaMemsetAsync(s->q_sh.q.count, 0, 4, s->stream));
-    tq.in = s->q_a.q, tq.shq = s->q_sh.q, tq.nxq = s->q_b.q, tq.mvq = null_queue(s->d_work + 2), tq.exq = s->q_ex.q;
+    CU(cudaMemsetAsync(s->q_hit.q.count, 0, 4, s->stream));
+    tq.in = s->q_a.q, tq.hq = s->q_hit.q, tq.hit = s->q_hit.hit, tq.mvq = null_queue(s->d_work + 2), tq.exq = s->q_ex.q;
     tq.fin = null_queue(s->d_work + 5), tq.work = s->d_work;
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[2], s->stream));
     launch_trace(s->profile, fp, sd, tq, 0, s->stream);
+    sq.hq = s->q_hit.q, sq.hit = s->q_hit.hit, sq.shq = s->q_sh.q, sq.nxq = s->q_b.q, sq.fin = null_queue(s->d_work + 5);
+    launch_shade(fp, sd, sq, 0, s->stream);
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[3], s->stream));
-    tq.in = s->q_sh.q, tq.shq = null_queue(s->d_work + 3), tq.nxq = null_queue(s->d_work + 4), tq.work = s->d_work + 1;
+    tq.in = s->q_sh.q, tq.hq = null_queue(s->d_work + 3), tq.hit = nullptr, tq.work = s->d_work + 1;
     launch_trace(s->profile, fp, sd, tq, 0, s->stream);
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[4], s->stream));
     std::swap(s->q_a, s->q_b);
@@ -1050,6 +1090,7 @@ static int frame_queues(gvtb200_scene s, size_t count) {
   CU(s->q_a.ensure(count));
   CU(s->q_b.ensure(s->depth > 1 ? count : 32));
   CU(s->q_sh.ensure(count * nl));
+  CU(s->q_hit.ensure(count, true));
   CU(s->q_ex.ensure(s->world > 1 ? count : 32));
   return 0;
 }
@@ -1239,6 +1280,7 @@ int gvtb200_domain_import(gvtb200_scene s, const void *d_rays, size_t n_rays) {
     CU(s->q_a.ensure(n_rays));
     CU(s->q_b.ensure(s->depth > 1 ? n_rays : 32));
     CU(s->q_sh.ensure(n_rays * std::max<size_t>(1, s->lights.size())));
+    CU(s->q_hit.ensure(n_rays, true));
   }
   k_import<<<blocks_for(n_rays, 256), 256, 0, st>>>((const uint4 *)d_rays, (unsigned)n_rays, s->q_a.q, have);
   unsigned total = have + (unsigned)n_rays;

@@ -53,15 +53,13 @@ __global__ void k_collapse(BuildCtx c, const CollapseTask *in, unsigned n_in, Co
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_in) return;
   CollapseTask t = in[i];
-  int slot_b[8], n_internal, n_leaf_tris;
-  uint32_t meta[8];
-  unsigned qlo[24], qhi[24];
-  float4 w0;
-  collapse_node(c, t, slot_b, n_internal, n_leaf_tris, meta, qlo, qhi, w0);
-  unsigned child_base = n_internal ? atomicAdd(c.node_count, (unsigned)n_internal) : 0u;
-  unsigned tri_base = n_leaf_tris ? atomicAdd(c.tri_count, (unsigned)n_leaf_tris) : 0u;
-  unsigned qpos = n_internal ? atomicAdd(n_out, (unsigned)n_internal) : 0u;
-  collapse_emit(c, t, slot_b, meta, qlo, qhi, w0, child_base, tri_base, out + qpos);
+  WideNode w;
+  collapse_node(c, t, w);
+  unsigned child_base = w.n_internal ? atomicAdd(c.node_count, (unsigned)w.n_internal) : 0u;
+  unsigned tri_base = w.n_leaves ? atomicAdd(c.tri_count, (unsigned)(GVT_LEAF_MAX * w.n_leaves)) : 0u;
+  unsigned qpos = w.n_internal ? atomicAdd(n_out, (unsigned)w.n_internal) : 0u;
+  if (w.n_tris) atomicAdd(c.tri_real, (unsigned)w.n_tris);
+  collapse_emit(c, t, w, child_base, tri_base, out + qpos);
 }
 
 // ---- LSD radix sort, 8 bits per pass, stable; keys + values (uint32) ---------------------------------------
@@ -273,120 +271,288 @@ __global__ void k_route(FrameParams fp, SceneDev sd, RayQueue in, unsigned n, in
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// The hot kernel.  Persistent CTAs; each warp pulls bundles of 32 queued rays from a global counter and runs
-// every ray to the end of its current life: trace in its instance (closest hit, or any hit for shadow rays);
-// on a miss, route to the next instance (from = this one), advance the origin, continue; on a hit, shade, emit
-// shadow rays (one per light) into `shq` and, if the bounce survives, the secondary ray into `nxq`.
-// This is Adapter::trace + shuffleRays (EmbreeMeshAdapter.cpp:436-623 + TracerBase.h:325-414) fused per ray.
+// The hot kernels: k_trace (traversal + routing) and k_shade (shading + ray generation).  Together they are
+// Adapter::trace + shuffleRays (EmbreeMeshAdapter.cpp:436-623 + TracerBase.h:325-414).
+//
+// k_trace: persistent CTAs.  Every lane owns one ray at a time and runs it to the end of its current life: trace in
+// its instance (closest hit, or any hit for shadow rays); on a miss, route to the next instance (from = this one),
+// advance the origin and carry on; a closest hit is appended -- ray + hit record -- to the hit queue `hq` for k_shade;
+// an occluded shadow ray is dropped; a shadow ray that leaves the scene adds its colour to the framebuffer.
+// The warp runs in lock step over "iterations" (one node visit, then triangle tests) so that
+//   * lanes whose ray is finished are refilled from the input queue as soon as `refill_at` lanes are waiting
+//     (one atomic per refill), instead of idling until the slowest ray of a 32-ray bundle ends, and
+//   * triangle tests are postponed (the triangle group goes onto the traversal stack) while fewer than
+//     postpone_num/8 of the traversing lanes have a triangle to test,
+// after Ylitie, Karras, Laine (HPG 2017) sections 4.3-4.4.  The traversal stack lives in shared memory
+// (TRACE_SM_STACK entries per lane, conflict-free 8-byte accesses) and spills to local memory beyond that.
 //   mode 0: scheduler mode (two-level, as above)
 //   mode 1: adapter mode (Adapter::trace contract): a ray that misses is appended to `mvq` instead of being routed
 // DomainScheduler: a ray routed to an instance owned by another rank is parked in `exq` (inst column = instance).
 // ---------------------------------------------------------------------------------------------------------
+#define TRACE_THREADS 128
+#define TRACE_SM_STACK 12
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 6 /* CTAs per SM the register allocation is bounded for */
+#endif
+
+struct TraceTune {
+  int refill_at;    // refill when at least this many lanes are idle (1..32)
+  int exit_at;      // leave the traversal loop when at least this many lanes are not traversing and work is waiting
+  int postpone_num; // postpone triangle tests while lanes_with_triangles * 8 < traversing_lanes * postpone_num
+};
+
 struct TraceQueues {
-  RayQueue in, shq, nxq, mvq, exq;
+  RayQueue in;
+  RayQueue hq;    // closest hits: ray (t = hit t) + hit column
+  int4 *hit;      // hit column of hq: prim, triangle slot, u bits, v bits
+  RayQueue mvq, exq;
   RayQueue fin;   // adapter mode: final state of every input ray, by input slot (Adapter::trace mutates rayList in place)
-  unsigned *work; // bundle counter
+  unsigned *work; // input cursor
+};
+struct ShadeQueues {
+  RayQueue hq;
+  const int4 *hit;
+  RayQueue shq, nxq, fin;
+};
+
+struct SmemStack {
+  uint2 *s; // entry k of this lane at s[k * TRACE_THREADS]
+  uint2 l[GVT_BLAS_STACK - TRACE_SM_STACK];
+  bool overflow;
+  __device__ __forceinline__ void push(int &sp, uint2 v) {
+    if (sp < TRACE_SM_STACK)
+      s[sp * TRACE_THREADS] = v;
+    else if (sp < GVT_BLAS_STACK)
+      l[sp - TRACE_SM_STACK] = v;
+    else {
+      overflow = true;
+      return;
+    }
+    ++sp;
+  }
+  __device__ __forceinline__ uint2 pop(int &sp) {
+    --sp;
+    return sp < TRACE_SM_STACK ? s[sp * TRACE_THREADS] : l[sp - TRACE_SM_STACK];
+  }
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(FrameParams fp, SceneDev sd, TraceQueues q, int mode) {
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(FrameParams fp, SceneDev sd, TraceQueues q, int mode, TraceTune tune) {
+  __shared__ uint2 s_stack[TRACE_SM_STACK * TRACE_THREADS];
+  __shared__ unsigned char s_lut[8 * 256]; // best_slot(hits8, octinv)
+  for (unsigned k = threadIdx.x; k < 8u * 256u; k += TRACE_THREADS) s_lut[k] = (unsigned char)best_slot(k & 255u, k >> 8);
+  __syncthreads();
+  const unsigned FULL = 0xffffffffu;
   const unsigned n = min(*q.in.count, q.in.cap);
   const unsigned lane = threadIdx.x & 31;
-  unsigned long long c_visits = 0, c_hits = 0, c_shgen = 0, c_shok = 0, c_sec = 0, c_fb = 0, c_exp = 0;
+  const unsigned ltmask = (1u << lane) - 1u;
+  const bool to_light = (fp.flags & FLAG_SHADOW_TO_LIGHT) != 0;
+  unsigned long long c_visits = 0, c_shok = 0, c_fb = 0, c_exp = 0, c_ovf = 0;
   TravCounters tc;
   tc.nodes = 0, tc.tris = 0;
+  SmemStack stack;
+  stack.s = s_stack + threadIdx.x;
+  stack.overflow = false;
+
+  // the lane's ray
+  bool active = false, first = true, any = false;
+  bool exhausted = false; // warp-uniform: the input queue has been handed out
+  unsigned idx = 0;
+  int inst = 0, type = 0;
+  V3 o = v3(0.f, 0.f, 0.f), d = o;
+  float t_min = 0.f, t_max = 0.f, tfar = FLT_MAX;
+  const float4 *nodes = nullptr, *tris = nullptr;
+  RayLocal rl;
+  Trav tv;
+  ray_local(rl, o, o);
+  trav_begin(tv, 0u, 0.f);
+
+  auto begin_instance = [&]() {
+    const Instance in = sd.inst[inst];
+    const Blas &bl = sd.blas[in.mesh];
+    V3 lo, ld;
+    to_local(in, o, d, lo, ld);
+    ray_local(rl, lo, ld);
+    nodes = bl.nodes, tris = bl.tris;
+    // prepGVT_EMBREE_PACKET_TYPE (EmbreeMeshAdapter.cpp:269-286): tnear = RAY_EPSILON, tfar = FLT_MAX
+    tfar = (any && to_light) ? t_max : FLT_MAX;
+    trav_begin(tv, bl.n_tris, tfar);
+    c_visits++;
+  };
+  auto reload = [&](Ray &r) { // the columns k_trace does not keep in registers
+    const float4 c2 = q.in.c2[idx];
+    const int4 c3 = q.in.c3[idx];
+    r.o = o, r.t_min = t_min, r.d = d, r.t_max = t_max;
+    r.color = v3(c2.x, c2.y, c2.z), r.t = c2.w;
+    r.id = c3.x, r.depth = c3.y, r.w = u2f((uint32_t)c3.z), r.type = c3.w;
+  };
+
   for (;;) {
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(q.work, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;
-    unsigned idx = base + lane;
-    if (idx >= n) continue;
-    Ray r;
-    int inst;
-    queue_load(q.in, idx, r, inst);
-    const bool born_shadow = (r.type == RAY_SHADOW);
-    bool first = true;
-    const int slot = inst; // adapter mode only
-    if (mode == 1) inst = 0;
+    // ---- refill idle lanes from the input queue --------------------------------------------------------
+    unsigned idle = __ballot_sync(FULL, !active);
+    if (idle != 0u && !exhausted && (idle == FULL || __popc(idle) >= tune.refill_at)) {
+      const unsigned cnt = (unsigned)__popc(idle);
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(q.work, cnt);
+      base = __shfl_sync(FULL, base, 0);
+      if (base + cnt >= n) exhausted = true;
+      if (!active) {
+        const unsigned my = base + (unsigned)__popc(idle & ltmask);
+        if (my < n) {
+          idx = my;
+          const float4 c0 = q.in.c0[idx], c1 = q.in.c1[idx];
+          type = q.in.c3[idx].w;
+          inst = (mode == 1) ? 0 : q.in.inst[idx];
+          o = v3(c0.x, c0.y, c0.z), t_min = c0.w, d = v3(c1.x, c1.y, c1.z), t_max = c1.w;
+          any = (type == RAY_SHADOW);
+          first = true;
+          active = true;
+          begin_instance();
+        }
+      }
+      idle = __ballot_sync(FULL, !active);
+    }
+    if (idle == FULL) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- traverse in lock step ---------------------------------------------------------------------------
+    bool done = false;
     for (;;) {
-      const Instance in = sd.inst[inst];
-      const Blas &bl = sd.blas[in.mesh];
-      V3 lo, ld;
-      to_local(in, r.o, r.d, lo, ld);
-      Hit h;
-      c_visits++;
-      // prepGVT_EMBREE_PACKET_TYPE (EmbreeMeshAdapter.cpp:269-286): tnear = RAY_EPSILON, tfar = FLT_MAX
-      const bool to_light = (fp.flags & FLAG_SHADOW_TO_LIGHT) != 0;
-      bool hit = (r.type == RAY_SHADOW) ? blas_traverse<true, COUNT>(bl, lo, ld, GVT_RAY_EPSILON, to_light ? r.t_max : FLT_MAX, h, &tc)
-                                        : blas_traverse<false, COUNT>(bl, lo, ld, GVT_RAY_EPSILON, FLT_MAX, h, &tc);
-      if (hit) {
-        if (r.type == RAY_SHADOW) break; // occluded: dropped (:487-489)
-        c_hits++;
-        r.t = h.t;
-        V3 normal;
-        Mat mat;
-        surface_at(bl, in, h, r, fp.flags, normal, mat);
-        if (r.type == RAY_SECONDARY) { // :572-575
-          float tt = (h.t > 1.f) ? xdiv(1.f, h.t) : h.t;
-          r.w = xmul(r.w, tt);
+      const bool trav = active && !done;
+      const unsigned tm = __ballot_sync(FULL, trav);
+      if (tm == 0u) break;
+      const unsigned waiting = 32u - (unsigned)__popc(tm);
+      if (waiting >= (unsigned)tune.exit_at && ((~tm & ~idle) != 0u || !exhausted)) break;
+      if (trav && trav_has_nodes(tv)) node_step<COUNT, true>(nodes, rl, GVT_RAY_EPSILON, tv, stack, &tc, s_lut);
+      for (;;) {
+        const bool ht = trav && !done && trav_has_tris(tv);
+        const unsigned tb = __ballot_sync(FULL, ht);
+        if (tb == 0u) break;
+        if (__popc(tb) * 8 < __popc(tm) * tune.postpone_num) {
+          // too few lanes have a triangle: lanes with node work postpone theirs, the others keep it pending
+          if (ht && trav_has_nodes(tv)) {
+            stack.push(tv.sp, tv.tg);
+            tv.tg.y &= 0xFF000000u;
+          }
+          break;
         }
-        for (int li = 0; li < fp.n_lights; ++li) {
-          const Light &L = fp.lights[li];
-          Ray sh;
-          if (!make_shadow_ray(r, normal, mat, L, light_position(L, fp.seed, r.id, r.depth, li), to_light, sh)) continue;
-          c_shgen++;
-          unsigned pos = queue_reserve(q.shq.count);
-          if (pos < q.shq.cap) queue_store(q.shq, pos, sh, mode == 1 ? -1 : inst);
+        if (ht) done = tri_step<COUNT>(tris, rl, GVT_RAY_EPSILON, tfar, any, tv, &tc);
+      }
+      if (trav && !done) done = !trav_next(tv, stack);
+    }
+    // ---- rays that finished their instance -------------------------------------------------------------------
+    if (active && done) {
+      if (tv.hit.prim >= 0) {
+        if (type != RAY_SHADOW) { // closest hit -> k_shade; an occluded shadow ray is dropped (:487-489)
+          Ray r;
+          reload(r);
+          r.t = tv.hit.t;
+          const unsigned pos = queue_reserve(q.hq.count);
+          if (pos < q.hq.cap) {
+            queue_store(q.hq, pos, r, mode == 1 ? q.in.inst[idx] : inst);
+            q.hit[pos] = make_int4(tv.hit.prim, tv.hit.slot, (int)f2u(tv.hit.u), (int)f2u(tv.hit.v));
+          }
         }
-        if (make_bounce(r, normal, fp.seed)) {
-          c_sec++;
-          unsigned pos = queue_reserve(q.nxq.count);
-          if (pos < q.nxq.cap) queue_store(q.nxq, pos, r, mode == 1 ? slot : inst);
-        } else if (mode == 1 && slot >= 0) {
-          queue_store(q.fin, (unsigned)slot, r, slot);
+        active = false;
+      } else {
+        if (any && first) c_shok++;
+        first = false;
+        if (mode == 1) { // adapter contract: hand the ray back (localDispatch, :604-609 / :377-381)
+          Ray r;
+          reload(r);
+          const int slot = q.in.inst[idx];
+          const unsigned pos = queue_reserve(q.mvq.count);
+          if (pos < q.mvq.cap) queue_store(q.mvq, pos, r, slot);
+          if (type != RAY_SHADOW && slot >= 0) queue_store(q.fin, (unsigned)slot, r, slot);
+          active = false;
+        } else {
+          float t;
+          const int next = tlas_route(sd.tlas, o, d, t_max, inst, false, t);
+          if (next < 0) {
+            if (type == RAY_SHADOW) { // TracerBase.h:396-399
+              Ray r;
+              reload(r);
+              if (xlength(r.color) > 0.f) {
+                fb_add(sd.fb, r.id, xmul(r.color, r.w));
+                c_fb++;
+              }
+            }
+            active = false;
+          } else {
+            o = xadd(o, xmul(d, xmul(t, 0.95f))); // TracerBase.h:394
+            if (fp.world > 1 && sd.inst[next].owner != fp.rank) {
+              Ray r;
+              reload(r);
+              const unsigned pos = queue_reserve(q.exq.count);
+              if (pos < q.exq.cap) queue_store(q.exq, pos, r, next);
+              c_exp++;
+              active = false;
+            } else {
+              inst = next;
+              begin_instance();
+            }
+          }
         }
-        break;
       }
-      // miss
-      if (born_shadow && first) c_shok++;
-      first = false;
-      if (mode == 1) { // adapter contract: hand the ray back (localDispatch, :604-609 / :377-381)
-        unsigned pos = queue_reserve(q.mvq.count);
-        if (pos < q.mvq.cap) queue_store(q.mvq, pos, r, slot);
-        if (r.type != RAY_SHADOW && slot >= 0) queue_store(q.fin, (unsigned)slot, r, slot);
-        break;
-      }
-      float t;
-      int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, inst, false, t);
-      if (next < 0) {
-        if (r.type == RAY_SHADOW && xlength(r.color) > 0.f) { // TracerBase.h:396-399
-          fb_add(sd.fb, r.id, xmul(r.color, r.w));
-          c_fb++;
-        }
-        break;
-      }
-      r.o = xadd(r.o, xmul(r.d, xmul(t, 0.95f))); // TracerBase.h:394
-      if (fp.world > 1 && sd.inst[next].owner != fp.rank) {
-        unsigned pos = queue_reserve(q.exq.count);
-        if (pos < q.exq.cap) queue_store(q.exq, pos, r, next);
-        c_exp++;
-        break;
-      }
-      inst = next;
     }
   }
+  if (stack.overflow) c_ovf = 1;
   count_add(&sd.ctr->instance_visits, c_visits);
-  count_add(&sd.ctr->primary_hits, c_hits);
-  count_add(&sd.ctr->shadow_generated, c_shgen);
   count_add(&sd.ctr->shadow_unoccluded, c_shok);
-  count_add(&sd.ctr->secondary_generated, c_sec);
   count_add(&sd.ctr->fb_adds, c_fb);
   count_add(&sd.ctr->rays_exported, c_exp);
+  count_add(&sd.ctr->stack_overflows, c_ovf);
   if (COUNT) {
     count_add(&sd.ctr->nodes_visited, tc.nodes);
     count_add(&sd.ctr->tris_tested, tc.tris);
   }
+}
+
+// k_shade: one thread per closest hit.  Surface data, Shade() per light -> shadow rays into `shq`, the bounce decision ->
+// the secondary ray into `nxq` (EmbreeMeshAdapter.cpp:491-601).  Fully coherent: every lane of a warp shades.
+__global__ void __launch_bounds__(256) k_shade(FrameParams fp, SceneDev sd, ShadeQueues q, int mode) {
+  const unsigned n = min(*q.hq.count, q.hq.cap);
+  const bool to_light = (fp.flags & FLAG_SHADOW_TO_LIGHT) != 0;
+  unsigned long long c_hits = 0, c_shgen = 0, c_sec = 0;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Ray r;
+    int inst;
+    queue_load(q.hq, i, r, inst);
+    const int4 hc = q.hit[i];
+    Hit h;
+    h.prim = hc.x, h.slot = hc.y, h.t = r.t, h.u = u2f((uint32_t)hc.z), h.v = u2f((uint32_t)hc.w);
+    const int slot = inst; // adapter mode only
+    if (mode == 1) inst = 0;
+    const Instance in = sd.inst[inst];
+    const Blas &bl = sd.blas[in.mesh];
+    c_hits++;
+    V3 normal;
+    Mat mat;
+    surface_at(bl, in, h, r, fp.flags, normal, mat);
+    if (r.type == RAY_SECONDARY) { // :572-575
+      float tt = (h.t > 1.f) ? xdiv(1.f, h.t) : h.t;
+      r.w = xmul(r.w, tt);
+    }
+    for (int li = 0; li < fp.n_lights; ++li) {
+      const Light &L = fp.lights[li];
+      Ray sh;
+      if (!make_shadow_ray(r, normal, mat, L, light_position(L, fp.seed, r.id, r.depth, li), to_light, sh)) continue;
+      c_shgen++;
+      unsigned pos = queue_reserve(q.shq.count);
+      if (pos < q.shq.cap) queue_store(q.shq, pos, sh, mode == 1 ? -1 : inst);
+    }
+    if (make_bounce(r, normal, fp.seed)) {
+      c_sec++;
+      unsigned pos = queue_reserve(q.nxq.count);
+      if (pos < q.nxq.cap) queue_store(q.nxq, pos, r, mode == 1 ? slot : inst);
+    } else if (mode == 1 && slot >= 0) {
+      queue_store(q.fin, (unsigned)slot, r, slot);
+    }
+  }
+  count_add(&sd.ctr->primary_hits, c_hits);
+  count_add(&sd.ctr->shadow_generated, c_shgen);
+  count_add(&sd.ctr->secondary_generated, c_sec);
 }
 
 // closest-hit / any-hit queries in mesh-local space (parity hooks)

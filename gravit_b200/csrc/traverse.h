@@ -111,113 +111,202 @@ GVT_HD int tlas_route(const Tlas &tl, V3 o, V3 d, float t_max, int from, bool en
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// 8-wide compressed BVH traversal.  One thread per ray; a small stack of (node group | triangle group) pairs.
-// Child boxes are dequantised in the ray's frame: t = q * (2^e / d) + (p - o) / d.  The box tests are free-form
-// float math (conservative boxes: see bvh_build.h), the triangle test is the canonical exact sequence.
+// 8-wide compressed BVH traversal, written as a resumable per-ray state machine so that the trace kernel can
+// interleave rays (lane refill) and postpone triangle tests (Ylitie, Karras, Laine, HPG 2017, sections 4.3-4.4):
+//   trav_begin   : empty state, root pending
+//   node_step    : visit the nearest pending child node, test its 8 quantised child boxes
+//   tri_step     : test one triangle of the current triangle group
+//   trav_next    : pop the next group, or report that the traversal is finished
+// Node layout: bvh_build.h.  A plane value is the float m = 1 + q/128 whose upper 16 bits are stored; t = m * A + B with
+// A = 128 * step / d and B = (origin - o) / d - A.  The value of slots 0-3 is the plane word read as a float as it is
+// (the lower field adds 0.2480 .. 0.2500 quanta; B is lowered by the bound that keeps near planes early and far planes
+// late), the value of slots 4-7 is the word shifted left by 16 (an IMAD on the FMA pipe): no I2F, no byte extraction on the ALU pipe, which is what bounds this kernel on sm_100.
+// Near / far plane blocks are picked by LOAD ADDRESS from the ray's direction signs, not by selects.  Hit slots are
+// collected as an 8-bit mask: internal hits are visited in descending (slot ^ octinv) order = front to back; triangle
+// bits are (leaf_hits * 0x010101) & tmask.  The box tests are free-form float math (conservative boxes), the triangle
+// test is the canonical exact sequence.
 // ---------------------------------------------------------------------------------------------------------
-GVT_HD uint32_t sign_extend_s8x4(uint32_t x) { return ((x >> 7) & 0x01010101u) * 0xFFu; }
-GVT_HD uint32_t byte_of(uint32_t w, int j) { return (w >> (8 * j)) & 0xFFu; }
+#if defined(__CUDA_ARCH__)
+#define GVT_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define GVT_LDG4(p) __ldg(p)
+#else
+#define GVT_FMA(a, b, c) fmaf((a), (b), (c))
+#define GVT_LDG4(p) (*(p))
+#endif
+/* what the lower field adds to the upper value, in quanta: (0x3F80 + q') / 65536, q' in 0..127 */
+#define GVT_LOWFIELD_MIN 0.24804f
+#define GVT_LOWFIELD_MAX 0.24999f
 
 #define GVT_BLAS_STACK 32
+#define GVT_TRI_TAG 0x80000000u /* .x bit of a triangle group */
 
-template <bool ANY_HIT, bool COUNT>
-GVT_HD bool blas_traverse(const Blas &bl, V3 o, V3 d, float tnear, float tfar, Hit &hit, TravCounters *ctr) {
-  hit.prim = -1, hit.slot = -1, hit.t = tfar, hit.u = 0.f, hit.v = 0.f;
-  if (bl.n_tris == 0) return false;
-  // slab directions: avoid 1/0 (the triangle test still sees the true direction)
+// the ray in mesh space, with what every node visit needs
+struct RayLocal {
+  V3 o, d;
+  float rdx, rdy, rdz; // 1 / d, with zero components replaced by +-1e-20 (the triangle test sees the true d)
+  uint32_t octinv;     // 7 - octant of d (bit 2/1/0 set = d.x/d.y/d.z >= 0)
+};
+GVT_HD void ray_local(RayLocal &rl, V3 o, V3 d) {
+  rl.o = o, rl.d = d;
   const float tiny = 1e-20f;
   float dxs = fabsf(d.x) < tiny ? (d.x < 0.f ? -tiny : tiny) : d.x;
   float dys = fabsf(d.y) < tiny ? (d.y < 0.f ? -tiny : tiny) : d.y;
   float dzs = fabsf(d.z) < tiny ? (d.z < 0.f ? -tiny : tiny) : d.z;
-  const float rdx = 1.0f / dxs, rdy = 1.0f / dys, rdz = 1.0f / dzs;
-  const uint32_t octinv = 7u - ((d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u));
-  const uint32_t octinv4 = octinv * 0x01010101u;
-  float tmax = tfar;
-  uint2 stack[GVT_BLAS_STACK];
-  int sp = 0;
-  uint2 ngroup = make_uint2(0u, 0x80000000u); // root: node 0, one pending child bit
-  uint2 tgroup = make_uint2(0u, 0u);
-  for (;;) {
-    { // invariant: ngroup.y > 0x00FFFFFF here (a node group with at least one pending child)
-      const uint32_t hits = ngroup.y;
-      const uint32_t imask = ngroup.y; // low byte
-      const int child_bit_index = bfind32(hits);
-      const uint32_t child_node_base = ngroup.x;
-      ngroup.y &= ~(1u << child_bit_index);
-      if (ngroup.y > 0x00FFFFFFu) {
-        if (sp < GVT_BLAS_STACK) stack[sp++] = ngroup;
-      }
-      const uint32_t slot_index = ((uint32_t)child_bit_index - 24u) ^ (octinv4 & 255u);
-      const uint32_t relative = (uint32_t)popc32(imask & ~(0xFFFFFFFFu << slot_index));
-      const uint32_t ni = child_node_base + relative;
-      const float4 n0 = bl.nodes[5 * ni + 0], n1 = bl.nodes[5 * ni + 1], n2 = bl.nodes[5 * ni + 2],
-                   n3 = bl.nodes[5 * ni + 3], n4 = bl.nodes[5 * ni + 4];
-      if (COUNT) ctr->nodes++;
-      const uint32_t ew = f2u(n0.w);
-      ngroup.x = f2u(n1.x);
-      tgroup.x = f2u(n1.y);
-      tgroup.y = 0u;
-      uint32_t hitmask = 0u;
-      const float adjx = u2f((ew & 0xFFu) << 23) * rdx;
-      const float adjy = u2f(((ew >> 8) & 0xFFu) << 23) * rdy;
-      const float adjz = u2f(((ew >> 16) & 0xFFu) << 23) * rdz;
-      const float ox = (n0.x - o.x) * rdx, oy = (n0.y - o.y) * rdy, oz = (n0.z - o.z) * rdz;
-      const uint32_t qw[12] = { f2u(n2.x), f2u(n2.y), f2u(n2.z), f2u(n2.w), f2u(n3.x), f2u(n3.y),
-                                f2u(n3.z), f2u(n3.w), f2u(n4.x), f2u(n4.y), f2u(n4.z), f2u(n4.w) };
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t meta4 = half ? f2u(n1.w) : f2u(n1.z);
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        // words: qlo.x = qw[0+half], qlo.y = qw[2+half], qlo.z = qw[4+half], qhi.x = qw[6+half], qhi.y = qw[8+half], qhi.z = qw[10+half]
-        const uint32_t lox = rdx < 0.f ? qw[6 + half] : qw[0 + half], hix = rdx < 0.f ? qw[0 + half] : qw[6 + half];
-        const uint32_t loy = rdy < 0.f ? qw[8 + half] : qw[2 + half], hiy = rdy < 0.f ? qw[2 + half] : qw[8 + half];
-        const uint32_t loz = rdz < 0.f ? qw[10 + half] : qw[4 + half], hiz = rdz < 0.f ? qw[4 + half] : qw[10 + half];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j < 4; ++j) {
-          const float tlx = (float)byte_of(lox, j) * adjx + ox, tly = (float)byte_of(loy, j) * adjy + oy,
-                      tlz = (float)byte_of(loz, j) * adjz + oz;
-          const float thx = (float)byte_of(hix, j) * adjx + ox, thy = (float)byte_of(hiy, j) * adjy + oy,
-                      thz = (float)byte_of(hiz, j) * adjz + oz;
-          const float cmin = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tnear));
-          const float cmax = fminf(fminf(thx, thy), fminf(thz, tmax));
-          if (cmin <= cmax) hitmask |= byte_of(child_bits4, j) << byte_of(bit_index4, j);
-        }
-      }
-      ngroup.y = (hitmask & 0xFF000000u) | ((ew >> 24) & 0xFFu);
-      tgroup.y = hitmask & 0x00FFFFFFu;
+  rl.rdx = 1.0f / dxs, rl.rdy = 1.0f / dys, rl.rdz = 1.0f / dzs;
+  rl.octinv = 7u - ((d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u));
+}
+
+// the pending slot to visit first: the set bit s of hits8 with the largest (s ^ octinv)
+GVT_HD uint32_t best_slot(uint32_t hits8, uint32_t octinv) {
+  uint32_t best = 0, bestkey = 0;
+  for (uint32_t s = 0; s < 8; ++s)
+    if ((hits8 >> s) & 1u) {
+      uint32_t key = (s ^ octinv) + 1u;
+      if (key > bestkey) bestkey = key, best = s;
     }
-    while (tgroup.y != 0u) {
-      const int ti = bfind32(tgroup.y);
-      tgroup.y &= ~(1u << ti);
-      const uint32_t slot = tgroup.x + (uint32_t)ti;
-      const float4 a = bl.tris[3 * slot], b = bl.tris[3 * slot + 1], c = bl.tris[3 * slot + 2];
-      if (COUNT) ctr->tris++;
-      float t, u, v;
-      if (tri_test(o, d, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), tnear, tfar, t, u, v)) {
-        const int prim = (int)f2u(a.w);
-        if (ANY_HIT) {
-          hit.prim = prim, hit.slot = (int)slot, hit.t = t, hit.u = u, hit.v = v;
-          return true;
-        }
-        // closest hit; equal t -> smaller primitive id (BVH-order independent, same rule as the oracle)
-        if (t < hit.t || (t == hit.t && (hit.prim < 0 || prim < hit.prim))) {
-          hit.prim = prim, hit.slot = (int)slot, hit.t = t, hit.u = u, hit.v = v;
-          tmax = t;
-        }
-      }
-    }
-    if (ngroup.y <= 0x00FFFFFFu) {
-      if (sp == 0) break;
-      ngroup = stack[--sp];
+  return best;
+}
+
+// traversal state of one ray in one BLAS
+struct Trav {
+  uint2 ng;   // node group {child base, hits8 << 24 | imask}: pending internal children of one wide node
+  uint2 tg;   // triangle group {triangle base | GVT_TRI_TAG, leaf_mask << 24 | 24 triangle bits}
+  int sp;     // stack entries in use
+  float tmax; // far limit for the box tests (shrinks with the closest hit)
+  Hit hit;
+};
+GVT_HD void trav_begin(Trav &tv, unsigned n_tris, float tfar) {
+  tv.hit.prim = -1, tv.hit.slot = -1, tv.hit.t = tfar, tv.hit.u = 0.f, tv.hit.v = 0.f;
+  tv.tmax = tfar;
+  tv.sp = 0;
+  // root: "child 0 of a virtual parent whose only internal slot is slot 0" -> node 0
+  tv.ng = make_uint2(0u, n_tris ? 0x01000001u : 0u);
+  tv.tg = make_uint2(GVT_TRI_TAG, 0u);
+}
+GVT_HD bool trav_has_nodes(const Trav &tv) { return (tv.ng.y >> 24) != 0u; }
+GVT_HD bool trav_has_tris(const Trav &tv) { return (tv.tg.y & 0x00FFFFFFu) != 0u; }
+
+// Visits the nearest pending child of the node group.  Precondition: trav_has_nodes(tv).  lut: optional table
+// lut[octinv * 256 + hits8] = best_slot(hits8, octinv) (the trace kernel keeps it in shared memory).
+template <bool COUNT, bool LUT, class Stack>
+GVT_HD void node_step(const float4 *nodes, const RayLocal &rl, float tnear, Trav &tv, Stack &stack, TravCounters *ctr,
+                      const unsigned char *lut = nullptr) {
+  const uint32_t hits8 = tv.ng.y >> 24;
+  const uint32_t imask = tv.ng.y & 0xFFu;
+  const uint32_t s = LUT ? (uint32_t)lut[rl.octinv * 256u + hits8] : best_slot(hits8, rl.octinv);
+  tv.ng.y &= ~(0x01000000u << s);
+  if (trav_has_nodes(tv)) stack.push(tv.sp, tv.ng);
+  const uint32_t ni = tv.ng.x + (uint32_t)popc32(imask & ((1u << s) - 1u));
+  const float4 *np = nodes + GVT_NODE_WORDS * (size_t)ni;
+  // direction signs pick the near / far plane block of every axis
+  const uint32_t sx = (rl.octinv >> 2) & 1u, sy = (rl.octinv >> 1) & 1u, sz = rl.octinv & 1u; // 1 = positive direction
+  const float4 h0 = GVT_LDG4(np), h1 = GVT_LDG4(np + 1);
+  const float4 nx = GVT_LDG4(np + 3 - sx), fx = GVT_LDG4(np + 2 + sx);
+  const float4 ny = GVT_LDG4(np + 5 - sy), fy = GVT_LDG4(np + 4 + sy);
+  const float4 nz = GVT_LDG4(np + 7 - sz), fz = GVT_LDG4(np + 6 + sz);
+  if (COUNT) ctr->nodes++;
+  const uint32_t ew = f2u(h0.w);
+  const float ax = u2f((ew & 0xFFu) << 23) * rl.rdx, ay = u2f(((ew >> 8) & 0xFFu) << 23) * rl.rdy, az = u2f(((ew >> 16) & 0xFFu) << 23) * rl.rdz;
+  const float bx = GVT_FMA(h0.x - rl.o.x, rl.rdx, -ax), by = GVT_FMA(h0.y - rl.o.y, rl.rdy, -ay), bz = GVT_FMA(h0.z - rl.o.z, rl.rdz, -az);
+  // upper-half values carry +c quanta, c in [MIN, MAX]: near planes must not come out late, far planes not early.
+  // t_err = (c - c_comp) * A / 128: near wants it <= 0, far >= 0
+  const float kmin = -GVT_LOWFIELD_MIN / 128.f, kmax = -GVT_LOWFIELD_MAX / 128.f;
+  const float bxn = GVT_FMA(ax, sx ? kmax : kmin, bx), byn = GVT_FMA(ay, sy ? kmax : kmin, by), bzn = GVT_FMA(az, sz ? kmax : kmin, bz);
+  const float bxf = GVT_FMA(ax, sx ? kmin : kmax, bx), byf = GVT_FMA(ay, sy ? kmin : kmax, by), bzf = GVT_FMA(az, sz ? kmin : kmax, bz);
+  const float tmax = tv.tmax;
+  uint32_t hit8 = 0u;
+#define GVT_LOWF(w) u2f(f2u(w) << 16)
+#define GVT_PAIR(j, comp)                                                                                                \
+  {                                                                                                                      \
+    const float cminH = fmaxf(fmaxf(GVT_FMA(nx.comp, ax, bxn), GVT_FMA(ny.comp, ay, byn)), fmaxf(GVT_FMA(nz.comp, az, bzn), tnear)); \
+    const float cmaxH = fminf(fminf(GVT_FMA(fx.comp, ax, bxf), GVT_FMA(fy.comp, ay, byf)), fminf(GVT_FMA(fz.comp, az, bzf), tmax));  \
+    if (cminH <= cmaxH) hit8 |= 1u << (j);                                                                               \
+    const float cminL = fmaxf(fmaxf(GVT_FMA(GVT_LOWF(nx.comp), ax, bx), GVT_FMA(GVT_LOWF(ny.comp), ay, by)),             \
+                              fmaxf(GVT_FMA(GVT_LOWF(nz.comp), az, bz), tnear));                                         \
+    const float cmaxL = fminf(fminf(GVT_FMA(GVT_LOWF(fx.comp), ax, bx), GVT_FMA(GVT_LOWF(fy.comp), ay, by)),             \
+                              fminf(GVT_FMA(GVT_LOWF(fz.comp), az, bz), tmax));                                          \
+    if (cminL <= cmaxL) hit8 |= 1u << ((j) + 4);                                                                         \
+  }
+  GVT_PAIR(0, x) GVT_PAIR(1, y) GVT_PAIR(2, z) GVT_PAIR(3, w)
+#undef GVT_PAIR
+#undef GVT_LOWF
+  const uint32_t tmask = f2u(h1.z);
+  tv.ng.x = f2u(h1.x);
+  tv.ng.y = ((hit8 & (ew >> 24)) << 24) | (ew >> 24);
+  tv.tg.x = f2u(h1.y) | GVT_TRI_TAG;
+  tv.tg.y = ((tmask & 0xFFu) << 24) | ((hit8 * 0x010101u) & tmask);
+}
+
+// Tests the next triangle of the triangle group.  Precondition: trav_has_tris(tv).  Returns true when an any-hit query
+// is satisfied (the traversal is over).  Bit 8k+s = k-th triangle of leaf slot s, stored at
+// tri_base + 3 * (number of leaf slots below s) + k.
+template <bool COUNT>
+GVT_HD bool tri_step(const float4 *tris, const RayLocal &rl, float tnear, float tfar, bool any_hit, Trav &tv, TravCounters *ctr) {
+  const int ti = bfind32(tv.tg.y & 0x00FFFFFFu);
+  tv.tg.y &= ~(1u << ti);
+  const uint32_t ls = (uint32_t)ti & 7u, lk = (uint32_t)ti >> 3;
+  const uint32_t slot = (tv.tg.x & ~GVT_TRI_TAG) + 3u * (uint32_t)popc32((tv.tg.y >> 24) & ((1u << ls) - 1u)) + lk;
+  const float4 *tp = tris + 3 * (size_t)slot;
+  const float4 a = GVT_LDG4(tp), b = GVT_LDG4(tp + 1), c = GVT_LDG4(tp + 2);
+  if (COUNT) ctr->tris++;
+  float t, u, v;
+  if (tri_test(rl.o, rl.d, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), tnear, tfar, t, u, v)) {
+    const int prim = (int)f2u(a.w);
+    // closest hit; equal t -> smaller primitive id (BVH-order independent, same rule as the oracle)
+    if (any_hit || t < tv.hit.t || (t == tv.hit.t && (tv.hit.prim < 0 || prim < tv.hit.prim))) {
+      tv.hit.prim = prim, tv.hit.slot = (int)slot, tv.hit.t = t, tv.hit.u = u, tv.hit.v = v;
+      tv.tmax = t;
+      return any_hit;
     }
   }
+  return false;
+}
+
+// After the node / triangle work of one iteration: if the node group is used up, pop the next group.  A popped
+// triangle group (postponed earlier) becomes the current triangle group.  Returns false when nothing is left.
+template <class Stack> GVT_HD bool trav_next(Trav &tv, Stack &stack) {
+  if (!trav_has_nodes(tv)) {
+    if (trav_has_tris(tv)) return true; // a triangle group kept in place is still pending
+    if (tv.sp == 0) return false;
+    uint2 g = stack.pop(tv.sp);
+    if (g.x & GVT_TRI_TAG)
+      tv.tg = g, tv.ng = make_uint2(0u, 0u);
+    else
+      tv.ng = g;
+  }
+  return true;
+}
+
+// plain per-thread stack (host emulation, parity kernels)
+struct LocalStack {
+  uint2 e[GVT_BLAS_STACK];
+  bool overflow = false;
+  GVT_HD void push(int &sp, uint2 v) {
+    if (sp < GVT_BLAS_STACK)
+      e[sp++] = v;
+    else
+      overflow = true;
+  }
+  GVT_HD uint2 pop(int &sp) { return e[--sp]; }
+};
+
+// One ray, start to finish (parity hooks and the host emulation; the trace kernel drives the steps itself).
+template <bool ANY_HIT, bool COUNT>
+GVT_HD bool blas_traverse(const Blas &bl, V3 o, V3 d, float tnear, float tfar, Hit &hit, TravCounters *ctr) {
+  RayLocal rl;
+  ray_local(rl, o, d);
+  Trav tv;
+  trav_begin(tv, bl.n_tris, tfar);
+  LocalStack stack;
+  bool more = trav_has_nodes(tv);
+  while (more) {
+    if (trav_has_nodes(tv)) node_step<COUNT, false>(bl.nodes, rl, tnear, tv, stack, ctr);
+    bool done = false;
+    while (trav_has_tris(tv) && !done) done = tri_step<COUNT>(bl.tris, rl, tnear, tfar, ANY_HIT, tv, ctr);
+    if (done) break;
+    more = trav_next(tv, stack);
+  }
+  hit = tv.hit;
   return hit.prim >= 0;
 }
 

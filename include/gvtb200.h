@@ -87,6 +87,10 @@ typedef struct gvtb200_scene_s *gvtb200_scene;
 GVTB200_API int gvtb200_init(int device);
 GVTB200_API const char *gvtb200_last_error(void);
 GVTB200_API int gvtb200_device_info(int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor);
+/* scheduling knobs of the trace kernel (results do not depend on them): refill idle lanes when >= refill_at lanes wait,
+ * leave the lock-step traversal loop when >= exit_at lanes are not traversing, postpone triangle tests while fewer than
+ * postpone_num/8 of the traversing lanes hold a triangle.  Replaces the TBB grain size of EmbreeMeshAdapter.cpp:648. */
+GVTB200_API int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num);
 
 /* ---- B1: the engine adapter (Adapter.h:44-88) --------------------------------------------------------- */
 /* replaces EmbreeMeshAdapter::EmbreeMeshAdapter (adapter/embree/EmbreeMeshAdapter.cpp:125-162): takes the
@@ -174,7 +178,7 @@ typedef struct gvtb200_counters {
   uint64_t nodes_visited;   /* only when profiling counters are enabled */
   uint64_t tris_tested;
   uint64_t rays_exported; /* domain scheduler: rays handed to other ranks */
-  uint64_t reserved;
+  uint64_t stack_overflows; /* rays whose traversal stack overflowed (must be 0; deeper BVHs need GVT_BLAS_STACK raised) */
 } gvtb200_counters;
 GVTB200_API int gvtb200_render_frame(gvtb200_scene scene, int row0, int row1, float *rgba_out, gvtb200_counters *counters);
 /* same, asynchronous on the scene's stream, nothing copied back (bench / multi-GPU drivers) */

@@ -83,10 +83,10 @@ EM_API void *emul_build(const float *verts, unsigned nv, const uint32_t *faces, 
     }
   }
   // collapse, level by level
-  m->wnodes.assign(5 * (size_t)std::max(1u, nf), make_float4(0, 0, 0, 0));
-  m->wtris.assign(3 * (size_t)std::max(1u, nf), make_float4(0, 0, 0, 0));
+  m->wnodes.assign(GVT_NODE_WORDS * (size_t)std::max(1u, nf), make_float4(0, 0, 0, 0));
+  m->wtris.assign(3 * GVT_LEAF_MAX * (size_t)std::max(1u, nf), make_float4(0, 0, 0, 0));
   c.wnodes = m->wnodes.data(), c.wtris = m->wtris.data();
-  unsigned node_count = 1, tri_count = 0;
+  unsigned node_count = 1, tri_count = 0, tri_slots = 0;
   if (nf > 0) {
     std::vector<CollapseTask> cur, next;
     CollapseTask root;
@@ -97,16 +97,13 @@ EM_API void *emul_build(const float *verts, unsigned nv, const uint32_t *faces, 
       m->depth++;
       next.clear();
       for (auto &t : cur) {
-        int slot_b[8], n_internal, n_leaf_tris;
-        uint32_t meta[8];
-        unsigned qlo[24], qhi[24];
-        float4 w0;
-        collapse_node(c, t, slot_b, n_internal, n_leaf_tris, meta, qlo, qhi, w0);
-        unsigned child_base = node_count, tri_base = tri_count;
-        node_count += n_internal, tri_count += n_leaf_tris;
+        WideNode w;
+        collapse_node(c, t, w);
+        unsigned child_base = node_count, tri_base = tri_slots;
+        node_count += w.n_internal, tri_slots += GVT_LEAF_MAX * w.n_leaves, tri_count += w.n_tris;
         size_t q = next.size();
-        next.resize(q + n_internal);
-        collapse_emit(c, t, slot_b, meta, qlo, qhi, w0, child_base, tri_base, next.data() + q);
+        next.resize(q + w.n_internal);
+        collapse_emit(c, t, w, child_base, tri_base, next.data() + q);
       }
       cur.swap(next);
     }

@@ -9,7 +9,7 @@ import pytest
 
 from oracle import pyoracle as po
 from scenes import library
-from tests.scene_util import oracle_scene, random_rays
+from tests.scene_util import grazing_rays, oracle_scene, random_rays
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -81,4 +81,29 @@ def test_edge_cases(E):
         he = np.zeros(len(rays), po.HIT_DTYPE)
         E.emul_intersect(h, po._fp(rays), len(rays), 0, po._fp(he), None)
         assert he["prim"].tolist() == expect
+        E.emul_destroy(h)
+
+
+def test_grazing_rays_near_faces(E):
+    """Rays that start within a few 1e-6 of a face (hit t just above RAY_EPSILON) must not be culled by the quantised
+    child boxes: the node frame keeps its conservative margins at the grid boundary (bvh_build.h GVT_QPAD) and the
+    lower-field compensation is sign-aware (traverse.h node_step).  Seeds 104/108 are known offenders of an earlier build."""
+    d = library.simple_scene(64, 64)
+    o = oracle_scene(d)
+    for k in range(len(d.meshes)):
+        h, nf, bbox = _mesh(E, o, d, k)
+        for seed in (104, 108):
+            rays = random_rays(bbox, 200000, seed=seed)
+            ho = o.intersect(k, rays, threads=4)
+            he = np.zeros(len(rays), po.HIT_DTYPE)
+            E.emul_intersect(h, po._fp(rays), len(rays), 0, po._fp(he), None)
+            assert np.array_equal(ho, he)
+        # rays launched from just above / below every face towards it
+        v = po.f32(d.meshes[k].verts).reshape(-1, 3)
+        faces, _, _ = o.mesh_get(k, len(v))
+        rays = grazing_rays(v, faces)
+        ho = o.intersect(k, rays, threads=4)
+        he = np.zeros(len(rays), po.HIT_DTYPE)
+        E.emul_intersect(h, po._fp(rays), len(rays), 0, po._fp(he), None)
+        assert np.array_equal(ho, he)
         E.emul_destroy(h)

@@ -8,7 +8,7 @@ import pytest
 
 from oracle import pyoracle as po
 from scenes import library
-from tests.scene_util import golden_ppm, oracle_scene, random_rays, sorted_payload
+from tests.scene_util import golden_ppm, grazing_rays, oracle_scene, random_rays, sorted_payload
 
 pytestmark = pytest.mark.gpu
 
@@ -54,6 +54,29 @@ def test_blas_morton_and_hits_bit_exact(gpu, name):
         hg = mesh.intersect(rays)
         assert np.array_equal(ho, hg)
         assert np.array_equal(o.occluded(k, rays, threads=8), mesh.occluded(rays))
+        mesh.close()
+
+
+@pytest.mark.parametrize("name", ["simple", "bunny_obj"])
+def test_blas_grazing_rays_bit_exact(gpu, name):
+    """Hits just above RAY_EPSILON (ray origins 1e-6 .. 1e-4 off a face) survive the quantised child boxes; also through
+    the trace kernel's lane-refill / triangle-postponing path (Adapter::trace)."""
+    g = gpu
+    d = SCENES[name]()
+    o = oracle_scene(d)
+    for k in range(len(d.meshes)):
+        mesh, bbox = _mesh_handle(g, o, d, k)
+        v = po.f32(d.meshes[k].verts).reshape(-1, 3)
+        faces, _, _ = o.mesh_get(k, len(v))
+        rays = np.concatenate([grazing_rays(v, faces, reps=max(20, 40000 // max(1, len(faces)))), random_rays(bbox, 200000, seed=104 + 4 * k)])
+        ho = o.intersect(k, rays, threads=8)
+        assert np.array_equal(ho, mesh.intersect(rays))
+        assert np.array_equal(o.occluded(k, rays, threads=8), mesh.occluded(rays))
+        # the same rays through k_trace (adapter mode, no lights): rays that miss come back, in any order
+        ident = np.eye(4, dtype=np.float32).reshape(16)
+        normi = np.eye(3, dtype=np.float32).reshape(9)
+        _, moved = mesh.trace(rays, ident, ident, normi, np.zeros(0, g.LIGHT_DTYPE), flags=0)
+        assert sorted(moved["id"].tolist()) == sorted(rays["id"][ho["prim"] < 0].tolist())
         mesh.close()
 
 
