@@ -415,6 +415,7 @@ int gvtb200_init(int device) {
 }
 
 const char *gvtb200_last_error(void) { return t_err.c_str(); }
+int gvtb200_current_device(void) { return g_device; }
 
 int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num) {
   if (refill_at < 1 || refill_at > 32 || exit_at < 1 || exit_at > 32 || postpone_num < 0 || postpone_num > 8)

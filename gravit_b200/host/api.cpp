@@ -209,7 +209,7 @@ void mat4_point(const float *a, const float *p, float *out) {
 
 void ensure_init() {
   if (db().initialised) return;
-  if (gvtb200_init(0) != GVTB200_OK) engine_error("gvtInit");
+  if (gvtb200_current_device() < 0 && gvtb200_init(0) != GVTB200_OK) engine_error("gvtInit"); // keep a device the caller chose
   db().initialised = true;
 }
 

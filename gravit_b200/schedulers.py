@@ -105,3 +105,63 @@ def render_domain_schedule(engine, dist, rank, world, device, fb_tensor, max_rou
     if rank == 0:
         engine.fb_clamp()
     return log
+
+
+def build_domain_rank(desc, rank, world, flags=None, boxes=None):
+    """The scene one DomainScheduler rank holds: every instance (matrices + boxes, for routing) but only the meshes of
+    the instances it owns (DomainTracer.h:115-144: instance k lives on rank k % world).  `desc` is a scenes.library
+    description.  A mesh this rank does not own may have verts=None; then boxes[k] = its (lo.xyz, hi.xyz) bounding box
+    (ranks exchange them, see mesh_boxes_allgather) and a two-corner placeholder stands in for it in the host layer, so
+    that api::addInstance computes the same instance box on every rank.  Returns (StandaloneScene, owner table)."""
+    import gravit_b200 as g
+
+    owner = domain_owner(len(desc.instances), world)
+    flags = desc.flags if flags is None else flags
+    needed = [any(owner[i] == rank and mi == k for i, (mi, _) in enumerate(desc.instances)) for k in range(len(desc.meshes))]
+    host = g.GvtScene(flags=flags)  # host layer: Mesh::addFace filter, normals, addInstance matrices and boxes
+    ids = []
+    for k, m in enumerate(desc.meshes):
+        if m.verts is not None:
+            ids.append(host.add_mesh(m.verts, m.tris, one_based=m.one_based, kd=m.kd))
+        else:
+            if needed[k]:
+                raise ValueError(f"mesh {k} is owned by rank {rank} but has no geometry")
+            lo, hi = np.asarray(boxes[k][:3], np.float32), np.asarray(boxes[k][3:], np.float32)
+            # Mesh::addFace drops the degenerate face, Mesh::computeBoundingBox still sees the two corners
+            ids.append(host.add_mesh(np.stack([lo, hi, lo]), np.array([[1, 2, 3]], np.uint32), one_based=True, kd=m.kd))
+    for mesh, m16 in desc.instances:
+        host.add_instance(ids[mesh], m16)
+    lights = np.array([g.point_light(p, c) for p, c in desc.lights], g.LIGHT_DTYPE)
+    inst = [(mi,) + tuple(host.instance_get(i)) for i, (mi, _) in enumerate(desc.instances)]
+    meshes = []
+    for k, m in enumerate(desc.meshes):
+        if not needed[k]:
+            meshes.append(None)
+            continue
+        nv = len(np.asarray(m.verts).reshape(-1, 3))
+        faces, normals, _ = host.mesh_get(k, nv)
+        meshes.append(g.Mesh(m.verts, faces, normals=normals, material=(0, tuple(m.kd or (0.5, 0.5, 0.5)), (0.5, 0.5, 0.5), 1.0)))
+    cam = (desc.eye, desc.focus, desc.up, desc.fov, desc.depth, desc.samples, desc.jitter)
+    scene = g.StandaloneScene(meshes, inst, lights, cam, (desc.width, desc.height), flags=flags, owner=owner, rank=rank, world=world)
+    return scene, owner
+
+
+def mesh_boxes_allgather(desc, dist, world):
+    """Bounding boxes of all meshes of a description whose geometry is spread over the ranks (verts=None where another
+    rank holds it): each rank contributes the boxes of the meshes it holds; max/min-reduced across ranks."""
+    import torch
+
+    n = len(desc.meshes)
+    lo = np.full((n, 3), np.inf, np.float32)
+    hi = np.full((n, 3), -np.inf, np.float32)
+    for k, m in enumerate(desc.meshes):
+        if m.verts is not None and len(m.verts):
+            v = np.asarray(m.verts, np.float32).reshape(-1, 3)
+            lo[k], hi[k] = v.min(0), v.max(0)
+    if world > 1:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        tl, th = torch.as_tensor(lo, device=dev), torch.as_tensor(hi, device=dev)
+        dist.all_reduce(tl, op=dist.ReduceOp.MIN)
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        lo, hi = tl.cpu().numpy(), th.cpu().numpy()
+    return np.concatenate([lo, hi], axis=1)

@@ -86,6 +86,9 @@ typedef struct gvtb200_scene_s *gvtb200_scene;
 /* replaces api::gvtInit (api/api.cpp:76-98) for the device side: selects the CUDA device, creates streams. */
 GVTB200_API int gvtb200_init(int device);
 GVTB200_API const char *gvtb200_last_error(void);
+/* the device gvtb200_init selected, or -1: lets a second client in the process (the api:: host layer under torchrun,
+ * where each rank has already picked its GPU) reuse the selection instead of re-initialising on device 0 */
+GVTB200_API int gvtb200_current_device(void);
 GVTB200_API int gvtb200_device_info(int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor);
 /* scheduling knobs of the trace kernel (results do not depend on them): refill idle lanes when >= refill_at lanes wait,
  * leave the lock-step traversal loop when >= exit_at lanes are not traversing, postpone triangle tests while fewer than

@@ -292,23 +292,12 @@ def test_full_size_properties(gpu):
 
 def _standalone_ranks(g, d, flags, world):
     """One engine scene per simulated rank on the same GPU: rank r holds only the meshes of the instances it owns."""
-    host = library.apply(d, g.GvtScene(flags=flags))  # host layer: Mesh::addFace filter, normals, addInstance matrices
-    owner = np.arange(len(d.instances)) % world  # DomainTracer.h:115-144 with one location per mesh
-    lights = np.array([g.point_light(p, c) for p, c in d.lights], g.LIGHT_DTYPE)
-    inst = [(mi,) + tuple(host.instance_get(i)) for i, (mi, _) in enumerate(d.instances)]
+    from gravit_b200 import schedulers
+
     ranks = []
     for r in range(world):
-        meshes = []
-        for k, m in enumerate(d.meshes):
-            needed = any(owner[i] == r and mi == k for i, (mi, _) in enumerate(d.instances))
-            if not needed:
-                meshes.append(None)
-                continue
-            nv = len(np.asarray(m.verts).reshape(-1, 3))
-            faces, normals, _ = host.mesh_get(k, nv)
-            meshes.append(g.Mesh(m.verts, faces, normals=normals, material=(0, tuple(m.kd or (0.5, 0.5, 0.5)), (0.5, 0.5, 0.5), 1.0)))
-        cam = (d.eye, d.focus, d.up, d.fov, d.depth, d.samples, d.jitter)
-        ranks.append(g.StandaloneScene(meshes, inst, lights, cam, (d.width, d.height), flags=flags, owner=owner, rank=r, world=world))
+        scene, owner = schedulers.build_domain_rank(d, r, world, flags=flags)
+        ranks.append(scene)
     return ranks, owner
 
 
