@@ -118,6 +118,131 @@ GVT_HD void karras_node(const BuildCtx &c, int i) {
   if (i == 0) c.bn_parent[0] = -1;
 }
 
+// ---- binned-SAH binary tree (top-down, level-synchronous) ----------------------------------------------------
+// The Morton order only seeds the element order (locality); the tree itself is built top-down: per level, every active
+// node bins the centroids of its triangles (GVT_SAH_BINS bins on each axis, bin bounds grown with integer atomics),
+// picks the split with the smallest SA(L)*|L| + SA(R)*|R|, and its element range is stably partitioned (one device-wide
+// scan of the goes-left flags per level).  Nodes of at most GVT_SAH_SMALL triangles evaluate every centroid threshold
+// exactly instead of binning.  The output has the layout the Karras tree had (internal nodes 0..n-2 with root 0, leaf
+// n-1+k = sorted position k, bn_child / bn_range / bn_parent / bn_lo / bn_hi), so refit is not needed and the wide
+// collapse below is unchanged.  Replaces the SAH builder inside Embree's rtcCommit (EmbreeMeshAdapter.cpp:125-162).
+#define GVT_SAH_BINS 16
+#define GVT_SAH_SMALL 8
+
+GVT_HD int fenc(float f) { // order-preserving float -> signed int
+  int i = (int)f2u(f);
+  return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+GVT_HD float fdec(int i) { return u2f((uint32_t)(i >= 0 ? i : i ^ 0x7FFFFFFF)); }
+
+struct SahBin {
+  int lo[3], hi[3]; // encoded box of the triangles whose centroid falls into the bin
+  int cnt, pad;
+};
+struct SahNode {   // an active node of the current level
+  int lo, hi;      // element range [lo, hi)
+  int id;          // binary node id
+  int bslot;       // index of its 3 * GVT_SAH_BINS bins, -1 for small nodes
+  int cb[6];       // encoded centroid bounds (min.xyz, max.xyz)
+  // split decision
+  int axis, bin, mode; // mode 0: left = (bin index <= bin); 1: left = first half by position; 2: left = (centroid <= thr)
+  float thr;
+  int n_left, child_active[2];
+};
+GVT_HD int sah_bin(float c, float cmin, float cmax) {
+  float ext = cmax - cmin;
+  if (!(ext > 0.f)) return 0;
+  int b = (int)((c - cmin) * ((float)GVT_SAH_BINS * (1.f - 1e-6f) / ext));
+  return b < 0 ? 0 : (b >= GVT_SAH_BINS ? GVT_SAH_BINS - 1 : b);
+}
+GVT_HD float sah_area(const float *lo, const float *hi) {
+  float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+// choose the split of a binned node; also returns the node box (union of its bins)
+GVT_HD void sah_eval_bins(const SahBin *bins /* [3][GVT_SAH_BINS] */, SahNode &nd, float *blo, float *bhi) {
+  float best = FLT_MAX;
+  nd.mode = 1, nd.axis = 0, nd.bin = 0;
+  for (int q = 0; q < 3; ++q) blo[q] = FLT_MAX, bhi[q] = -FLT_MAX;
+  for (int a = 0; a < 3; ++a) {
+    const SahBin *B = bins + a * GVT_SAH_BINS;
+    float ra[GVT_SAH_BINS];
+    int rc[GVT_SAH_BINS];
+    float l[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, h[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    int n = 0;
+    for (int b = GVT_SAH_BINS - 1; b >= 0; --b) {
+      if (B[b].cnt) {
+        n += B[b].cnt;
+        for (int q = 0; q < 3; ++q) l[q] = fminf(l[q], fdec(B[b].lo[q])), h[q] = fmaxf(h[q], fdec(B[b].hi[q]));
+      }
+      rc[b] = n, ra[b] = n ? sah_area(l, h) : 0.f;
+    }
+    if (a == 0)
+      for (int q = 0; q < 3; ++q) blo[q] = l[q], bhi[q] = h[q];
+    for (int q = 0; q < 3; ++q) l[q] = FLT_MAX, h[q] = -FLT_MAX;
+    n = 0;
+    for (int b = 0; b + 1 < GVT_SAH_BINS; ++b) {
+      if (B[b].cnt) {
+        n += B[b].cnt;
+        for (int q = 0; q < 3; ++q) l[q] = fminf(l[q], fdec(B[b].lo[q])), h[q] = fmaxf(h[q], fdec(B[b].hi[q]));
+      }
+      if (!n || !rc[b + 1]) continue;
+      float cost = sah_area(l, h) * (float)n + ra[b + 1] * (float)rc[b + 1];
+      if (cost < best) best = cost, nd.mode = 0, nd.axis = a, nd.bin = b, nd.n_left = n;
+    }
+  }
+}
+// small node: every centroid of the node is a threshold candidate on every axis (exact sweep, O(k^2))
+GVT_HD void sah_eval_small(const float4 *tb_lo, const float4 *tb_hi, const uint32_t *idx, SahNode &nd, float *blo, float *bhi) {
+  float best = FLT_MAX;
+  nd.mode = 1, nd.axis = 0, nd.bin = 0, nd.thr = 0.f;
+  const int k = nd.hi - nd.lo;
+  for (int q = 0; q < 3; ++q) blo[q] = FLT_MAX, bhi[q] = -FLT_MAX;
+  for (int i = 0; i < k; ++i) {
+    float4 l = tb_lo[idx[nd.lo + i]], h = tb_hi[idx[nd.lo + i]];
+    blo[0] = fminf(blo[0], l.x), blo[1] = fminf(blo[1], l.y), blo[2] = fminf(blo[2], l.z);
+    bhi[0] = fmaxf(bhi[0], h.x), bhi[1] = fmaxf(bhi[1], h.y), bhi[2] = fmaxf(bhi[2], h.z);
+  }
+  for (int a = 0; a < 3; ++a)
+    for (int i = 0; i < k; ++i) {
+      float4 li = tb_lo[idx[nd.lo + i]], hi_ = tb_hi[idx[nd.lo + i]];
+      float thr = 0.5f * ((&li.x)[a] + (&hi_.x)[a]);
+      float l0[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, h0[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX }, l1[3] = { FLT_MAX, FLT_MAX, FLT_MAX },
+            h1[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+      int n0 = 0, n1 = 0;
+      for (int j = 0; j < k; ++j) {
+        float4 l = tb_lo[idx[nd.lo + j]], h = tb_hi[idx[nd.lo + j]];
+        float c = 0.5f * ((&l.x)[a] + (&h.x)[a]);
+        if (c <= thr) {
+          n0++;
+          l0[0] = fminf(l0[0], l.x), l0[1] = fminf(l0[1], l.y), l0[2] = fminf(l0[2], l.z);
+          h0[0] = fmaxf(h0[0], h.x), h0[1] = fmaxf(h0[1], h.y), h0[2] = fmaxf(h0[2], h.z);
+        } else {
+          n1++;
+          l1[0] = fminf(l1[0], l.x), l1[1] = fminf(l1[1], l.y), l1[2] = fminf(l1[2], l.z);
+          h1[0] = fmaxf(h1[0], h.x), h1[1] = fmaxf(h1[1], h.y), h1[2] = fmaxf(h1[2], h.z);
+        }
+      }
+      if (!n0 || !n1) continue;
+      float cost = sah_area(l0, h0) * (float)n0 + sah_area(l1, h1) * (float)n1;
+      if (cost < best) best = cost, nd.mode = 2, nd.axis = a, nd.thr = thr, nd.n_left = n0;
+    }
+}
+// does element `f` at position `pos` go to the left child?
+GVT_HD bool sah_goes_left(const SahNode &nd, const float4 *tb_lo, const float4 *tb_hi, uint32_t f, int pos) {
+  if (nd.mode == 1) return (pos - nd.lo) < (nd.hi - nd.lo) / 2;
+  float c = 0.5f * ((&tb_lo[f].x)[nd.axis] + (&tb_hi[f].x)[nd.axis]);
+  if (nd.mode == 2) return c <= nd.thr;
+  return sah_bin(c, fdec(nd.cb[nd.axis]), fdec(nd.cb[3 + nd.axis])) <= nd.bin;
+}
+GVT_HD void tri_box_padded(const BuildCtx &c, unsigned f, float4 &lo, float4 &hi) {
+  V3 a, b, d;
+  tri_verts(c, f, a, b, d);
+  float p = c.pad;
+  lo = make_float4(fminf(fminf(a.x, b.x), d.x) - p, fminf(fminf(a.y, b.y), d.y) - p, fminf(fminf(a.z, b.z), d.z) - p, 0.f);
+  hi = make_float4(fmaxf(fmaxf(a.x, b.x), d.x) + p, fmaxf(fmaxf(a.y, b.y), d.y) + p, fmaxf(fmaxf(a.z, b.z), d.z) + p, 0.f);
+}
+
 // ---- wide-node collapse ------------------------------------------------------------------------------------
 // Wide node = 128 bytes = one cache line = eight 16-byte words (coalesced LDG.128 each):
 //   u0: frame origin.xyz (fp32), {ex, ey, ez, imask} bytes   e* = biased exponent of 128 * grid step; imask bit s = slot s

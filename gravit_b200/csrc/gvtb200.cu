@@ -207,7 +207,7 @@ int scan_inplace(unsigned *d, size_t n, std::vector<unsigned *> &levels, size_t 
   return 0;
 }
 
-TraceTune g_tune = { 8, 12, 2 };
+TraceTune g_tune = { 16, 20, 2 };
 
 int trace_grid(bool count) {
   int idx = count ? 1 : 0;
@@ -457,16 +457,23 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
   float *d_verts = nullptr;
   uint32_t *d_faces3 = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_keys2 = nullptr, *d_vals2 = nullptr;
   unsigned *d_hist = nullptr, *d_flag = nullptr, *d_counts = nullptr;
-  float4 *bn_lo = nullptr, *bn_hi = nullptr, *wnodes = nullptr, *wtris = nullptr;
+  float4 *bn_lo = nullptr, *bn_hi = nullptr, *wnodes = nullptr, *wtris = nullptr, *sah_tb_lo = nullptr, *sah_tb_hi = nullptr;
+  uint32_t *sah_idx2 = nullptr;
+  int *sah_node_of = nullptr, *sah_node_of2 = nullptr;
+  SahNode *sah_act = nullptr, *sah_act2 = nullptr;
+  SahBin *sah_bins = nullptr;
+  unsigned sah_levels = 0;
   int2 *bn_child = nullptr, *bn_range = nullptr;
   int *bn_parent = nullptr;
   CollapseTask *d_ta = nullptr, *d_tb = nullptr;
-  std::vector<unsigned *> scan_levels;
+  std::vector<unsigned *> scan_levels, scan_levels_flag; // per-size scratch of the two device-wide scans (radix histogram, SAH flags)
   int rc = GVTB200_OK;
   auto cleanup = [&]() {
     dfree(d_verts), dfree(d_faces3), dfree(d_keys), dfree(d_vals), dfree(d_keys2), dfree(d_vals2), dfree(d_hist), dfree(d_flag);
+    dfree(sah_tb_lo), dfree(sah_tb_hi), dfree(sah_idx2), dfree(sah_node_of), dfree(sah_node_of2), dfree(sah_act), dfree(sah_act2), dfree(sah_bins);
     dfree(d_counts), dfree(bn_lo), dfree(bn_hi), dfree(wnodes), dfree(wtris), dfree(bn_child), dfree(bn_range), dfree(bn_parent), dfree(d_ta), dfree(d_tb);
     for (auto *p : scan_levels) cudaFree(p);
+    for (auto *p : scan_levels_flag) cudaFree(p);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
   };
 #define CUB(expr)                                                                                                        \
@@ -517,16 +524,65 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
     }
     c.keys = ka, c.vals = va; // 4 passes: back in d_keys / d_vals
     CUB(cudaMemcpyAsync(m->d_sorted_faces, va, n * 4, cudaMemcpyDeviceToDevice, st));
-    // binary radix tree + bottom-up fit
+    // binary tree: top-down binned SAH over the Morton-ordered triangles (GVTB200_BUILD=lbvh keeps the Karras radix tree)
     CUB(dalloc(&bn_lo, 2 * n)); CUB(dalloc(&bn_hi, 2 * n)); CUB(dalloc(&bn_child, n)); CUB(dalloc(&bn_range, n));
-    CUB(dalloc(&bn_parent, 2 * n)); CUB(dalloc(&d_flag, n));
-    CUB(cudaMemsetAsync(d_flag, 0, n * 4, st));
+    CUB(dalloc(&bn_parent, 2 * n)); CUB(dalloc(&d_flag, n + 1));
+    CUB(cudaMemsetAsync(d_flag, 0, (n + 1) * 4, st));
     CUB(cudaMemsetAsync(bn_parent, 0xFF, 2 * n * 4, st));
     c.bn_lo = bn_lo, c.bn_hi = bn_hi, c.bn_child = bn_child, c.bn_range = bn_range, c.bn_parent = bn_parent, c.bn_flag = d_flag;
-    k_leaf_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
-    if (nf > 1) {
-      k_karras<<<blocks_for(n, 256), 256, 0, st>>>(c);
-      k_refit<<<blocks_for(n, 256), 256, 0, st>>>(c);
+    const char *bmode = getenv("GVTB200_BUILD");
+    const bool use_sah = !(bmode && !strcmp(bmode, "lbvh")) && nf > 1;
+    if (use_sah) {
+      SahCtx sc;
+      memset(&sc, 0, sizeof(sc));
+      const size_t max_big = n / (GVT_SAH_SMALL + 1) + 1;
+      CUB(dalloc(&sah_tb_lo, n)); CUB(dalloc(&sah_tb_hi, n)); CUB(dalloc(&sah_idx2, n)); CUB(dalloc(&sah_node_of, n)); CUB(dalloc(&sah_node_of2, n));
+      CUB(dalloc(&sah_act, n / 2 + 1)); CUB(dalloc(&sah_act2, n / 2 + 1)); CUB(dalloc(&sah_bins, max_big * 3 * GVT_SAH_BINS));
+      sc.c = c, sc.tb_lo = sah_tb_lo, sc.tb_hi = sah_tb_hi, sc.idx = va, sc.idx2 = sah_idx2, sc.node_of = sah_node_of, sc.node_of2 = sah_node_of2;
+      sc.act = sah_act, sc.act_next = sah_act2, sc.bins = sah_bins, sc.flag = d_flag, sc.counters = d_counts;
+      k_sah_tbox<<<blocks_for(n, 256), 256, 0, st>>>(sc);
+      CUB(cudaMemsetAsync(sah_node_of, 0, n * 4, st)); // every element belongs to active node 0 (the root)
+      SahNode root;
+      memset(&root, 0, sizeof(root));
+      root.lo = 0, root.hi = (int)nf, root.id = 0, root.bslot = nf > GVT_SAH_SMALL ? 0 : -1;
+      CUB(cudaMemcpyAsync(sah_act, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+      const int2 root_range = make_int2(0, (int)nf - 1);
+      CUB(cudaMemcpyAsync(bn_range, &root_range, sizeof(int2), cudaMemcpyHostToDevice, st));
+      unsigned m_act = 1, m_big = nf > GVT_SAH_SMALL ? 1u : 0u, levels = 0;
+      while (m_act) {
+        if (++levels > 4096) CUB(cudaErrorUnknown);
+        unsigned ctr[3] = { 0u, 0u, 0u };
+        if (levels == 1) ctr[0] = 1u; // internal id 0 is the root
+        // counters[0] persists (next internal id); [1], [2] restart per level
+        if (levels == 1) CUB(cudaMemcpyAsync(d_counts, ctr, 12, cudaMemcpyHostToDevice, st));
+        else CUB(cudaMemsetAsync(d_counts + 1, 0, 8, st));
+        const unsigned n_bins = m_big * 3 * GVT_SAH_BINS;
+        k_sah_reset<<<blocks_for(std::max<size_t>(m_act, n_bins), 256), 256, 0, st>>>(sc, m_act, n_bins);
+        k_sah_cb<<<blocks_for(n, 256), 256, 0, st>>>(sc);
+        if (m_big) k_sah_bin<<<blocks_for(n, 256), 256, 0, st>>>(sc);
+        k_sah_split<<<blocks_for(m_act, 64), 64, 0, st>>>(sc, m_act);
+        k_sah_flag<<<blocks_for(n + 1, 256), 256, 0, st>>>(sc);
+        if (scan_inplace(d_flag, n + 1, scan_levels_flag, 0, st)) CUB(cudaErrorMemoryAllocation);
+        k_sah_children<<<blocks_for(m_act, 64), 64, 0, st>>>(sc, m_act);
+        k_sah_scatter<<<blocks_for(n, 256), 256, 0, st>>>(sc);
+        unsigned out[3];
+        CUB(cudaMemcpyAsync(out, d_counts, 12, cudaMemcpyDeviceToHost, st));
+        CUB(cudaStreamSynchronize(st));
+        m_act = out[1], m_big = out[2];
+        std::swap(sc.idx, sc.idx2), std::swap(sc.node_of, sc.node_of2), std::swap(sc.act, sc.act_next);
+      }
+      // final element order -> c.vals (d_vals), then the leaf boxes
+      if (sc.idx != va) CUB(cudaMemcpyAsync(va, sc.idx, n * 4, cudaMemcpyDeviceToDevice, st));
+      CUB(cudaMemsetAsync(d_counts, 0, 16, st));
+      k_leaf_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
+      sah_levels = levels;
+    } else {
+      k_leaf_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
+      if (nf > 1) {
+        CUB(cudaMemsetAsync(d_flag, 0, n * 4, st));
+        k_karras<<<blocks_for(n, 256), 256, 0, st>>>(c);
+        k_refit<<<blocks_for(n, 256), 256, 0, st>>>(c);
+      }
     }
     // collapse into 8-wide compressed nodes, one level per launch
     // worst case: one wide node per face, GVT_LEAF_MAX record slots per single-triangle leaf; shrunk below

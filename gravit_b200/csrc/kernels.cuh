@@ -62,6 +62,150 @@ __global__ void k_collapse(BuildCtx c, const CollapseTask *in, unsigned n_in, Co
   collapse_emit(c, t, w, child_base, tri_base, out + qpos);
 }
 
+// ---- binned-SAH tree, one level per round (bodies in bvh_build.h) ------------------------------------------------
+struct SahCtx {
+  BuildCtx c;
+  float4 *tb_lo, *tb_hi;     // padded triangle boxes, by triangle id
+  uint32_t *idx, *idx2;      // element order (triangle ids), current / next level
+  int *node_of, *node_of2;   // active-node index per position, -1 = settled (leaf)
+  SahNode *act, *act_next;   // active nodes of this / the next level
+  SahBin *bins;              // 3 * GVT_SAH_BINS per big active node
+  unsigned *flag;            // n + 1 goes-left flags -> exclusive scan
+  unsigned *counters;        // [0] next internal node id, [1] active nodes of the next level, [2] bin slots of the next level
+};
+__global__ void k_sah_tbox(SahCtx s) {
+  unsigned f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= s.c.n) return;
+  float4 lo, hi;
+  tri_box_padded(s.c, f, lo, hi);
+  s.tb_lo[f] = lo, s.tb_hi[f] = hi;
+}
+__global__ void k_sah_reset(SahCtx s, unsigned m, unsigned n_bins) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) {
+    for (int q = 0; q < 3; ++q) s.act[i].cb[q] = 0x7FFFFFFF, s.act[i].cb[3 + q] = (int)0x80000000;
+  }
+  if (i < n_bins) {
+    SahBin b;
+    for (int q = 0; q < 3; ++q) b.lo[q] = 0x7FFFFFFF, b.hi[q] = (int)0x80000000;
+    b.cnt = 0, b.pad = 0;
+    s.bins[i] = b;
+  }
+}
+__global__ void k_sah_cb(SahCtx s) {
+  unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= s.c.n) return;
+  int a = s.node_of[pos];
+  if (a < 0) return;
+  uint32_t f = s.idx[pos];
+  float4 l = s.tb_lo[f], h = s.tb_hi[f];
+  float c[3] = { 0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z) };
+  for (int q = 0; q < 3; ++q) {
+    int e = fenc(c[q]);
+    atomicMin(&s.act[a].cb[q], e);
+    atomicMax(&s.act[a].cb[3 + q], e);
+  }
+}
+__global__ void k_sah_bin(SahCtx s) {
+  unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= s.c.n) return;
+  int a = s.node_of[pos];
+  if (a < 0) return;
+  const SahNode &nd = s.act[a];
+  if (nd.bslot < 0) return;
+  uint32_t f = s.idx[pos];
+  float4 l = s.tb_lo[f], h = s.tb_hi[f];
+  int el[3] = { fenc(l.x), fenc(l.y), fenc(l.z) }, eh[3] = { fenc(h.x), fenc(h.y), fenc(h.z) };
+  for (int ax = 0; ax < 3; ++ax) {
+    float c = 0.5f * ((&l.x)[ax] + (&h.x)[ax]);
+    int b = sah_bin(c, fdec(nd.cb[ax]), fdec(nd.cb[3 + ax]));
+    SahBin *B = s.bins + ((size_t)nd.bslot * 3 + ax) * GVT_SAH_BINS + b;
+    for (int q = 0; q < 3; ++q) {
+      atomicMin(&B->lo[q], el[q]);
+      atomicMax(&B->hi[q], eh[q]);
+    }
+    atomicAdd(&B->cnt, 1);
+  }
+}
+__global__ void k_sah_split(SahCtx s, unsigned m) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  SahNode nd = s.act[i];
+  float lo[3], hi[3];
+  if (nd.bslot >= 0)
+    sah_eval_bins(s.bins + (size_t)nd.bslot * 3 * GVT_SAH_BINS, nd, lo, hi);
+  else
+    sah_eval_small(s.tb_lo, s.tb_hi, s.idx, nd, lo, hi);
+  s.c.bn_lo[nd.id] = make_float4(lo[0], lo[1], lo[2], 0.f);
+  s.c.bn_hi[nd.id] = make_float4(hi[0], hi[1], hi[2], 0.f);
+  s.act[i] = nd;
+}
+__global__ void k_sah_flag(SahCtx s) {
+  unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos > s.c.n) return;
+  unsigned fl = 0;
+  if (pos < s.c.n) {
+    int a = s.node_of[pos];
+    if (a >= 0) fl = sah_goes_left(s.act[a], s.tb_lo, s.tb_hi, s.idx[pos], (int)pos) ? 1u : 0u;
+  }
+  s.flag[pos] = fl;
+}
+__global__ void k_sah_children(SahCtx s, unsigned m) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  SahNode nd = s.act[i];
+  const int n = (int)s.c.n, cnt = nd.hi - nd.lo;
+  int nl = (int)(s.flag[nd.hi] - s.flag[nd.lo]);
+  if (nl <= 0 || nl >= cnt) nd.mode = 1, nl = cnt / 2; // cannot happen with consistent binning; keep the tree valid anyway
+  nd.n_left = nl;
+  int child[2];
+  for (int side = 0; side < 2; ++side) {
+    int lo = side ? nd.lo + nl : nd.lo, hi = side ? nd.hi : nd.lo + nl;
+    if (hi - lo == 1) {
+      child[side] = n - 1 + lo;
+      nd.child_active[side] = -1;
+    } else {
+      int id = (int)atomicAdd(&s.counters[0], 1u);
+      unsigned ai = atomicAdd(&s.counters[1], 1u);
+      SahNode ch;
+      ch.lo = lo, ch.hi = hi, ch.id = id;
+      ch.bslot = (hi - lo > GVT_SAH_SMALL) ? (int)atomicAdd(&s.counters[2], 1u) : -1;
+      ch.axis = ch.bin = ch.mode = ch.n_left = 0, ch.thr = 0.f, ch.child_active[0] = ch.child_active[1] = -1;
+      for (int q = 0; q < 6; ++q) ch.cb[q] = 0;
+      s.act_next[ai] = ch;
+      s.c.bn_range[id] = make_int2(lo, hi - 1);
+      child[side] = id;
+      nd.child_active[side] = (int)ai;
+    }
+    s.c.bn_parent[child[side]] = nd.id;
+  }
+  s.c.bn_child[nd.id] = make_int2(child[0], child[1]);
+  s.act[i] = nd;
+}
+__global__ void k_sah_scatter(SahCtx s) {
+  unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= s.c.n) return;
+  int a = s.node_of[pos];
+  uint32_t f = s.idx[pos];
+  if (a < 0) {
+    s.idx2[pos] = f, s.node_of2[pos] = -1;
+    return;
+  }
+  const SahNode &nd = s.act[a];
+  unsigned np;
+  bool left;
+  if (nd.mode == 1) {
+    left = ((int)pos - nd.lo) < nd.n_left;
+    np = pos;
+  } else {
+    left = (s.flag[pos + 1] - s.flag[pos]) != 0u;
+    unsigned lbefore = s.flag[pos] - s.flag[nd.lo];
+    np = left ? (unsigned)nd.lo + lbefore : (unsigned)(nd.lo + nd.n_left) + (pos - (unsigned)nd.lo) - lbefore;
+  }
+  s.idx2[np] = f;
+  s.node_of2[np] = nd.child_active[left ? 0 : 1];
+}
+
 // ---- LSD radix sort, 8 bits per pass, stable; keys + values (uint32) ---------------------------------------
 #define RS_THREADS 256
 #define RS_ITEMS 8

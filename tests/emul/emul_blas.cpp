@@ -18,7 +18,7 @@ using namespace gvt;
 struct EmulMesh {
   std::vector<float> verts;
   std::vector<uint32_t> faces;
-  std::vector<uint32_t> keys_unsorted, keys, vals;
+  std::vector<uint32_t> keys_unsorted, keys, vals, morton_order;
   std::vector<float4> bn_lo, bn_hi;
   std::vector<int2> bn_child, bn_range;
   std::vector<int> bn_parent;
@@ -60,8 +60,87 @@ EM_API void *emul_build(const float *verts, unsigned nv, const uint32_t *faces, 
   m->bn_lo.resize(nb), m->bn_hi.resize(nb), m->bn_child.resize(nb), m->bn_range.resize(nb), m->bn_parent.assign(nb, -1);
   c.bn_lo = m->bn_lo.data(), c.bn_hi = m->bn_hi.data(), c.bn_child = m->bn_child.data(), c.bn_range = m->bn_range.data();
   c.bn_parent = m->bn_parent.data();
+  m->morton_order = m->vals; // the Morton-sorted face order (parity hook); the SAH build re-orders vals
+  const char *bmode = getenv("GVTB200_BUILD");
+  const bool use_sah = !(bmode && !strcmp(bmode, "lbvh")) && nf > 1;
+  if (use_sah) {
+    // top-down binned SAH with the product's per-node bodies (bvh_build.h); the device runs the same bodies level by level
+    std::vector<float4> tb_lo(nf), tb_hi(nf);
+    for (unsigned f = 0; f < nf; ++f) tri_box_padded(c, f, tb_lo[f], tb_hi[f]);
+    std::vector<uint32_t> idx(m->vals);
+    std::vector<SahBin> bins(3 * GVT_SAH_BINS);
+    int next_internal = 1;
+    std::vector<SahNode> work;
+    SahNode root;
+    memset(&root, 0, sizeof(root));
+    root.lo = 0, root.hi = (int)nf, root.id = 0;
+    c.bn_range[0] = make_int2(0, (int)nf - 1);
+    c.bn_parent[0] = -1;
+    work.push_back(root);
+    while (!work.empty()) {
+      SahNode nd = work.back();
+      work.pop_back();
+      const int cnt = nd.hi - nd.lo;
+      for (int q = 0; q < 3; ++q) nd.cb[q] = 0x7FFFFFFF, nd.cb[3 + q] = (int)0x80000000;
+      for (int p = nd.lo; p < nd.hi; ++p) {
+        float4 l = tb_lo[idx[p]], h = tb_hi[idx[p]];
+        float cc[3] = { 0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z) };
+        for (int q = 0; q < 3; ++q) nd.cb[q] = std::min(nd.cb[q], fenc(cc[q])), nd.cb[3 + q] = std::max(nd.cb[3 + q], fenc(cc[q]));
+      }
+      float lo[3], hi[3];
+      if (cnt > GVT_SAH_SMALL) {
+        for (auto &b : bins) {
+          for (int q = 0; q < 3; ++q) b.lo[q] = 0x7FFFFFFF, b.hi[q] = (int)0x80000000;
+          b.cnt = 0, b.pad = 0;
+        }
+        for (int p = nd.lo; p < nd.hi; ++p) {
+          float4 l = tb_lo[idx[p]], h = tb_hi[idx[p]];
+          for (int ax = 0; ax < 3; ++ax) {
+            float cc = 0.5f * ((&l.x)[ax] + (&h.x)[ax]);
+            SahBin &B = bins[ax * GVT_SAH_BINS + sah_bin(cc, fdec(nd.cb[ax]), fdec(nd.cb[3 + ax]))];
+            B.lo[0] = std::min(B.lo[0], fenc(l.x)), B.lo[1] = std::min(B.lo[1], fenc(l.y)), B.lo[2] = std::min(B.lo[2], fenc(l.z));
+            B.hi[0] = std::max(B.hi[0], fenc(h.x)), B.hi[1] = std::max(B.hi[1], fenc(h.y)), B.hi[2] = std::max(B.hi[2], fenc(h.z));
+            B.cnt++;
+          }
+        }
+        sah_eval_bins(bins.data(), nd, lo, hi);
+      } else {
+        sah_eval_small(tb_lo.data(), tb_hi.data(), idx.data(), nd, lo, hi);
+      }
+      c.bn_lo[nd.id] = make_float4(lo[0], lo[1], lo[2], 0.f);
+      c.bn_hi[nd.id] = make_float4(hi[0], hi[1], hi[2], 0.f);
+      std::vector<uint32_t> L, R;
+      for (int p = nd.lo; p < nd.hi; ++p) (sah_goes_left(nd, tb_lo.data(), tb_hi.data(), idx[p], p) ? L : R).push_back(idx[p]);
+      if (L.empty() || R.empty()) { // same guard as k_sah_children
+        L.assign(idx.begin() + nd.lo, idx.begin() + nd.lo + cnt / 2);
+        R.assign(idx.begin() + nd.lo + cnt / 2, idx.begin() + nd.hi);
+      }
+      std::copy(L.begin(), L.end(), idx.begin() + nd.lo);
+      std::copy(R.begin(), R.end(), idx.begin() + nd.lo + L.size());
+      int child[2];
+      for (int side = 0; side < 2; ++side) {
+        int clo = side ? nd.lo + (int)L.size() : nd.lo, chi = side ? nd.hi : nd.lo + (int)L.size();
+        if (chi - clo == 1) {
+          child[side] = (int)nf - 1 + clo;
+        } else {
+          SahNode ch;
+          memset(&ch, 0, sizeof(ch));
+          ch.lo = clo, ch.hi = chi, ch.id = next_internal++;
+          c.bn_range[ch.id] = make_int2(clo, chi - 1);
+          child[side] = ch.id;
+          work.push_back(ch);
+        }
+        c.bn_parent[child[side]] = nd.id;
+      }
+      c.bn_child[nd.id] = make_int2(child[0], child[1]);
+    }
+    m->vals = idx;
+    c.vals = m->vals.data();
+    for (unsigned k = 0; k < nf; ++k) leaf_setup(c, k);
+  } else {
   for (unsigned k = 0; k < nf; ++k) leaf_setup(c, k);
   for (unsigned i = 0; i + 1 < nf; ++i) karras_node(c, (int)i);
+
   // refit: post-order
   if (nf > 1) {
     std::vector<int> stack, order;
@@ -81,6 +160,7 @@ EM_API void *emul_build(const float *verts, unsigned nv, const uint32_t *faces, 
       c.bn_lo[b] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
       c.bn_hi[b] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
     }
+  }
   }
   // collapse, level by level
   m->wnodes.assign(GVT_NODE_WORDS * (size_t)std::max(1u, nf), make_float4(0, 0, 0, 0));
@@ -120,7 +200,7 @@ EM_API void emul_destroy(void *p) { delete (EmulMesh *)p; }
 EM_API void emul_morton(void *p, uint32_t *codes, uint32_t *sorted_faces) {
   EmulMesh *m = (EmulMesh *)p;
   if (codes) memcpy(codes, m->keys_unsorted.data(), m->keys_unsorted.size() * 4);
-  if (sorted_faces) memcpy(sorted_faces, m->vals.data(), m->vals.size() * 4);
+  if (sorted_faces) memcpy(sorted_faces, m->morton_order.data(), m->morton_order.size() * 4);
 }
 EM_API void emul_stats(void *p, uint64_t *st) {
   EmulMesh *m = (EmulMesh *)p;

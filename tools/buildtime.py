@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""BLAS build time / size for the bench meshes and a large gyroid brick.  python tools/buildtime.py [res]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+import gravit_b200 as g  # noqa: E402
+from scenes import library  # noqa: E402
+
+g.init(0)
+res = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+cases = [("bunny70k", library.bunny70k_mesh()), ("sibenik", library.sibenik_scene(64, 36).meshes[0])]
+t0 = time.time()
+v, t = library.gyroid_brick(res, (0, 0, 0), 1)
+print(f"gyroid res {res}: {len(t)} tris generated in {time.time()-t0:.1f} s", flush=True)
+cases.append((f"gyroid{res}", library.MeshDesc(v, t, True, None)))
+for name, m in cases:
+    verts = np.asarray(m.verts, np.float32).reshape(-1, 3)
+    faces = np.asarray(m.tris, np.uint32).reshape(-1, 3) - (1 if m.one_based else 0)
+    for rep in range(2):
+        t0 = time.time()
+        mesh = g.Mesh(verts, faces)
+        wall = time.time() - t0
+        st = mesh.stats()
+        if rep == 1:
+            print(name, "tris", len(faces), st, f"wall {wall*1e3:.1f} ms", flush=True)
+        mesh.close()
