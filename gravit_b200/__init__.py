@@ -88,7 +88,7 @@ def lib():
         vp, sz, i32, u32, f = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_float
         L.gvtb200_init.argtypes = [i32]
         L.gvtb200_device_info.argtypes = [vp, vp, vp, vp]
-        L.gvtb200_set_tuning.argtypes = [i32, i32, i32]
+        L.gvtb200_set_tuning.argtypes = [i32, i32, i32, i32]
         L.gvtb200_mesh_create.argtypes = [vp, u32, vp, u32, vp, vp, vp, u32, vp, vp, vp]
         L.gvtb200_mesh_destroy.argtypes = [vp]
         L.gvtb200_mesh_morton.argtypes = [vp, vp, vp]

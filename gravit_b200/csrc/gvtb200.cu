@@ -207,7 +207,7 @@ int scan_inplace(unsigned *d, size_t n, std::vector<unsigned *> &levels, size_t 
   return 0;
 }
 
-TraceTune g_tune = { 16, 20, 2 };
+TraceTune g_tune = { 16, 20, 2, 2 };
 
 int trace_grid(bool count) {
   int idx = count ? 1 : 0;
@@ -407,8 +407,8 @@ int gvtb200_init(int device) {
   g_device = device;
   g_trace_blocks_per_sm[0] = g_trace_blocks_per_sm[1] = 0;
   if (const char *e = getenv("GVTB200_TUNE")) { // "refill_at,exit_at,postpone_num" (measurement hook)
-    int a = 0, b = 0, c = 0;
-    if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && gvtb200_set_tuning(a, b, c)) return GVTB200_ERR_INVALID;
+    int a = 0, b = 0, c = 0, d = 1;
+    if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &d) >= 3 && gvtb200_set_tuning(a, b, c, d)) return GVTB200_ERR_INVALID;
   }
   CU(cudaFree(0));
   return GVTB200_OK;
@@ -417,10 +417,11 @@ int gvtb200_init(int device) {
 const char *gvtb200_last_error(void) { return t_err.c_str(); }
 int gvtb200_current_device(void) { return g_device; }
 
-int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num) {
-  if (refill_at < 1 || refill_at > 32 || exit_at < 1 || exit_at > 32 || postpone_num < 0 || postpone_num > 8)
-    return fail(GVTB200_ERR_INVALID, "tuning out of range: refill_at %d exit_at %d (1..32), postpone_num %d (0..8)", refill_at, exit_at, postpone_num);
-  g_tune.refill_at = refill_at, g_tune.exit_at = exit_at, g_tune.postpone_num = postpone_num;
+int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num, int node_burst) {
+  if (refill_at < 1 || refill_at > 32 || exit_at < 1 || exit_at > 32 || postpone_num < 0 || postpone_num > 8 || node_burst < 1 || node_burst > 64)
+    return fail(GVTB200_ERR_INVALID, "tuning out of range: refill_at %d exit_at %d (1..32), postpone_num %d (0..8), node_burst %d (1..64)",
+                refill_at, exit_at, postpone_num, node_burst);
+  g_tune.refill_at = refill_at, g_tune.exit_at = exit_at, g_tune.postpone_num = postpone_num, g_tune.node_burst = node_burst;
   return GVTB200_OK;
 }
 
@@ -575,6 +576,7 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
       if (sc.idx != va) CUB(cudaMemcpyAsync(va, sc.idx, n * 4, cudaMemcpyDeviceToDevice, st));
       CUB(cudaMemsetAsync(d_counts, 0, 16, st));
       k_leaf_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
+      (void)sah_levels;
       sah_levels = levels;
     } else {
       k_leaf_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
@@ -801,6 +803,7 @@ int gvtb200_trace(gvtb200_mesh m, gvtb200_ray *rays, size_t n_rays, size_t begin
   CU(m->q_hit.ensure(n, true));
   TraceQueues tq;
   ShadeQueues sq;
+  memset(&tq, 0, sizeof(tq));
   QueueMem *qa = &m->q_in, *qb = &m->q_nx;
   for (int wave = 0; wave < max_depth; ++wave) {
     CU(cudaMemsetAsync(m->d_work, 0, 8, st));
@@ -1117,11 +1120,14 @@ int gvtb200_framebuffer_read(gvtb200_scene s, float *rgba, size_t n_floats) {
 }
 
 // one wave = Adapter::trace on every queued ray + the shadow rays it generated; `depth` waves drain a frame
-static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool timed) {
+static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool timed, const CameraGen *gen = nullptr) {
   SceneDev sd = scene_dev(*s);
   TraceQueues tq;
   ShadeQueues sq;
+  memset(&tq, 0, sizeof(tq));
   for (int wave = 0; wave < waves; ++wave) {
+    tq.gen.enabled = 0;
+    if (gen && wave == 0) tq.gen = *gen; // the first wave makes its own camera rays (no queue round trip through HBM)
     CU(cudaMemsetAsync(s->d_work, 0, 32, s->stream));
     CU(cudaMemsetAsync(s->q_b.q.count, 0, 4, s->stream));
     CU(cudaMemsetAsync(s->q_sh.q.count, 0, 4, s->stream));
@@ -1133,6 +1139,7 @@ static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool tim
     sq.hq = s->q_hit.q, sq.hit = s->q_hit.hit, sq.shq = s->q_sh.q, sq.nxq = s->q_b.q, sq.fin = null_queue(s->d_work + 5);
     launch_shade(fp, sd, sq, 0, s->stream);
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[3], s->stream));
+    tq.gen.enabled = 0;
     tq.in = s->q_sh.q, tq.hq = null_queue(s->d_work + 3), tq.hit = nullptr, tq.work = s->d_work + 1;
     launch_trace(s->profile, fp, sd, tq, 0, s->stream);
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[4], s->stream));
@@ -1173,9 +1180,17 @@ int gvtb200_render_frame_tiles(gvtb200_scene s, int row0, int row1, int tile_row
   CU(cudaMemsetAsync(s->q_a.q.count, 0, 4, st));
   CU(cudaMemsetAsync(s->q_ex.q.count, 0, 4, st));
   if (count) {
-    k_camera_route<<<g_sms * 8, 256, 0, st>>>(fp, scene_dev(*s), tiles, count, s->q_a.q);
-    LAUNCHED(1);
-    if (int rc = run_waves(s, fp, std::max(1, s->depth), true)) return rc;
+    // few instances: the first trace wave makes and routes its own camera rays in registers.  Many instances: the
+    // top-level routing is long and runs better with full warps in its own kernel (measured: 32x32 grid, 1.79 vs 1.87 ms)
+    if (s->inst.size() <= 4) {
+      CameraGen gen;
+      gen.enabled = 1, gen.tiles = tiles, gen.count = (unsigned)count;
+      if (int rc = run_waves(s, fp, std::max(1, s->depth), true, &gen)) return rc;
+    } else {
+      k_camera_route<<<g_sms * 8, 256, 0, st>>>(fp, scene_dev(*s), tiles, count, s->q_a.q);
+      LAUNCHED(1);
+      if (int rc = run_waves(s, fp, std::max(1, s->depth), true)) return rc;
+    }
   }
   k_fb_clamp<<<blocks_for(s->fb_pix, 256), 256, 0, st>>>(s->d_fb, s->fb_pix);
   LAUNCHED(1);

@@ -443,9 +443,17 @@ struct TraceTune {
   int refill_at;    // refill when at least this many lanes are idle (1..32)
   int exit_at;      // leave the traversal loop when at least this many lanes are not traversing and work is waiting
   int postpone_num; // postpone triangle tests while lanes_with_triangles * 8 < traversing_lanes * postpone_num
+  int node_burst;   // node visits a lane may make per lock-step iteration before the warp votes again (it stops at the
+                    // first triangle group)
 };
 
+struct CameraGen { // in-kernel camera-ray source (replaces reading a queue of camera rays back from HBM)
+  int enabled;
+  RowTiles tiles;
+  unsigned count; // rays of this film shard
+};
 struct TraceQueues {
+  CameraGen gen; // enabled: input ray i is camera ray i of the shard, generated and routed in registers; `in` is unused
   RayQueue in;
   RayQueue hq;    // closest hits: ray (t = hit t) + hit column
   int4 *hit;      // hit column of hq: prim, triangle slot, u bits, v bits
@@ -487,11 +495,19 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
   for (unsigned k = threadIdx.x; k < 8u * 256u; k += TRACE_THREADS) s_lut[k] = (unsigned char)best_slot(k & 255u, k >> 8);
   __syncthreads();
   const unsigned FULL = 0xffffffffu;
-  const unsigned n = min(*q.in.count, q.in.cap);
+  const bool gen = q.gen.enabled != 0;
+  const unsigned n = gen ? q.gen.count : min(*q.in.count, q.in.cap);
   const unsigned lane = threadIdx.x & 31;
   const unsigned ltmask = (1u << lane) - 1u;
   const bool to_light = (fp.flags & FLAG_SHADOW_TO_LIGHT) != 0;
-  unsigned long long c_visits = 0, c_shok = 0, c_fb = 0, c_exp = 0, c_ovf = 0;
+  unsigned long long c_visits = 0, c_shok = 0, c_fb = 0, c_exp = 0, c_ovf = 0, c_routed = 0;
+  const unsigned per_row = (unsigned)(fp.cam.W * fp.cam.samples * fp.cam.samples);
+  auto camera_index = [&](unsigned i) -> size_t { // shard ray i -> global camera-ray index (RowTiles arithmetic)
+    unsigned lr = i / per_row, within = i - lr * per_row;
+    unsigned b = lr / (unsigned)q.gen.tiles.tile_rows, k = lr - b * (unsigned)q.gen.tiles.tile_rows;
+    size_t row = (size_t)q.gen.tiles.row0 + ((size_t)b * q.gen.tiles.stride + q.gen.tiles.index) * q.gen.tiles.tile_rows + k;
+    return row * per_row + within;
+  };
   TravCounters tc;
   tc.nodes = 0, tc.tris = 0;
   SmemStack stack;
@@ -524,11 +540,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
     c_visits++;
   };
   auto reload = [&](Ray &r) { // the columns k_trace does not keep in registers
-    const float4 c2 = q.in.c2[idx];
-    const int4 c3 = q.in.c3[idx];
+    if (gen) {
+      camera_ray(fp.cam, camera_index(idx), r); // regenerated: cheaper than a round trip through HBM
+    } else {
+      const float4 c2 = q.in.c2[idx];
+      const int4 c3 = q.in.c3[idx];
+      r.color = v3(c2.x, c2.y, c2.z), r.t = c2.w;
+      r.id = c3.x, r.depth = c3.y, r.w = u2f((uint32_t)c3.z), r.type = c3.w;
+    }
     r.o = o, r.t_min = t_min, r.d = d, r.t_max = t_max;
-    r.color = v3(c2.x, c2.y, c2.z), r.t = c2.w;
-    r.id = c3.x, r.depth = c3.y, r.w = u2f((uint32_t)c3.z), r.type = c3.w;
   };
 
   for (;;) {
@@ -544,14 +564,28 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
         const unsigned my = base + (unsigned)__popc(idle & ltmask);
         if (my < n) {
           idx = my;
-          const float4 c0 = q.in.c0[idx], c1 = q.in.c1[idx];
-          type = q.in.c3[idx].w;
-          inst = (mode == 1) ? 0 : q.in.inst[idx];
-          o = v3(c0.x, c0.y, c0.z), t_min = c0.w, d = v3(c1.x, c1.y, c1.z), t_max = c1.w;
-          any = (type == RAY_SHADOW);
-          first = true;
-          active = true;
-          begin_instance();
+          if (gen) { // gvtPerspectiveCamera::generateRays + FilterRaysLocally (first routing hop), in registers
+            Ray r;
+            camera_ray(fp.cam, camera_index(idx), r);
+            float t;
+            const int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, -1, (fp.flags & FLAG_ENTER_INSIDE) != 0, t);
+            if (next >= 0) {
+              c_routed++;
+              o = xadd(r.o, xmul(r.d, xmul(t, 0.95f))); // TracerBase.h:394
+              t_min = r.t_min, d = r.d, t_max = r.t_max, type = r.type, inst = next;
+              any = false, first = true, active = true;
+              begin_instance();
+            }
+          } else {
+            const float4 c0 = q.in.c0[idx], c1 = q.in.c1[idx];
+            type = q.in.c3[idx].w;
+            inst = (mode == 1) ? 0 : q.in.inst[idx];
+            o = v3(c0.x, c0.y, c0.z), t_min = c0.w, d = v3(c1.x, c1.y, c1.z), t_max = c1.w;
+            any = (type == RAY_SHADOW);
+            first = true;
+            active = true;
+            begin_instance();
+          }
         }
       }
       idle = __ballot_sync(FULL, !active);
@@ -568,7 +602,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
       if (tm == 0u) break;
       const unsigned waiting = 32u - (unsigned)__popc(tm);
       if (waiting >= (unsigned)tune.exit_at && ((~tm & ~idle) != 0u || !exhausted)) break;
-      if (trav && trav_has_nodes(tv)) node_step<COUNT, true>(nodes, rl, GVT_RAY_EPSILON, tv, stack, &tc, s_lut);
+      if (trav) {
+#pragma unroll 1
+        for (int k = 0; k < tune.node_burst; ++k) {
+          if (!trav_has_nodes(tv)) {
+            if (k == 0 || trav_has_tris(tv)) break; // first trip: the group popped last time may be a triangle group
+            if (!trav_next(tv, stack)) {
+              done = true;
+              break;
+            }
+            if (!trav_has_nodes(tv)) break; // popped a postponed triangle group
+          }
+          node_step<COUNT, true>(nodes, rl, GVT_RAY_EPSILON, tv, stack, &tc, s_lut);
+          if (trav_has_tris(tv)) break;
+        }
+      }
       for (;;) {
         const bool ht = trav && !done && trav_has_tris(tv);
         const unsigned tb = __ballot_sync(FULL, ht);
@@ -647,6 +695,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
   count_add(&sd.ctr->fb_adds, c_fb);
   count_add(&sd.ctr->rays_exported, c_exp);
   count_add(&sd.ctr->stack_overflows, c_ovf);
+  if (gen) {
+    count_add(&sd.ctr->routed_initial, c_routed);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&sd.ctr->camera_rays, (unsigned long long)n);
+  }
   if (COUNT) {
     count_add(&sd.ctr->nodes_visited, tc.nodes);
     count_add(&sd.ctr->tris_tested, tc.tris);

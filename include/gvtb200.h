@@ -92,8 +92,9 @@ GVTB200_API int gvtb200_current_device(void);
 GVTB200_API int gvtb200_device_info(int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor);
 /* scheduling knobs of the trace kernel (results do not depend on them): refill idle lanes when >= refill_at lanes wait,
  * leave the lock-step traversal loop when >= exit_at lanes are not traversing, postpone triangle tests while fewer than
- * postpone_num/8 of the traversing lanes hold a triangle.  Replaces the TBB grain size of EmbreeMeshAdapter.cpp:648. */
-GVTB200_API int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num);
+ * postpone_num/8 of the traversing lanes hold a triangle, let a lane visit up to node_burst nodes between two warp votes.
+ * Replaces the TBB grain size of EmbreeMeshAdapter.cpp:648. */
+GVTB200_API int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num, int node_burst);
 
 /* ---- B1: the engine adapter (Adapter.h:44-88) --------------------------------------------------------- */
 /* replaces EmbreeMeshAdapter::EmbreeMeshAdapter (adapter/embree/EmbreeMeshAdapter.cpp:125-162): takes the

@@ -46,7 +46,7 @@ def main():
         e = s.engine()
         ref_crc = None
         for tune in tunes:
-            g.check(g.lib().gvtb200_set_tuning(*tune))
+            g.check(g.lib().gvtb200_set_tuning(*(tune + (1,) * (4 - len(tune)))))
             for _ in range(3):
                 e.render_async(d.height)
             e.sync()
