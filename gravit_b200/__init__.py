@@ -55,7 +55,7 @@ C_ABI_SYMBOLS = (
     "gvtb200_scene_add_instance gvtb200_scene_set_lights gvtb200_scene_set_camera gvtb200_scene_set_film "
     "gvtb200_scene_set_flags gvtb200_scene_commit gvtb200_scene_tlas_order gvtb200_camera_rays gvtb200_route "
     "gvtb200_shuffle gvtb200_framebuffer_clear gvtb200_framebuffer_read gvtb200_render_frame gvtb200_render_frame_async "
-    "gvtb200_render_frame_tiles gvtb200_scene_set_stream gvtb200_launch_count gvtb200_scene_sync gvtb200_scene_counters gvtb200_scene_profile_counters gvtb200_scene_device_framebuffer "
+    "gvtb200_render_frame_tiles gvtb200_scene_set_stream gvtb200_launch_count gvtb200_scene_sync gvtb200_scene_counters gvtb200_scene_profile_counters gvtb200_scene_profile_launches gvtb200_scene_launch_records gvtb200_scene_device_framebuffer "
     "gvtb200_framebuffer_clamp gvtb200_scene_last_timing gvtb200_domain_set_owner gvtb200_domain_begin_frame "
     "gvtb200_domain_drain_local gvtb200_domain_export gvtb200_domain_import gvtb200_domain_pending"
 ).split()
@@ -119,6 +119,8 @@ def lib():
         L.gvtb200_launch_count.restype = C.c_ulonglong
         L.gvtb200_scene_counters.argtypes = [vp, vp]
         L.gvtb200_scene_profile_counters.argtypes = [vp, i32]
+        L.gvtb200_scene_profile_launches.argtypes = [vp, i32]
+        L.gvtb200_scene_launch_records.argtypes = [vp, i32, vp, vp, vp, vp]
         L.gvtb200_scene_device_framebuffer.argtypes = [vp, vp, vp]
         L.gvtb200_scene_last_timing.argtypes = [vp, vp, vp]
         L.gvtb200_domain_set_owner.argtypes = [vp, vp, i32, i32, i32]
@@ -352,6 +354,17 @@ class EngineScene:
 
     def profile_counters(self, on=True):
         check(lib().gvtb200_scene_profile_counters(self.h, int(on)))
+
+    def profile_launches(self, on=True):
+        check(lib().gvtb200_scene_profile_launches(self.h, 1 if on else 0))
+
+    def launch_records(self):
+        """[(kind, ms, counters-after-the-launch)] of the last frame; kind 0 camera+route, 1 closest-hit trace, 2 shade, 3 shadow trace."""
+        cap = 64
+        n = C.c_int(0)
+        kind, ms, ctr = np.zeros(cap, np.int32), np.zeros(cap, np.float32), np.zeros((cap, len(COUNTER_FIELDS)), np.uint64)
+        check(lib().gvtb200_scene_launch_records(self.h, cap, C.byref(n), _fp(kind), _fp(ms), _fp(ctr)))
+        return [(int(kind[i]), float(ms[i]), dict(zip(COUNTER_FIELDS, (int(x) for x in ctr[i])))) for i in range(n.value)]
 
     def last_timing(self):
         ms, k = C.c_float(), (C.c_float * 3)()

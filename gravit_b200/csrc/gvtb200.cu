@@ -167,6 +167,13 @@ struct gvtb200_scene_s {
   // device
   cudaStream_t stream = nullptr, own_stream = nullptr;
   cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+  // per-launch instrumentation (gvtb200_scene_profile_launches): one event pair and one counter snapshot per kernel launch
+  enum { MAX_LAUNCH_REC = 64 };
+  bool launch_prof = false;
+  int n_launch_rec = 0;
+  int launch_kind[MAX_LAUNCH_REC];
+  cudaEvent_t lev[2 * MAX_LAUNCH_REC] = {};
+  DevCounters *d_snap = nullptr;
   Instance *d_inst = nullptr;
   Blas *d_blas = nullptr;
   float4 *d_tnodes = nullptr, *d_tboxes = nullptr;
@@ -879,6 +886,9 @@ int gvtb200_scene_destroy(gvtb200_scene s) {
   s->q_a.release(), s->q_b.release(), s->q_sh.release(), s->q_ex.release(), s->q_tmp.release(), s->q_hit.release();
   for (auto &e : s->ev)
     if (e) cudaEventDestroy(e);
+  for (auto &e : s->lev)
+    if (e) cudaEventDestroy(e);
+  dfree(s->d_snap);
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   delete s;
   return GVTB200_OK;
@@ -1119,6 +1129,22 @@ int gvtb200_framebuffer_read(gvtb200_scene s, float *rgba, size_t n_floats) {
   return GVTB200_OK;
 }
 
+// per-launch instrumentation: bracket one kernel launch with events, snapshot the counters after it
+static int launch_rec_begin(gvtb200_scene s, int kind) {
+  if (!s->launch_prof || s->n_launch_rec >= gvtb200_scene_s::MAX_LAUNCH_REC) return -1;
+  int k = s->n_launch_rec++;
+  s->launch_kind[k] = kind;
+  for (int j = 0; j < 2; ++j)
+    if (!s->lev[2 * k + j] && cudaEventCreate(&s->lev[2 * k + j]) != cudaSuccess) return -1;
+  cudaEventRecord(s->lev[2 * k], s->stream);
+  return k;
+}
+static void launch_rec_end(gvtb200_scene s, int k) {
+  if (k < 0) return;
+  cudaEventRecord(s->lev[2 * k + 1], s->stream);
+  if (s->d_snap) cudaMemcpyAsync(s->d_snap + k, s->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToDevice, s->stream);
+}
+
 // one wave = Adapter::trace on every queued ray + the shadow rays it generated; `depth` waves drain a frame
 static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool timed, const CameraGen *gen = nullptr) {
   SceneDev sd = scene_dev(*s);
@@ -1135,13 +1161,19 @@ static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool tim
     tq.in = s->q_a.q, tq.hq = s->q_hit.q, tq.hit = s->q_hit.hit, tq.mvq = null_queue(s->d_work + 2), tq.exq = s->q_ex.q;
     tq.fin = null_queue(s->d_work + 5), tq.work = s->d_work;
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[2], s->stream));
+    int rk = launch_rec_begin(s, 1);
     launch_trace(s->profile, fp, sd, tq, 0, s->stream);
+    launch_rec_end(s, rk);
     sq.hq = s->q_hit.q, sq.hit = s->q_hit.hit, sq.shq = s->q_sh.q, sq.nxq = s->q_b.q, sq.fin = null_queue(s->d_work + 5);
+    rk = launch_rec_begin(s, 2);
     launch_shade(fp, sd, sq, 0, s->stream);
+    launch_rec_end(s, rk);
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[3], s->stream));
     tq.gen.enabled = 0;
     tq.in = s->q_sh.q, tq.hq = null_queue(s->d_work + 3), tq.hit = nullptr, tq.work = s->d_work + 1;
+    rk = launch_rec_begin(s, 3);
     launch_trace(s->profile, fp, sd, tq, 0, s->stream);
+    launch_rec_end(s, rk);
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[4], s->stream));
     std::swap(s->q_a, s->q_b);
   }
@@ -1179,6 +1211,7 @@ int gvtb200_render_frame_tiles(gvtb200_scene s, int row0, int row1, int tile_row
   CU(cudaMemsetAsync(s->d_ctr, 0, sizeof(DevCounters), st));
   CU(cudaMemsetAsync(s->q_a.q.count, 0, 4, st));
   CU(cudaMemsetAsync(s->q_ex.q.count, 0, 4, st));
+  s->n_launch_rec = 0;
   if (count) {
     // few instances: the first trace wave makes and routes its own camera rays in registers.  Many instances: the
     // top-level routing is long and runs better with full warps in its own kernel (measured: 32x32 grid, 1.79 vs 1.87 ms)
@@ -1187,8 +1220,10 @@ int gvtb200_render_frame_tiles(gvtb200_scene s, int row0, int row1, int tile_row
       gen.enabled = 1, gen.tiles = tiles, gen.count = (unsigned)count;
       if (int rc = run_waves(s, fp, std::max(1, s->depth), true, &gen)) return rc;
     } else {
+      int rk = launch_rec_begin(s, 0);
       k_camera_route<<<g_sms * 8, 256, 0, st>>>(fp, scene_dev(*s), tiles, count, s->q_a.q);
       LAUNCHED(1);
+      launch_rec_end(s, rk);
       if (int rc = run_waves(s, fp, std::max(1, s->depth), true)) return rc;
     }
   }
@@ -1232,6 +1267,29 @@ int gvtb200_render_frame(gvtb200_scene s, int row0, int row1, float *rgba_out, g
   if (counters) CU(cudaMemcpyAsync(counters, s->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaGetLastError());
+  return GVTB200_OK;
+}
+int gvtb200_scene_profile_launches(gvtb200_scene s, int enable) {
+  NEED_INIT();
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  CU(cudaSetDevice(g_device));
+  if (enable && !s->d_snap) CU(dalloc(&s->d_snap, (size_t)gvtb200_scene_s::MAX_LAUNCH_REC));
+  s->launch_prof = enable != 0;
+  s->n_launch_rec = 0;
+  return GVTB200_OK;
+}
+int gvtb200_scene_launch_records(gvtb200_scene s, int cap, int *n, int32_t *kind, float *ms, gvtb200_counters *after) {
+  NEED_INIT();
+  if (!s || !n) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(g_device));
+  CU(cudaStreamSynchronize(s->stream));
+  int k = std::min(cap, s->n_launch_rec);
+  for (int i = 0; i < k; ++i) {
+    if (kind) kind[i] = s->launch_kind[i];
+    if (ms) CU(cudaEventElapsedTime(&ms[i], s->lev[2 * i], s->lev[2 * i + 1]));
+  }
+  if (after && k) CU(cudaMemcpy(after, s->d_snap, (size_t)k * sizeof(DevCounters), cudaMemcpyDeviceToHost));
+  *n = k;
   return GVTB200_OK;
 }
 int gvtb200_scene_profile_counters(gvtb200_scene s, int enable) {

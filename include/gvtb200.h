@@ -198,6 +198,11 @@ GVTB200_API int gvtb200_scene_set_stream(gvtb200_scene scene, void *cuda_stream)
 GVTB200_API unsigned long long gvtb200_launch_count(void);
 GVTB200_API int gvtb200_scene_counters(gvtb200_scene scene, gvtb200_counters *out);
 GVTB200_API int gvtb200_scene_profile_counters(gvtb200_scene scene, int enable);
+/* per-launch instrumentation of the frame calls: when enabled every kernel launch of a frame is bracketed by CUDA events on
+ * the scene's stream and followed by a snapshot of the (cumulative) counters.  launch_records returns, for the last frame,
+ * kind[i] (0 camera+route, 1 closest-hit trace, 2 shade, 3 shadow trace), ms[i] and after[i]; any of the three may be NULL. */
+GVTB200_API int gvtb200_scene_profile_launches(gvtb200_scene scene, int enable);
+GVTB200_API int gvtb200_scene_launch_records(gvtb200_scene scene, int cap, int *n, int32_t *kind, float *ms, gvtb200_counters *after);
 /* device pointer of the RGBA float framebuffer (W*H*4) and the CUDA stream the scene launches on, so that
  * the multi-GPU drivers can hand them to NCCL (replaces icetCompositeImage, composite/IceTComposite.cpp:96) */
 GVTB200_API int gvtb200_scene_device_framebuffer(gvtb200_scene scene, void **d_rgba, void **cuda_stream);
