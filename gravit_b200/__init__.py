@@ -40,7 +40,7 @@ LIGHT_DTYPE = np.dtype(
 MATERIAL_DTYPE = np.dtype([("type", "<i4"), ("kd", "<f4", 3), ("ks", "<f4", 3), ("alpha", "<f4")])
 COUNTER_FIELDS = (
     "camera_rays routed_initial primary_hits shadow_generated shadow_unoccluded secondary_generated fb_adds "
-    "instance_visits nodes_visited tris_tested rays_exported stack_overflows"
+    "instance_visits nodes_visited tris_tested rays_exported stack_overflows queue_overflows"
 ).split()
 
 PRIMARY, SHADOW, SECONDARY = 0, 1, 2
@@ -57,8 +57,10 @@ C_ABI_SYMBOLS = (
     "gvtb200_shuffle gvtb200_framebuffer_clear gvtb200_framebuffer_read gvtb200_render_frame gvtb200_render_frame_async "
     "gvtb200_render_frame_tiles gvtb200_scene_set_stream gvtb200_launch_count gvtb200_scene_sync gvtb200_scene_counters gvtb200_scene_profile_counters gvtb200_scene_profile_launches gvtb200_scene_launch_records gvtb200_scene_device_framebuffer "
     "gvtb200_framebuffer_clamp gvtb200_scene_last_timing gvtb200_domain_set_owner gvtb200_domain_begin_frame "
-    "gvtb200_domain_drain_local gvtb200_domain_export gvtb200_domain_import gvtb200_domain_pending"
+    "gvtb200_domain_drain_local gvtb200_domain_export gvtb200_domain_import gvtb200_domain_pending "
+    "gvtb200_p2p_export gvtb200_p2p_attach gvtb200_p2p_detach gvtb200_image_frame_p2p gvtb200_domain_round_p2p gvtb200_domain_composite_p2p"
 ).split()
+PEER_DESC_BYTES = 64 * 4 + 8 * 4 + 8 + 8 + 4 + 4  # sizeof(gvtb200_peer_desc)
 
 
 class EngineError(RuntimeError):
@@ -129,6 +131,12 @@ def lib():
         L.gvtb200_domain_export.argtypes = [vp, vp, vp, vp]
         L.gvtb200_domain_import.argtypes = [vp, vp, sz]
         L.gvtb200_domain_pending.argtypes = [vp, vp]
+        L.gvtb200_p2p_export.argtypes = [vp, i32, vp]
+        L.gvtb200_p2p_attach.argtypes = [vp, i32, i32, vp]
+        L.gvtb200_p2p_detach.argtypes = [vp]
+        L.gvtb200_image_frame_p2p.argtypes = [vp, i32, i32, i32, i32, i32]
+        L.gvtb200_domain_round_p2p.argtypes = [vp, i32, vp]
+        L.gvtb200_domain_composite_p2p.argtypes = [vp, i32]
         _lib = L
     return _lib
 
@@ -400,6 +408,35 @@ class EngineScene:
         n = C.c_uint64(0)
         check(lib().gvtb200_domain_pending(self.h, C.byref(n)))
         return n.value
+
+    # ---- NVLink peer path ----
+    def p2p_export(self, world):
+        """This rank's gvtb200_peer_desc as bytes (to be exchanged with the peers)."""
+        buf = C.create_string_buffer(PEER_DESC_BYTES)
+        check(lib().gvtb200_p2p_export(self.h, world, buf))
+        return buf.raw
+
+    def p2p_attach(self, rank, world, descs):
+        """descs: the `world` descriptors concatenated in rank order."""
+        descs = bytes(descs)
+        if len(descs) != world * PEER_DESC_BYTES:
+            raise EngineError(f"expected {world} descriptors of {PEER_DESC_BYTES} bytes, got {len(descs)} bytes")
+        check(lib().gvtb200_p2p_attach(self.h, rank, world, C.c_char_p(descs)))
+
+    def p2p_detach(self):
+        check(lib().gvtb200_p2p_detach(self.h))
+
+    def image_frame_p2p(self, h, tile_rows=8, root=0, row0=0, row1=None, phases=7):
+        check(lib().gvtb200_image_frame_p2p(self.h, row0, h if row1 is None else row1, tile_rows, root, phases))
+
+    def domain_round_p2p(self, rnd):
+        """One exchange round; returns the device address of the cumulative exported-ray counter (uint64)."""
+        p = C.c_void_p()
+        check(lib().gvtb200_domain_round_p2p(self.h, rnd, C.byref(p)))
+        return p.value
+
+    def domain_composite_p2p(self, root=0):
+        check(lib().gvtb200_domain_composite_p2p(self.h, root))
 
 
 class GvtScene:

@@ -205,7 +205,7 @@ struct FrameParams {
 
 struct DevCounters {
   unsigned long long camera_rays, routed_initial, primary_hits, shadow_generated, shadow_unoccluded, secondary_generated,
-      fb_adds, instance_visits, nodes_visited, tris_tested, rays_exported, stack_overflows;
+      fb_adds, instance_visits, nodes_visited, tris_tested, rays_exported, stack_overflows, queue_overflows;
 };
 
 // ---- counter-based RNG (replaces the per-TBB-chunk stateful generator) ------------------------

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -191,6 +192,18 @@ struct gvtb200_scene_s {
   size_t aos_cap = 0, route_cap = 0;
   float last_frame_ms = 0.f, last_kernel_ms[3] = { 0, 0, 0 };
   bool timing_valid = false;
+  // NVLink peer path (gvtb200_p2p_*): this rank's shared objects and the peers' objects mapped with CUDA IPC
+  struct {
+    bool exported = false, attached = false;
+    int rank = 0, world = 1;
+    unsigned seq = 0;            // frame sequence number (the same on every rank: all ranks render the same frames)
+    QueueMem inbox[2];           // inbound ray queues, alternated by exchange rounds
+    Mailbox *d_mail = nullptr;
+    RayQueue *d_peer_inbox = nullptr; // [2][world]
+    float *peer_fb[GVT_P2P_MAX] = {};
+    PeerMail mail;
+    void *opened[GVT_P2P_MAX][4] = {}; // cudaIpcOpenMemHandle results (closed on detach)
+  } p2p;
 };
 
 namespace {
@@ -881,6 +894,7 @@ int gvtb200_scene_create(gvtb200_scene *out) {
 int gvtb200_scene_destroy(gvtb200_scene s) {
   if (!s) return GVTB200_OK;
   if (s->stream) cudaStreamSynchronize(s->stream);
+  gvtb200_p2p_detach(s);
   dfree(s->d_inst), dfree(s->d_blas), dfree(s->d_tnodes), dfree(s->d_tboxes), dfree(s->d_fb), dfree(s->d_ctr), dfree(s->d_work), dfree(s->d_peer);
   dfree(s->d_export), dfree(s->d_next), dfree(s->d_t), dfree(s->d_aos);
   s->q_a.release(), s->q_b.release(), s->q_sh.release(), s->q_ex.release(), s->q_tmp.release(), s->q_hit.release();
@@ -1004,6 +1018,7 @@ int gvtb200_scene_tlas_order(gvtb200_scene s, int32_t *sorted_ids, int *n) {
 static int scene_fb(gvtb200_scene s) {
   size_t npix = (size_t)s->W * s->H;
   if (s->fb_pix != npix) {
+    if (s->p2p.exported) return fail(GVTB200_ERR_INVALID, "film size changed while the framebuffer is shared with peers: gvtb200_p2p_detach first");
     dfree(s->d_fb);
     CU(dalloc(&s->d_fb, npix * 4));
     s->fb_pix = npix;
@@ -1146,11 +1161,13 @@ static void launch_rec_end(gvtb200_scene s, int k) {
 }
 
 // one wave = Adapter::trace on every queued ray + the shadow rays it generated; `depth` waves drain a frame
-static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool timed, const CameraGen *gen = nullptr) {
+static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool timed, const CameraGen *gen = nullptr,
+                     const RayQueue *first_in = nullptr, const RayQueue *peer_inbox = nullptr) {
   SceneDev sd = scene_dev(*s);
   TraceQueues tq;
   ShadeQueues sq;
   memset(&tq, 0, sizeof(tq));
+  tq.peer_inbox = peer_inbox;
   for (int wave = 0; wave < waves; ++wave) {
     tq.gen.enabled = 0;
     if (gen && wave == 0) tq.gen = *gen; // the first wave makes its own camera rays (no queue round trip through HBM)
@@ -1158,7 +1175,8 @@ static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool tim
     CU(cudaMemsetAsync(s->q_b.q.count, 0, 4, s->stream));
     CU(cudaMemsetAsync(s->q_sh.q.count, 0, 4, s->stream));
     CU(cudaMemsetAsync(s->q_hit.q.count, 0, 4, s->stream));
-    tq.in = s->q_a.q, tq.hq = s->q_hit.q, tq.hit = s->q_hit.hit, tq.mvq = null_queue(s->d_work + 2), tq.exq = s->q_ex.q;
+    tq.in = (first_in && wave == 0) ? *first_in : s->q_a.q;
+    tq.hq = s->q_hit.q, tq.hit = s->q_hit.hit, tq.mvq = null_queue(s->d_work + 2), tq.exq = s->q_ex.q;
     tq.fin = null_queue(s->d_work + 5), tq.work = s->d_work;
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[2], s->stream));
     int rk = launch_rec_begin(s, 1);
@@ -1191,7 +1209,12 @@ static int frame_queues(gvtb200_scene s, size_t count) {
   return 0;
 }
 
-int gvtb200_render_frame_tiles(gvtb200_scene s, int row0, int row1, int tile_rows, int tile_index, int tile_stride) {
+// p2p_root < 0: plain frame.  p2p_root >= 0: ImageScheduler over NVLink -- the root releases its peers after its own clear,
+// every rank clamps and stores its rows into the root's framebuffer, the root waits for all of them.
+// phases (peer path only): 1 = clear (+ the root's go), 2 = trace + store the rows, 4 = the root's wait.  A production call
+// runs all three; the single-process tests, where every simulated rank shares one GPU, run the root's phase 1 before the
+// peers' frames and its phases 2|4 after them so that no spinning kernel ever waits for a kernel that is not launched yet.
+static int frame_tiles(gvtb200_scene s, int row0, int row1, int tile_rows, int tile_index, int tile_stride, int p2p_root, int phases = 7) {
   NEED_SCENE();
   if (s->world > 1) return fail(GVTB200_ERR_INVALID, "domain-partitioned scene: use the gvtb200_domain_* calls");
   if (row0 < 0 || row1 > s->H || row0 > row1) return fail(GVTB200_ERR_INVALID, "bad row range [%d,%d) of %d", row0, row1, s->H);
@@ -1206,13 +1229,23 @@ int gvtb200_render_frame_tiles(gvtb200_scene s, int row0, int row1, int tile_row
   FrameParams fp;
   build_frame_params(*s, fp);
   cudaStream_t st = s->stream;
-  CU(cudaEventRecord(s->ev[0], st));
-  CU(cudaMemsetAsync(s->d_fb, 0, s->fb_pix * 16, st)); // clearBuffer, TracerBase.h:310
-  CU(cudaMemsetAsync(s->d_ctr, 0, sizeof(DevCounters), st));
-  CU(cudaMemsetAsync(s->q_a.q.count, 0, 4, st));
-  CU(cudaMemsetAsync(s->q_ex.q.count, 0, 4, st));
-  s->n_launch_rec = 0;
-  if (count) {
+  const bool p2p = p2p_root >= 0;
+  if (!p2p) phases = 7;
+  if (phases & 1) {
+    CU(cudaEventRecord(s->ev[0], st));
+    CU(cudaMemsetAsync(s->d_fb, 0, s->fb_pix * 16, st)); // clearBuffer, TracerBase.h:310
+    CU(cudaMemsetAsync(s->d_ctr, 0, sizeof(DevCounters), st));
+    CU(cudaMemsetAsync(s->q_a.q.count, 0, 4, st));
+    CU(cudaMemsetAsync(s->q_ex.q.count, 0, 4, st));
+    s->n_launch_rec = 0;
+    if (p2p) ++s->p2p.seq;
+    if (p2p && s->p2p.rank == p2p_root) { // the framebuffer is clear: the peers may store their rows of frame `seq`
+      k_p2p_go<<<1, GVT_P2P_MAX, 0, st>>>(s->p2p.mail, s->p2p.world, s->p2p.rank, s->p2p.seq);
+      LAUNCHED(1);
+    }
+  }
+  const unsigned seq = s->p2p.seq;
+  if (count && (phases & 2)) {
     // few instances: the first trace wave makes and routes its own camera rays in registers.  Many instances: the
     // top-level routing is long and runs better with full warps in its own kernel (measured: 32x32 grid, 1.79 vs 1.87 ms)
     if (s->inst.size() <= 4) {
@@ -1227,12 +1260,35 @@ int gvtb200_render_frame_tiles(gvtb200_scene s, int row0, int row1, int tile_row
       if (int rc = run_waves(s, fp, std::max(1, s->depth), true)) return rc;
     }
   }
-  k_fb_clamp<<<blocks_for(s->fb_pix, 256), 256, 0, st>>>(s->d_fb, s->fb_pix);
-  LAUNCHED(1);
+  if (!p2p) {
+    k_fb_clamp<<<blocks_for(s->fb_pix, 256), 256, 0, st>>>(s->d_fb, s->fb_pix);
+    LAUNCHED(1);
+  } else {
+    const int rank = s->p2p.rank;
+    Mailbox *mine = s->p2p.d_mail, *root_mail = s->p2p.mail.m[p2p_root];
+    const unsigned grid = (unsigned)std::min<size_t>((size_t)g_sms * 8, std::max<size_t>(1, (count / std::max<size_t>(1, s2) + 255) / 256));
+    if (rank == p2p_root) {
+      if (count && (phases & 2)) {
+        k_rows_to_root<<<grid, 256, 0, st>>>((const float4 *)s->d_fb, (float4 *)s->d_fb, tiles, s->W, mine, nullptr, rank, seq);
+        LAUNCHED(1);
+      }
+      if (phases & 4) {
+        k_p2p_wait<<<1, GVT_P2P_MAX, 0, st>>>(mine->done, s->p2p.world, rank, seq, &mine->err);
+        LAUNCHED(1);
+      }
+    } else if (phases & 2) {
+      k_p2p_wait<<<1, 32, 0, st>>>(&mine->go, 1, -1, seq, &mine->err);
+      k_rows_to_root<<<grid, 256, 0, st>>>((const float4 *)s->d_fb, (float4 *)s->p2p.peer_fb[p2p_root], tiles, s->W, mine, root_mail, rank, seq);
+      LAUNCHED(2);
+    }
+  }
   CU(cudaEventRecord(s->ev[1], st));
   CU(cudaGetLastError());
   s->timing_valid = count > 0;
   return GVTB200_OK;
+}
+int gvtb200_render_frame_tiles(gvtb200_scene s, int row0, int row1, int tile_rows, int tile_index, int tile_stride) {
+  return frame_tiles(s, row0, row1, tile_rows, tile_index, tile_stride, -1);
 }
 int gvtb200_render_frame_async(gvtb200_scene s, int row0, int row1) { return gvtb200_render_frame_tiles(s, row0, row1, 1, 0, 1); }
 // run the scene's work on a caller-owned CUDA stream (e.g. the stream NCCL collectives are enqueued on); NULL restores
@@ -1250,6 +1306,14 @@ int gvtb200_scene_sync(gvtb200_scene s) {
   if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaGetLastError());
+  if (s->p2p.d_mail) {
+    unsigned err = 0;
+    CU(cudaMemcpy(&err, &s->p2p.d_mail->err, 4, cudaMemcpyDeviceToHost));
+    if (err) {
+      CU(cudaMemset(&s->p2p.d_mail->err, 0, 4));
+      return fail(GVTB200_ERR_CUDA, "NVLink peer path: rank %d waited more than 4 s for a peer's flag (frame %u)", s->p2p.rank, s->p2p.seq);
+    }
+  }
   return GVTB200_OK;
 }
 int gvtb200_scene_counters(gvtb200_scene s, gvtb200_counters *out) {
@@ -1430,4 +1494,149 @@ int gvtb200_domain_pending(gvtb200_scene s, uint64_t *n) {
   return GVTB200_OK;
 }
 
-} // extern "C"
+// =============================================================================================================
+// NVLink peer path
+// =============================================================================================================
+static RayQueue queue_at(void *slab, size_t cap) { // the layout QueueMem::ensure gives a slab (no hit column)
+  RayQueue q;
+  char *p = (char *)slab;
+  q.count = (unsigned *)p, p += 256;
+  q.c0 = (float4 *)p, p += cap * 16;
+  q.c1 = (float4 *)p, p += cap * 16;
+  q.c2 = (float4 *)p, p += cap * 16;
+  q.c3 = (int4 *)p, p += cap * 16;
+  q.inst = (int *)p;
+  q.cap = (unsigned)cap;
+  return q;
+}
+int gvtb200_p2p_export(gvtb200_scene s, int world, gvtb200_peer_desc *out) {
+  NEED_SCENE();
+  if (!out) return fail(GVTB200_ERR_INVALID, "out is NULL");
+  if (world < 1 || world > GVT_P2P_MAX) return fail(GVTB200_ERR_INVALID, "world size %d outside 1..%d", world, GVT_P2P_MAX);
+  if (s->p2p.attached) return fail(GVTB200_ERR_INVALID, "already attached: gvtb200_p2p_detach first");
+  if (int rc = scene_fb(s)) return rc;
+  const size_t nl = std::max<size_t>(1, s->lights.size());
+  const size_t cap = (size_t)s->W * s->H * s->samples * s->samples * nl;
+  if (cap > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "frame has too many rays for one queue");
+  for (int k = 0; k < 2; ++k) {
+    if (s->p2p.inbox[k].slab && s->p2p.inbox[k].q.cap != cap) s->p2p.inbox[k].release();
+    CU(s->p2p.inbox[k].ensure(s->world > 1 ? cap : 32)); // only the DomainScheduler exchanges rays
+  }
+  if (!s->p2p.d_mail) CU(dalloc(&s->p2p.d_mail, 1));
+  CU(cudaMemset(s->p2p.d_mail, 0, sizeof(Mailbox)));
+  CU(cudaStreamSynchronize(s->stream));
+  memset(out, 0, sizeof(*out));
+  void *ptrs[4] = { s->d_fb, s->p2p.inbox[0].slab, s->p2p.inbox[1].slab, s->p2p.d_mail };
+  uint8_t *handles[4] = { out->fb_handle, out->inbox_handle[0], out->inbox_handle[1], out->mail_handle };
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  for (int k = 0; k < 4; ++k) {
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ptrs[k]));
+    memcpy(handles[k], &h, 64);
+    out->raw[k] = (uint64_t)(uintptr_t)ptrs[k];
+  }
+  out->inbox_cap = s->p2p.inbox[0].q.cap, out->fb_pix = s->fb_pix, out->pid = (int32_t)getpid(), out->device = g_device;
+  s->p2p.exported = true;
+  return GVTB200_OK;
+}
+int gvtb200_p2p_attach(gvtb200_scene s, int rank, int world, const gvtb200_peer_desc *all) {
+  NEED_SCENE();
+  if (!all) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  if (!s->p2p.exported) return fail(GVTB200_ERR_INVALID, "gvtb200_p2p_export has not been called on this scene");
+  if (world < 1 || world > GVT_P2P_MAX || rank < 0 || rank >= world) return fail(GVTB200_ERR_INVALID, "bad rank/world %d/%d", rank, world);
+  if (s->world > 1 && (s->world != world || s->rank != rank)) return fail(GVTB200_ERR_INVALID, "rank/world differ from gvtb200_domain_set_owner (%d/%d)", s->rank, s->world);
+  if (s->p2p.attached) return fail(GVTB200_ERR_INVALID, "already attached");
+  std::vector<RayQueue> table(2 * (size_t)world);
+  for (int r = 0; r < world; ++r) {
+    const gvtb200_peer_desc &d = all[r];
+    if (d.fb_pix != s->fb_pix) return fail(GVTB200_ERR_INVALID, "rank %d renders a different film (%llu vs %zu pixels)", r, (unsigned long long)d.fb_pix, s->fb_pix);
+    void *ptrs[4];
+    if (r == rank) {
+      ptrs[0] = s->d_fb, ptrs[1] = s->p2p.inbox[0].slab, ptrs[2] = s->p2p.inbox[1].slab, ptrs[3] = s->p2p.d_mail;
+    } else if (d.pid == (int32_t)getpid()) {
+      // another scene of this process: same address space.  (A different device of the same process would need
+      // cudaDeviceEnablePeerAccess; one process per GPU is the supported layout.)
+      if (d.device != g_device) return fail(GVTB200_ERR_INVALID, "rank %d lives on device %d of this process: use one process per GPU", r, d.device);
+      for (int k = 0; k < 4; ++k) ptrs[k] = (void *)(uintptr_t)d.raw[k];
+    } else {
+      const uint8_t *handles[4] = { d.fb_handle, d.inbox_handle[0], d.inbox_handle[1], d.mail_handle };
+      for (int k = 0; k < 4; ++k) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles[k], 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&ptrs[k], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+          gvtb200_p2p_detach(s);
+          return fail(GVTB200_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d, object %d): %s", r, k, cudaGetErrorString(e));
+        }
+        s->p2p.opened[r][k] = ptrs[k];
+      }
+    }
+    s->p2p.peer_fb[r] = (float *)ptrs[0];
+    table[r] = queue_at(ptrs[1], d.inbox_cap), table[(size_t)world + r] = queue_at(ptrs[2], d.inbox_cap);
+    s->p2p.mail.m[r] = (Mailbox *)ptrs[3];
+  }
+  dfree(s->p2p.d_peer_inbox);
+  CU(dalloc(&s->p2p.d_peer_inbox, table.size()));
+  CU(cudaMemcpy(s->p2p.d_peer_inbox, table.data(), table.size() * sizeof(RayQueue), cudaMemcpyHostToDevice));
+  s->p2p.rank = rank, s->p2p.world = world, s->p2p.seq = 0, s->p2p.attached = true;
+  return GVTB200_OK;
+}
+int gvtb200_p2p_detach(gvtb200_scene s) {
+  if (!s) return GVTB200_OK;
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  for (auto &r : s->p2p.opened)
+    for (auto &p : r) {
+      if (p) cudaIpcCloseMemHandle(p);
+      p = nullptr;
+    }
+  dfree(s->p2p.d_peer_inbox), dfree(s->p2p.d_mail);
+  s->p2p.inbox[0].release(), s->p2p.inbox[1].release();
+  s->p2p.exported = s->p2p.attached = false;
+  return GVTB200_OK;
+}
+int gvtb200_image_frame_p2p(gvtb200_scene s, int row0, int row1, int tile_rows, int root, int phases) {
+  if (!s || !s->p2p.attached) return fail(GVTB200_ERR_INVALID, "scene is not attached to its peers (gvtb200_p2p_attach)");
+  if (root < 0 || root >= s->p2p.world) return fail(GVTB200_ERR_INVALID, "root %d outside 0..%d", root, s->p2p.world - 1);
+  if (phases < 1 || phases > 7) return fail(GVTB200_ERR_INVALID, "phases %d outside 1..7", phases);
+  return frame_tiles(s, row0, row1, tile_rows, s->p2p.rank, s->p2p.world, root, phases);
+}
+int gvtb200_domain_round_p2p(gvtb200_scene s, int round, void **d_exported_total) {
+  NEED_SCENE();
+  if (!s->p2p.attached || s->world < 2) return fail(GVTB200_ERR_INVALID, "needs gvtb200_domain_set_owner with world > 1 and gvtb200_p2p_attach");
+  if (round < 0) return fail(GVTB200_ERR_INVALID, "round %d", round);
+  // the frame's queues must hold whatever the peers may send: up to the inbound queue's capacity
+  const size_t cap = s->p2p.inbox[0].q.cap, nl = std::max<size_t>(1, s->lights.size());
+  if (cap * nl > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "frame has too many rays for one queue");
+  CU(s->q_b.ensure(s->depth > 1 ? cap : 32));
+  CU(s->q_sh.ensure(cap * nl));
+  CU(s->q_hit.ensure(cap, true));
+  FrameParams fp;
+  build_frame_params(*s, fp);
+  const RayQueue *first = round == 0 ? nullptr : &s->p2p.inbox[(round - 1) & 1].q;
+  const RayQueue *peers = s->p2p.d_peer_inbox + (size_t)(round & 1) * s->p2p.world;
+  if (int rc = run_waves(s, fp, std::max(1, s->depth), false, nullptr, first, peers)) return rc;
+  // what this round consumed is empty again before any peer can store into it (round + 1 starts after the all-reduce)
+  if (round > 0) CU(cudaMemsetAsync(s->p2p.inbox[(round - 1) & 1].q.count, 0, 4, s->stream));
+  CU(cudaGetLastError());
+  if (d_exported_total) *d_exported_total = (void *)&s->d_ctr->rays_exported;
+  return GVTB200_OK;
+}
+int gvtb200_domain_composite_p2p(gvtb200_scene s, int root) {
+  NEED_SCENE();
+  if (!s->p2p.attached) return fail(GVTB200_ERR_INVALID, "scene is not attached to its peers (gvtb200_p2p_attach)");
+  if (root < 0 || root >= s->p2p.world) return fail(GVTB200_ERR_INVALID, "root %d outside 0..%d", root, s->p2p.world - 1);
+  cudaStream_t st = s->stream;
+  const unsigned seq = ++s->p2p.seq;
+  Mailbox *mine = s->p2p.d_mail;
+  if (s->p2p.rank == root) {
+    k_p2p_wait<<<1, GVT_P2P_MAX, 0, st>>>(mine->done, s->p2p.world, root, seq, &mine->err);
+    k_fb_clamp<<<blocks_for(s->fb_pix, 256), 256, 0, st>>>(s->d_fb, s->fb_pix);
+  } else {
+    k_fb_accumulate_root<<<g_sms * 8, 256, 0, st>>>((const float4 *)s->d_fb, s->p2p.peer_fb[root], s->fb_pix, mine, s->p2p.mail.m[root], s->p2p.rank, seq);
+  }
+  LAUNCHED(s->p2p.rank == root ? 2 : 1);
+  CU(cudaGetLastError());
+  return GVTB200_OK;
+}
+
+} // extern "C\"

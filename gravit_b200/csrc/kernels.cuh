@@ -334,6 +334,14 @@ __device__ __forceinline__ unsigned queue_reserve(unsigned *count) {
   if (g.thread_rank() == 0) base = atomicAdd(count, g.size());
   return g.shfl(base, 0) + g.thread_rank();
 }
+// the same for a queue that lives in another GPU's memory: lanes are grouped by destination rank, the group leader does
+// one system-scope atomic over NVLink
+__device__ __forceinline__ unsigned queue_reserve_peer(unsigned *count, int owner) {
+  cg::coalesced_group g = cg::labeled_partition(cg::coalesced_threads(), owner);
+  unsigned base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd_system(count, g.size());
+  return g.shfl(base, 0) + g.thread_rank();
+}
 __device__ __forceinline__ void count_add(unsigned long long *c, unsigned long long v) {
   cg::coalesced_group g = cg::coalesced_threads();
   unsigned long long s = cg::reduce(g, v, cg::plus<unsigned long long>());
@@ -460,6 +468,9 @@ struct TraceQueues {
   RayQueue mvq, exq;
   RayQueue fin;   // adapter mode: final state of every input ray, by input slot (Adapter::trace mutates rayList in place)
   unsigned *work; // input cursor
+  // NVLink peer path: peer_inbox[p] = rank p's inbound ray queue, mapped into this GPU's address space (CUDA IPC).  When
+  // set, a ray bound for another rank's instance is stored there directly instead of being parked in `exq`.
+  const RayQueue *peer_inbox;
 };
 struct ShadeQueues {
   RayQueue hq;
@@ -500,7 +511,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
   const unsigned lane = threadIdx.x & 31;
   const unsigned ltmask = (1u << lane) - 1u;
   const bool to_light = (fp.flags & FLAG_SHADOW_TO_LIGHT) != 0;
-  unsigned long long c_visits = 0, c_shok = 0, c_fb = 0, c_exp = 0, c_ovf = 0, c_routed = 0;
+  unsigned long long c_visits = 0, c_shok = 0, c_fb = 0, c_exp = 0, c_ovf = 0, c_qovf = 0, c_routed = 0;
   const unsigned per_row = (unsigned)(fp.cam.W * fp.cam.samples * fp.cam.samples);
   auto camera_index = [&](unsigned i) -> size_t { // shard ray i -> global camera-ray index (RowTiles arithmetic)
     unsigned lr = i / per_row, within = i - lr * per_row;
@@ -673,11 +684,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
             active = false;
           } else {
             o = xadd(o, xmul(d, xmul(t, 0.95f))); // TracerBase.h:394
-            if (fp.world > 1 && sd.inst[next].owner != fp.rank) {
+            const int owner = fp.world > 1 ? sd.inst[next].owner : fp.rank;
+            if (owner != fp.rank) {
               Ray r;
               reload(r);
-              const unsigned pos = queue_reserve(q.exq.count);
-              if (pos < q.exq.cap) queue_store(q.exq, pos, r, next);
+              if (q.peer_inbox) { // SendRays over NVLink: slot reservation + SoA stores in the owner's memory
+                const RayQueue dst = q.peer_inbox[owner];
+                const unsigned pos = queue_reserve_peer(dst.count, owner);
+                if (pos < dst.cap)
+                  queue_store(dst, pos, r, next);
+                else
+                  c_qovf++;
+              } else {
+                const unsigned pos = queue_reserve(q.exq.count);
+                if (pos < q.exq.cap) queue_store(q.exq, pos, r, next);
+              }
               c_exp++;
               active = false;
             } else {
@@ -695,6 +716,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
   count_add(&sd.ctr->fb_adds, c_fb);
   count_add(&sd.ctr->rays_exported, c_exp);
   count_add(&sd.ctr->stack_overflows, c_ovf);
+  count_add(&sd.ctr->queue_overflows, c_qovf);
   if (gen) {
     count_add(&sd.ctr->routed_initial, c_routed);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&sd.ctr->camera_rays, (unsigned long long)n);
@@ -842,6 +864,84 @@ __global__ void k_import(const uint4 *packed, unsigned n, RayQueue q, unsigned o
   reinterpret_cast<uint4 *>(q.c2)[offset + i] = p[2];
   reinterpret_cast<uint4 *>(q.c3)[offset + i] = p[3];
   q.inst[offset + i] = (int)p[4].x;
+}
+
+// ---- NVLink peer path: flags, framebuffer gather / accumulate (replace icetCompositeImage, IceTComposite.cpp:96) ----------
+// Every rank owns one Mailbox that its peers can write: `go` is set by the root when its framebuffer may be overwritten,
+// done[r] by rank r when its contribution to this rank's framebuffer is complete.  Values are frame sequence numbers.
+#define GVT_P2P_MAX 16
+struct Mailbox {
+  unsigned go, err, cta_done, pad;
+  unsigned done[60];
+};
+struct PeerMail {
+  Mailbox *m[GVT_P2P_MAX];
+};
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// thread i < n (i != skip) waits until flags[i] has reached sequence number seq; gives up after ~4 s (err is set)
+__global__ void k_p2p_wait(const unsigned *flags, int n, int skip, unsigned seq, unsigned *err) {
+  const int i = (int)threadIdx.x;
+  if (i >= n || i == skip) return;
+  const unsigned long long t0 = global_ns();
+  while ((int)(ld_acquire_sys(flags + i) - seq) < 0) {
+    __nanosleep(128);
+    if (global_ns() - t0 > 4000000000ull) {
+      atomicExch(err, 1u);
+      return;
+    }
+  }
+}
+// the root releases its peers: thread r stores seq into rank r's `go`
+__global__ void k_p2p_go(PeerMail pm, int world, int self, unsigned seq) {
+  const int r = (int)threadIdx.x;
+  if (r < world && r != self) st_release_sys(&pm.m[r]->go, seq);
+}
+// last CTA of a kernel that wrote into the root's memory: publish done[rank] = seq at the root
+__device__ __forceinline__ void p2p_signal_done(Mailbox *mine, Mailbox *root_mail, int rank, unsigned seq) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned d = atomicAdd(&mine->cta_done, 1u);
+    if (d == gridDim.x - 1) {
+      mine->cta_done = 0;
+      __threadfence_system();
+      st_release_sys(&root_mail->done[rank], seq);
+    }
+  }
+}
+// ImageScheduler: clamp this shard's film rows and store them into dst (the root's framebuffer; dst == src on the root)
+__global__ void k_rows_to_root(const float4 *src, float4 *dst, RowTiles tiles, int W, Mailbox *mine, Mailbox *root_mail, int rank, unsigned seq) {
+  const size_t n = tiles_local_rows(tiles) * (size_t)W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t lr = i / W, x = i - lr * W;
+    const size_t b = lr / tiles.tile_rows, k = lr - b * tiles.tile_rows;
+    const size_t pix = ((size_t)tiles.row0 + (b * tiles.stride + tiles.index) * tiles.tile_rows + k) * W + x;
+    float4 v = src[pix];
+    v.x = fminf(v.x, 1.f), v.y = fminf(v.y, 1.f), v.z = fminf(v.z, 1.f);
+    dst[pix] = v;
+  }
+  if (root_mail) p2p_signal_done(mine, root_mail, rank, seq);
+}
+// DomainScheduler: add the pixels this rank touched (alpha counts contributions) to the root's framebuffer
+__global__ void k_fb_accumulate_root(const float4 *src, float *dst, size_t npix, Mailbox *mine, Mailbox *root_mail, int rank, unsigned seq) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    if (v.w != 0.f) {
+      atomicAdd_system(dst + 4 * i, v.x), atomicAdd_system(dst + 4 * i + 1, v.y);
+      atomicAdd_system(dst + 4 * i + 2, v.z), atomicAdd_system(dst + 4 * i + 3, v.w);
+    }
+  }
+  p2p_signal_done(mine, root_mail, rank, seq);
 }
 
 } // namespace gvt

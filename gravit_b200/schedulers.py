@@ -8,6 +8,11 @@
                    one all_to_all_single of 80-byte wire records over NCCL/NVLink; the gather/scatter termination test
                    (:339-349) becomes an all_reduce(sum); IceT compositing becomes reduce(sum) + clamp on the device.
 
+Both schedulers also have an NVLink peer path (`p2p_connect`, then `p2p=True` / `render_domain_schedule_p2p`): the ranks map
+each other's framebuffer and inbound ray queues with CUDA IPC; the trace kernel stores migrating rays straight into the
+owner's queue and the film rows / touched pixels go straight into the root's framebuffer, so the only collective left on
+the data path is the 8-byte termination all-reduce of the DomainScheduler.
+
 The host logic (row shards, split sizes, termination) is backend-agnostic and is covered on CPU with gloo, world_size 2.
 """
 import numpy as np
@@ -72,12 +77,56 @@ def device_tensor(ptr, shape, typestr="<f4"):
     return torch.as_tensor(_DevArray(ptr, shape, typestr), device="cuda")
 
 
-def render_image_schedule(engine, width, height, dist=None, rank=0, world=1, tile_rows=8, fb_tensor=None):
-    """One ImageScheduler frame.  Leaves the composited image in rank 0's device framebuffer."""
+def gather_descriptors(dist, desc, world, device="cpu"):
+    """all-gather of one fixed-size byte string per rank (works with gloo on CPU tensors and with nccl on CUDA tensors)."""
+    import torch
+
+    mine = torch.frombuffer(bytearray(desc), dtype=torch.uint8).to(device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+
+
+def p2p_connect(engine, dist, rank, world, device):
+    """Maps every peer's framebuffer, inbound ray queues and mailbox into this rank (CUDA IPC over NVLink)."""
+    desc = engine.p2p_export(world)
+    engine.p2p_attach(rank, world, gather_descriptors(dist, desc, world, device))
+    dist.barrier()  # nobody stores into a peer before every peer has attached
+
+
+def render_image_schedule(engine, width, height, dist=None, rank=0, world=1, tile_rows=8, fb_tensor=None, p2p=False):
+    """One ImageScheduler frame.  Leaves the composited image in rank 0's device framebuffer.
+    p2p=True (after p2p_connect): the ranks store their clamped rows into rank 0's framebuffer over NVLink, no collective."""
+    if p2p and world > 1:
+        engine.image_frame_p2p(height, tile_rows, 0)
+        return
     engine.render_tiles(height, tile_rows, rank, world)
     if world > 1:
         # every pixel is written by exactly one rank, the others hold zeros: sum == gather
         dist.reduce(fb_tensor, dst=0, op=dist.ReduceOp.SUM)
+
+
+def domain_terminated(log):
+    """Termination rule of the peer path: `log` holds the all-reduced cumulative exported-ray totals after each round; the
+    frame is over when a round exported nothing anywhere (DomainTracer.h:339-349: no rank has rays in flight)."""
+    return len(log) >= 1 and (log[-1] == (log[-2] if len(log) > 1 else 0))
+
+
+def render_domain_schedule_p2p(engine, dist, rank, world, max_rounds=10000, root=0):
+    """One DomainScheduler frame over the NVLink peer path (after p2p_connect).  The engine must launch on torch's current
+    stream (engine.set_stream) so that the counter read below is ordered after the round's kernels.  Returns the
+    all-reduced cumulative exported-ray total after each round."""
+    log = []
+    engine.domain_begin_frame()
+    for rnd in range(max_rounds):
+        ptr = engine.domain_round_p2p(rnd)
+        total = device_tensor(ptr, (1,), "<i8").clone()
+        dist.all_reduce(total)  # the only collective: 8 bytes per round (and the barrier that ends the round)
+        log.append(int(total.item()))
+        if domain_terminated(log):
+            break
+    engine.domain_composite_p2p(root)
+    return log
 
 
 def render_domain_schedule(engine, dist, rank, world, device, fb_tensor, max_rounds=10000):

@@ -183,6 +183,7 @@ typedef struct gvtb200_counters {
   uint64_t tris_tested;
   uint64_t rays_exported; /* domain scheduler: rays handed to other ranks */
   uint64_t stack_overflows; /* rays whose traversal stack overflowed (must be 0; deeper BVHs need GVT_BLAS_STACK raised) */
+  uint64_t queue_overflows; /* NVLink peer path: rays dropped because a peer's inbound queue was full (must be 0) */
 } gvtb200_counters;
 GVTB200_API int gvtb200_render_frame(gvtb200_scene scene, int row0, int row1, float *rgba_out, gvtb200_counters *counters);
 /* same, asynchronous on the scene's stream, nothing copied back (bench / multi-GPU drivers) */
@@ -229,6 +230,50 @@ GVTB200_API int gvtb200_domain_export(gvtb200_scene scene, uint32_t *counts, voi
 GVTB200_API int gvtb200_domain_import(gvtb200_scene scene, const void *d_rays, size_t n_rays);
 /* rays still queued locally (termination test, DomainTracer.h:339-349) */
 GVTB200_API int gvtb200_domain_pending(gvtb200_scene scene, uint64_t *n);
+
+/* ---- NVLink peer path: one process per GPU, peers' memory mapped with CUDA IPC ----------------------------------
+ * Replaces, with direct loads/stores/atomics over NVLink 5 / NVSwitch instead of a library collective:
+ *   - SendRays' two MPI phases (DomainTracer.h:409-415 counts, :433-463 payload): the trace kernel itself reserves a slot in
+ *     the owning rank's inbound ray queue (one remote atomic per warp and owner) and stores the SoA ray there, so the
+ *     exchange overlaps the traversal ray by ray and there is no pack / all-to-all / unpack step;
+ *   - icetCompositeImage (composite/IceTComposite.cpp:96): ImageScheduler ranks store their clamped film rows into the
+ *     root's framebuffer, DomainScheduler ranks add the pixels they touched to it (device-side gather / accumulate).
+ * What stays a collective is the termination test (DomainTracer.h:339-349), one 8-byte all-reduce per round.
+ *
+ * gvtb200_p2p_export allocates this rank's shared objects (framebuffer, two inbound ray queues, a mailbox of flags) and
+ * describes them; the ranks exchange the descriptors (any transport: torch.distributed all_gather, MPI, a file) and each
+ * calls gvtb200_p2p_attach with all `world` of them.  Descriptors created by the same process (several scenes on one GPU:
+ * the single-process tests) are attached by pointer, others through cudaIpcOpenMemHandle. */
+typedef struct gvtb200_peer_desc {
+  uint8_t fb_handle[64];       /* cudaIpcMemHandle_t of the RGBA float framebuffer */
+  uint8_t inbox_handle[2][64]; /* inbound ray queues, used alternately by exchange rounds */
+  uint8_t mail_handle[64];     /* flags: go, done[world], error */
+  uint64_t raw[4];             /* the same four device pointers, valid inside the creating process */
+  uint64_t inbox_cap;          /* rays per inbound queue */
+  uint64_t fb_pix;
+  int32_t pid, device;
+} gvtb200_peer_desc;
+GVTB200_API int gvtb200_p2p_export(gvtb200_scene scene, int world_size, gvtb200_peer_desc *out);
+GVTB200_API int gvtb200_p2p_attach(gvtb200_scene scene, int rank, int world_size, const gvtb200_peer_desc *all);
+GVTB200_API int gvtb200_p2p_detach(gvtb200_scene scene);
+/* Tracer<ImageScheduler> on `world_size` GPUs: this rank's row tiles (as gvtb200_render_frame_tiles, index = rank, stride =
+ * world_size), then the clamped rows go straight into rank `root`'s framebuffer over NVLink.  The root tells the peers when
+ * its framebuffer may be overwritten (after its own clear) and waits for their rows before the call's work completes on
+ * its stream; a peer that waits longer than ~4 s gives up and the next gvtb200_scene_sync reports it. */
+enum { GVTB200_P2P_CLEAR = 1, GVTB200_P2P_TRACE = 2, GVTB200_P2P_WAIT = 4, GVTB200_P2P_ALL = 7 };
+/* phases: GVTB200_P2P_ALL for a frame.  Several scenes of ONE process on ONE GPU (the single-process tests) split the
+ * root's call -- CLEAR before the peers' frames, TRACE|WAIT after them -- so that no spinning kernel waits for a launch
+ * the host has not made yet. */
+GVTB200_API int gvtb200_image_frame_p2p(gvtb200_scene scene, int row0, int row1, int tile_rows, int root, int phases);
+/* Tracer<DomainScheduler>, one exchange round: trace what is queued locally (round 0: the camera rays this rank kept in
+ * gvtb200_domain_begin_frame; round r > 0: what the peers stored into this rank's inbound queue during round r-1); rays
+ * routed to another rank's instance are stored into that rank's inbound queue by the trace kernel.  *d_exported_total
+ * (may be NULL) receives the DEVICE address of the frame's cumulative exported-ray counter (uint64) for the termination
+ * all-reduce: the frame is over when the sum over ranks did not grow during a round. */
+GVTB200_API int gvtb200_domain_round_p2p(gvtb200_scene scene, int round, void **d_exported_total);
+/* end of a DomainScheduler frame: every rank adds the pixels it touched to the root's framebuffer; the root waits for all
+ * of them, then clamps (IceTComposite::localAdd's clamp, composite/IceTComposite.cpp:113-114). */
+GVTB200_API int gvtb200_domain_composite_p2p(gvtb200_scene scene, int root);
 
 #ifdef __cplusplus
 }

@@ -358,3 +358,84 @@ def test_domain_scheduler_simulated_ranks(gpu, world):
     assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref1)) >= 50.0
     for e in ranks:
         e.close()
+
+
+# ---- NVLink peer path: ranks simulated as several engine scenes in one process (attached by pointer, not by IPC) -------
+def _connect(ranks):
+    world = len(ranks)
+    descs = b"".join(e.p2p_export(world) for e in ranks)
+    for r, e in enumerate(ranks):
+        e.p2p_attach(r, world, descs)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_image_scheduler_peer_gather_bit_identical(gpu, world):
+    """Tracer<ImageScheduler> over the peer path: every rank renders its row tiles and stores them, clamped, into the
+    root's framebuffer (replaces icetCompositeImage).  The root's image must equal the single-GPU frame bit for bit, for
+    two consecutive frames (the go / done flags carry frame sequence numbers)."""
+    from gravit_b200 import schedulers
+
+    d = library.simple_scene(320, 200)
+    ranks = [schedulers.build_domain_rank(d, 0, 1, flags=1)[0] for _ in range(world)]
+    ref, _ = ranks[0].render(d.width, d.height)
+    _connect(ranks)
+
+    def frame(tile_rows, root):
+        # Simulated ranks share ONE GPU and one host thread: the root's call is split (clear + go first, trace + wait after
+        # the peers' calls) so that no spinning kernel waits for a launch the host has not made yet.
+        ranks[root].image_frame_p2p(d.height, tile_rows, root, phases=1)
+        for r, e in enumerate(ranks):
+            if r != root:
+                e.image_frame_p2p(d.height, tile_rows, root)
+        ranks[root].image_frame_p2p(d.height, tile_rows, root, phases=2 | 4)
+        for e in ranks:
+            e.sync()
+        return ranks[root].fb_read(d.width, d.height)
+
+    for tile_rows in (3, 8, 8):  # consecutive frames: the go / done flags carry frame sequence numbers
+        assert np.array_equal(frame(tile_rows, 0), ref)
+    assert np.array_equal(frame(8, 1), ref)  # a non-zero root works the same way
+    for e in ranks:
+        e.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_domain_scheduler_peer_exchange(gpu, world):
+    """Tracer<DomainScheduler> over the peer path: the trace kernel stores migrating rays into the owner's inbound queue
+    (replaces SendRays, DomainTracer.h:370-496).  Rays exchanged per round equal the oracle's routing counts, the
+    composited image (touched pixels added into the root, then clamped) equals the single-process image."""
+    from gravit_b200 import schedulers
+
+    d = library.simple_scene(256, 256)
+    flags = 1
+    o = oracle_scene(d, flags)
+    o.set_owner(np.arange(len(d.instances)) % world)
+    ref, st = o.render(schedule=1, world_size=world, threads=8)
+    per_round_o = [int(m.sum()) for m in o.route_log(world) if m.sum() > 0]
+    ref1, _ = o.render(schedule=0, world_size=1, threads=8)
+    ranks, owner = _standalone_ranks(gpu, d, flags, world)
+    _connect(ranks)
+    for frame in range(2):  # twice: the inbound queues and flags must be reusable
+        for e in ranks:
+            e.domain_begin_frame()
+        log = []
+        for rnd in range(100):
+            for e in ranks:
+                e.domain_round_p2p(rnd)
+            for e in ranks:
+                e.sync()  # stands in for the all-reduce that ends a round
+            log.append(sum(e.counters()["rays_exported"] for e in ranks))
+            if schedulers.domain_terminated(log):
+                break
+        per_round = [b - a for a, b in zip([0] + log[:-1], log)][:-1]
+        assert per_round == per_round_o and len(per_round) >= 1
+        assert all(e.counters()["queue_overflows"] == 0 for e in ranks)
+        for e in ranks[1:] + ranks[:1]:  # peers add their pixels, the root waits and clamps
+            e.domain_composite_p2p(0)
+        for e in ranks:
+            e.sync()
+        fb = ranks[0].fb_read(d.width, d.height)
+        assert np.allclose(fb, ref, atol=1e-6) and np.allclose(fb, ref1, atol=1e-6)
+        assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref1)) >= 50.0
+    for e in ranks:
+        e.close()

@@ -52,6 +52,32 @@ def main():
             out = fb_t.cpu().numpy()
             say(check="image_scheduler", scene=name, world=world, bit_identical=bool(np.array_equal(out, ref)), lit_pixels=int((ref[..., 3] > 0).sum()))
             assert np.array_equal(out, ref)
+        if world > 1:  # the same frame over the NVLink peer path (CUDA IPC), and both variants timed
+            schedulers.p2p_connect(e, dist, rank, world, dev)
+            for _ in range(2):
+                schedulers.render_image_schedule(e, d.width, d.height, dist, rank, world, 8, fb_t, p2p=True)
+            e.sync()
+            dist.barrier()
+            if rank == 0:
+                out = fb_t.cpu().numpy()
+                say(check="image_scheduler_p2p", scene=name, world=world, bit_identical=bool(np.array_equal(out, ref)))
+                assert np.array_equal(out, ref)
+            ms = {}
+            for variant in ("nccl_reduce", "p2p"):
+                dist.barrier()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(20):
+                    schedulers.render_image_schedule(e, d.width, d.height, dist, rank, world, 8, fb_t, p2p=(variant == "p2p"))
+                b.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([a.elapsed_time(b) / 20], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms[variant] = float(t.item())
+            say(check="image_scheduler_timing", scene=name, world=world, ms_per_frame=ms)
+            e.sync()
+            e.p2p_detach()
         e.set_stream(None)
         del e, s
 
@@ -79,6 +105,38 @@ def main():
             say(check="domain_scheduler", scene=name, world=world, max_abs_err=err, rounds=len(log), rays_exchanged=int(tot[0]),
                 hits=int(tot[1]), hits_single=cref["primary_hits"], fb_adds=int(tot[2]), fb_adds_single=cref["fb_adds"])
             assert err < 1e-5 and int(tot[1]) == cref["primary_hits"] and int(tot[2]) == cref["fb_adds"]
+        if world > 1:  # the same frame with the trace kernel storing migrating rays into the owner's queue over NVLink
+            schedulers.p2p_connect(scene, dist, rank, world, dev)
+            for _ in range(2):
+                logp = schedulers.render_domain_schedule_p2p(scene, dist, rank, world)
+            scene.sync()
+            dist.barrier()
+            c = scene.counters()
+            tot = torch.tensor([c["rays_exported"], c["primary_hits"], c["fb_adds"], c["queue_overflows"]], dtype=torch.int64, device=dev)
+            dist.all_reduce(tot)
+            if rank == 0:
+                out = fb_t.cpu().numpy()
+                err = float(np.abs(out - ref).max())
+                say(check="domain_scheduler_p2p", scene=name, world=world, max_abs_err=err, rounds=len(logp), rays_exchanged=int(tot[0]),
+                    hits=int(tot[1]), hits_single=cref["primary_hits"], fb_adds=int(tot[2]), fb_adds_single=cref["fb_adds"], queue_overflows=int(tot[3]))
+                assert err < 1e-5 and int(tot[1]) == cref["primary_hits"] and int(tot[2]) == cref["fb_adds"] and int(tot[3]) == 0
+            ms = {}
+            for variant in ("nccl_all_to_all", "p2p"):
+                dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    if variant == "p2p":
+                        schedulers.render_domain_schedule_p2p(scene, dist, rank, world)
+                    else:
+                        schedulers.render_domain_schedule(scene, dist, rank, world, dev, fb_t)
+                scene.sync()
+                torch.cuda.synchronize()
+                t = torch.tensor([(time.perf_counter() - t0) * 100.0], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms[variant] = float(t.item())
+            say(check="domain_scheduler_timing", scene=name, world=world, ms_per_frame_wall=ms)
+            scene.p2p_detach()
         scene.set_stream(None)
         del scene, single
     if world > 1:
