@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- Mrays/s (primary + shadow + secondary) of the B200 render adapter on the BASELINE.json workloads.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sibenik|bunny|grid] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sibenik|bunny|grid|incoherent|gyroid] [--impl reference]
 
 A step = one frame of the hot path (camera rays -> instance routing -> two-level traversal -> shading -> shadow /
 secondary rays -> framebuffer) on one synthetic scene.  rays = camera rays generated + shadow rays traced + secondary
@@ -18,6 +18,12 @@ rays traced (device counters).  Prints ONE JSON line (rank 0).
   cpu_baseline  the CPU oracle (a port of the reference semantics; Embree is absent) on the host cores, bounded sample
 
 --impl reference times that CPU port alone (rank 0 only).
+
+N > 1 (torchrun, one rank per GPU).  ImageScheduler workloads: the film rows of ONE frame are dealt to the ranks in 8-row
+tiles, geometry replicated, and the rows are gathered into rank 0's framebuffer over the NVLink peer path (no collective;
+--no-p2p falls back to an NCCL reduce).  gyroid (BASELINE configs[3]): Tracer<DomainScheduler>, brick k of the 2x2x2 split
+lives on rank k mod N, the trace kernel stores migrating rays into the owner's queue over NVLink, one 8-byte all-reduce
+per exchange round.  Both are strong scaling of one frame.
 """
 import argparse
 import json
@@ -42,7 +48,12 @@ WORKLOADS = {
     "bunny": dict(make=lambda: library.bunny_scene(1920, 1080), name="bun_zipper 69,451 tris, 1920x1080, 1 point light, primary+shadow"),
     # configs[2]: 32x32 instanced bunnies at 4K
     "grid": dict(make=lambda: library.bunny_grid_scene(32, 3840, 2160), name="32x32 bunny instances (71.1M effective tris), 3840x2160, primary+shadow (configs[2])"),
+    # configs[4]: incoherent stress
+    "incoherent": dict(make=lambda: library.incoherent_scene(3840, 2160), name="sibenik.obj 3840x2160, 9 spp, rayMaxDepth 5 (4 diffuse bounces) (configs[4])"),
+    # configs[3]: 100M-triangle gyroid isosurface in 8 bricks (built per rank in main(): geometry is generated on the GPU)
+    "gyroid": dict(make=None, name="gyroid isosurface, 2x2x2 bricks, 3840x2160, primary+shadow (configs[3])"),
 }
+EXTRA_WORKLOADS = ("bunny", "grid", "incoherent")  # measured next to the default workload at N = 1
 
 
 def peaks():
@@ -53,16 +64,52 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region: an NVML polling thread (1 ms period, so that even a 50 ms
+    region is sampled), with `nvidia-smi -lms` as the fallback when NVML is not importable."""
+
     def __init__(self, index=0):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        import threading
+
+        self.rows, self.stop_flag, self.thread, self.p, self.f = [], False, None, None, None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {"hw_slowdown": "nvmlClocksEventReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksEventReasonHwThermalSlowdown",
+                     "sw_thermal_slowdown": "nvmlClocksEventReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksEventReasonSwPowerCap"}
+            bits = {k: getattr(pynvml, v, None) or getattr(pynvml, v.replace("Event", "Throttle"), 0) for k, v in names.items()}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        self.rows.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(get_reasons(h))))
+                    except Exception:
+                        break
+                    time.sleep(0.001)
+
+            self.bits = bits
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
         except Exception:
-            self.p = None
+            self.thread = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+            except Exception:
+                self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if not self.rows:
+                return None
+            reasons = sorted(k for k, b in self.bits.items() if b and any(r & b for _, r in self.rows))
+            return {"sm_mhz": statistics.median(c for c, _ in self.rows), "sm_max_mhz": self.mx, "reasons": reasons, "samples": len(self.rows), "source": "nvml, 1 ms period"}
         if self.p is None:
             return None
         self.p.terminate()
@@ -84,7 +131,7 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return None
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def cpu_reference(desc, threads, target_s=12.0):
@@ -115,6 +162,16 @@ def cpu_reference(desc, threads, target_s=12.0):
 
 
 def main():
+    # the JSON line must be the only thing on stdout: libraries (NCCL's version banner) write to fd 1, so fd 1 is pointed at
+    # stderr for the run and the line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -124,6 +181,9 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--no-p2p", action="store_true", help="N > 1: NCCL reduce / all-to-all instead of the NVLink peer path")
+    ap.add_argument("--owner", default="mod", choices=["mod", "balanced"], help="gyroid: brick k on rank k mod N (the reference's map) or the view-balanced placement")
+    ap.add_argument("--gyroid-res", type=int, default=library.GYROID_RES_100M, help="grid cells per axis of the gyroid volume (946 = 100 M triangles)")
     a = ap.parse_args()
     a.warmup = max(3, a.warmup)
     rank = int(os.environ.get("RANK", "0"))
@@ -135,6 +195,8 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
+        if wl["make"] is None:  # a CPU-sized gyroid: the port builds its own BVH in seconds at this size
+            wl = dict(wl, make=lambda: library.gyroid_scene(128, 2, 3840, 2160))
         vals = []
         sample = ""
         for _ in range(max(1, min(a.steps, 3))):
@@ -150,7 +212,7 @@ def main():
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(out))
+        emit(out)
         return 0
 
     import torch
@@ -165,7 +227,28 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
+    domain = a.workload == "gyroid"
+    p2p = world > 1 and not a.no_p2p
+    build_s = [0.0]
+
     def setup(name):
+        if name == "gyroid":
+            # every rank generates (on its GPU) and builds only the bricks it owns: brick k -> rank k mod N (DomainTracer.h:140)
+            t0 = time.perf_counter()
+            owner = schedulers.domain_owner(8, world) if a.owner == "mod" else schedulers.gyroid_balanced_owner(world)
+            mine = [k for k in range(8) if owner[k] == rank]
+            d = library.gyroid_scene(a.gyroid_res, 2, 3840, 2160, only_bricks=mine, brick_fn=lambda *args: library.gyroid_brick_torch(*args, device=dev))
+            boxes = schedulers.mesh_boxes_allgather(d, dist, world)
+            e, _ = schedulers.build_domain_rank(d, rank, world, boxes=boxes, owner=owner)
+            d.owner = [int(x) for x in owner]
+            n_tris = torch.tensor([sum(len(m.tris) for m in d.meshes if m.verts is not None)], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(n_tris)
+            d.n_tris = int(n_tris.item())
+            for m in d.meshes:
+                m.verts = m.tris = None  # the host copies are not needed any more
+            build_s[0] = time.perf_counter() - t0
+            return d, None, e
         d = WORKLOADS[name]["make"]()
         s = library.apply(d, g.GvtScene(flags=d.flags))
         e = s.engine()
@@ -181,19 +264,35 @@ def main():
     fb_t = schedulers.device_tensor(fb_ptr, (H, W, 4))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step():
-        schedulers.render_image_schedule(e, W, H, dist if world > 1 else None, rank, world, a.tile_rows, fb_t)
+    if p2p:
+        schedulers.p2p_connect(e, dist, rank, world, dev)
+    rounds = [0]
 
-    e.profile_launches(True)  # an event pair around every kernel launch of the frame, on the launching stream
+    def step():
+        if not domain:
+            schedulers.render_image_schedule(e, W, H, dist if world > 1 else None, rank, world, a.tile_rows, fb_t, p2p=p2p)
+        elif world == 1:
+            e.render_async(H)  # one rank owns every brick: Tracer<DomainScheduler> degenerates to the local drain loop
+        elif p2p:
+            rounds[0] = len(schedulers.render_domain_schedule_p2p(e, dist, rank, world))
+        else:
+            rounds[0] = len(schedulers.render_domain_schedule(e, dist, rank, world, dev, fb_t))
+
+    e.profile_launches(world == 1)  # an event pair around every kernel launch of the frame, on the launching stream
     for _ in range(a.warmup):
         step()
     torch.cuda.synchronize()
     ctr = e.counters()
-    rays_local = ctr["camera_rays"] + ctr["shadow_generated"] + ctr["secondary_generated"]
-    rays_t = torch.tensor([rays_local], dtype=torch.int64, device=dev)
+    # DomainScheduler: every rank generates all camera rays and keeps the ones that enter its bricks first (DomainTracer.h:148-181)
+    rays_local = ctr["shadow_generated"] + ctr["secondary_generated"] + (0 if (domain and world > 1) else ctr["camera_rays"])
+    ctr_keys = ("camera_rays", "routed_initial", "primary_hits", "shadow_generated", "shadow_unoccluded", "secondary_generated", "fb_adds", "rays_exported", "queue_overflows", "stack_overflows")
+    rays_t = torch.tensor([rays_local] + [ctr[k] for k in ctr_keys], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(rays_t)
-    rays_frame = int(rays_t.item())
+    rays_frame = int(rays_t[0].item()) + (W * H * d.samples * d.samples if (domain and world > 1) else 0)
+    ctr_all = {k: int(v) for k, v in zip(ctr_keys, rays_t[1:].tolist())}
+    if domain and world > 1:
+        ctr_all["camera_rays"] = W * H * d.samples * d.samples
 
     launches0 = g.lib().gvtb200_launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -305,10 +404,13 @@ def main():
                         "not by HBM; traffic = dram bytes of the same launch from the committed ncu capture",
             }
             if not a.no_cpu:
-                v, sample, _, _ = cpu_reference(wl["make"], threads)
+                cpu_make = WORKLOADS[a.workload]["make"] or (lambda: library.gyroid_scene(128, 2, 3840, 2160))
+                v, sample, _, _ = cpu_reference(cpu_make, threads)
+                if domain:
+                    sample += "; gyroid at res 128 (1.8 M triangles): the CPU port cannot build the 100 M-triangle BVH inside a bench run"
                 cpu = {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample}
             if not a.no_extra:
-                for name in WORKLOADS:
+                for name in EXTRA_WORKLOADS:
                     if name == a.workload:
                         continue
                     try:
@@ -329,27 +431,35 @@ def main():
                         extra[name] = {"workload": WORKLOADS[name]["name"], "Mrays_per_s": r2 / (m * 1e-3) / 1e6, "ms_per_frame": m, "rays_per_frame": r2}
                     except Exception as ex:  # noqa: BLE001
                         extra[name] = {"error": str(ex)}
+        if domain:
+            wl = dict(wl, name=f"gyroid isosurface {d.n_tris:,} tris in 2x2x2 bricks (res {a.gyroid_res}), 3840x2160, 1 point light, primary+shadow (configs[3])")
+            sched_desc = "DomainScheduler" + (f", {world} ranks, brick -> rank {d.owner}, " + ("rays stored into the owner's queue over NVLink (CUDA IPC) by the trace kernel, "
+                         f"8-byte all-reduce per round, {rounds[0]} rounds, framebuffer accumulated into rank 0 over NVLink" if p2p else f"NCCL all-to-all of 80-byte ray records, {rounds[0]} rounds, NCCL reduce") if world > 1 else ", 1 rank owns all bricks")
+        else:
+            sched_desc = "ImageScheduler" + (f", {world} ranks, row tiles of {a.tile_rows} dealt round-robin, " + ("rows stored into rank 0's framebuffer over NVLink (CUDA IPC), no collective" if p2p else "NCCL reduce to rank 0") if world > 1 else "")
         out = {
             "metric": "Mrays/s (primary+shadow+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": wl["name"], "film": [W, H], "depth": d.depth, "samples": d.samples, "rays_per_frame": rays_frame, "bvh": "binned SAH, 8-wide, 128 B nodes",
-                "scheduler": "ImageScheduler" + (f", {world} ranks, row tiles of {a.tile_rows} dealt round-robin, NCCL reduce to rank 0" if world > 1 else ""),
+                "scheduler": sched_desc,
                 "l2": "256 MiB buffer rewritten between timed frames (L2 flush)", "timing": "CUDA events per frame on the launching stream, max over ranks",
             },
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 496, "d2h_bytes_per_step": W * H * 16,
-                    "call": "gvtb200_render_frame (== api::render) into pinned host memory" if world == 1 else "ImageScheduler step + framebuffer to pinned host memory on rank 0"},
+                    "call": "gvtb200_render_frame (== api::render) into pinned host memory" if world == 1 else "scheduler step + framebuffer to pinned host memory on rank 0"},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
-            "counters": {k: ctr[k] for k in ("camera_rays", "routed_initial", "primary_hits", "shadow_generated", "shadow_unoccluded", "secondary_generated", "fb_adds")},
+            "counters": ctr_all,
         }
+        if domain:
+            out["config"]["scene_build_s"] = round(build_s[0], 2)
         if roof:
             out["roofline"] = roof
         if cpu:
             out["cpu_baseline"] = cpu
         if extra:
             out["other_workloads"] = extra
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -156,7 +156,24 @@ def render_domain_schedule(engine, dist, rank, world, device, fb_tensor, max_rou
     return log
 
 
-def build_domain_rank(desc, rank, world, flags=None, boxes=None):
+def gyroid_balanced_owner(world):
+    """Brick -> rank map for BASELINE config 4 (2x2x2 bricks, index = bx + 2 by + 4 bz, camera on the (1,1,1) diagonal).
+    In GraviT the owner of a domain is whichever rank loaded it (`Locations`, DomainTracer.h:115-144) -- data placement is
+    the application's choice.  Seen from the diagonal, brick 7 shows three quarter-faces, bricks 3/5/6 two, bricks 1/2/4 one
+    and brick 0 none, so `k mod N` puts 2/3 of the first-hit work on one of two ranks; this placement evens it out for
+    N = 2 and 4 (N = 8 is one brick per rank either way)."""
+    table = {
+        1: [0] * 8,
+        2: [0, 0, 0, 1, 0, 1, 1, 0],      # {7,0,1,2,4} = 3+0+1+1+1 | {3,5,6} = 2+2+2
+        4: [0, 1, 2, 1, 3, 2, 3, 0],      # {7,0} | {3,1} | {5,2} | {6,4}: 3 units each
+        8: list(range(8)),
+    }
+    if world not in table:
+        return domain_owner(8, world)
+    return np.asarray(table[world], dtype=np.int32)
+
+
+def build_domain_rank(desc, rank, world, flags=None, boxes=None, owner=None):
     """The scene one DomainScheduler rank holds: every instance (matrices + boxes, for routing) but only the meshes of
     the instances it owns (DomainTracer.h:115-144: instance k lives on rank k % world).  `desc` is a scenes.library
     description.  A mesh this rank does not own may have verts=None; then boxes[k] = its (lo.xyz, hi.xyz) bounding box
@@ -164,7 +181,7 @@ def build_domain_rank(desc, rank, world, flags=None, boxes=None):
     that api::addInstance computes the same instance box on every rank.  Returns (StandaloneScene, owner table)."""
     import gravit_b200 as g
 
-    owner = domain_owner(len(desc.instances), world)
+    owner = domain_owner(len(desc.instances), world) if owner is None else np.asarray(owner, dtype=np.int32)
     flags = desc.flags if flags is None else flags
     needed = [any(owner[i] == rank and mi == k for i, (mi, _) in enumerate(desc.instances)) for k in range(len(desc.meshes))]
     host = g.GvtScene(flags=flags)  # host layer: Mesh::addFace filter, normals, addInstance matrices and boxes

@@ -130,6 +130,14 @@ def bunny_scene(width=1920, height=1080):
     return _bunny_camera(d)
 
 
+def incoherent_scene(width=3840, height=2160):
+    """BASELINE config 5: sibenik at 4K, 9 spp (samples = 3: the reference allocates W*H*samples^2 rays, gvtCamera.cpp:205,
+    so 8 spp is not expressible), rayMaxDepth 5 = four diffuse bounces: divergent traversal, compaction heavy."""
+    d = sibenik_scene(width, height, depth=5, samples=3)
+    d.name = "sibenik_incoherent"
+    return d
+
+
 def sibenik_scene(width=1920, height=1080, depth=2, samples=1):
     """BASELINE configs 2/5: sibenik.obj, data/sibenik.conf:2-5 camera; light chosen.
     The eye is inside the cathedral's box, so FLAG_ENTER_INSIDE (deviation F6) is part of the scene, and so is
@@ -216,11 +224,16 @@ def gyroid_brick(res, brick, bricks=2, extent=8 * math.pi):
     return verts, idx
 
 
-def gyroid_scene(res=64, bricks=2, width=3840, height=2160, only_bricks=None):
+GYROID_RES_100M = 946  # triangles ~ 111.6 * res^2 (measured at res 128 and 256): 946 -> 99.9 M
+
+
+def gyroid_scene(res=64, bricks=2, width=3840, height=2160, only_bricks=None, brick_fn=None):
     """BASELINE config 4: gyroid isosurface cut into bricks^3 domains, one mesh + identity instance each.
-    res=64 is a test size (~0.2 M tris); res ~ 1340 gives ~100 M.  `only_bricks` builds geometry only for the
+    res=64 is a test size (~0.47 M tris); res = GYROID_RES_100M gives 100 M.  `only_bricks` builds geometry only for the
     listed brick indices (a DomainScheduler rank builds its own bricks); other meshes are tiny placeholders
-    with the same bounding box corners so that every rank holds the same instance boxes."""
+    with the same bounding box corners so that every rank holds the same instance boxes.  brick_fn: gyroid_brick
+    (numpy, default) or gyroid_brick_torch (GPU, for the full-size scene)."""
+    brick_fn = brick_fn or gyroid_brick
     d = SceneDesc(f"gyroid_{res}", width=width, height=height)
     extent = 8 * math.pi
     k = 0
@@ -228,7 +241,7 @@ def gyroid_scene(res=64, bricks=2, width=3840, height=2160, only_bricks=None):
         for by in range(bricks):
             for bx in range(bricks):
                 if only_bricks is None or k in only_bricks:
-                    v, t = gyroid_brick(res, (bx, by, bz), bricks, extent)
+                    v, t = brick_fn(res, (bx, by, bz), bricks, extent)
                 else:
                     v, t = None, None
                 d.meshes.append(MeshDesc(v, t, True, (0.8, 0.8, 0.8)))
@@ -242,3 +255,59 @@ def gyroid_scene(res=64, bricks=2, width=3840, height=2160, only_bricks=None):
     d.lights = [(d.eye, (40.0, 40.0, 40.0))]
     d.depth, d.samples, d.jitter = 1, 1, 0.0
     return d
+
+
+def gyroid_brick_torch(res, brick, bricks=2, extent=8 * math.pi, device="cuda", slab=32):
+    """gyroid_brick on the GPU with torch, one z-slab of cells at a time (the 100 M-triangle bricks of BASELINE config 4 are
+    out of reach for the numpy version: 3e8 grid points per brick).  Same marching-tetrahedra cases and the same
+    interpolation as gyroid_brick; the triangles come out in slab-major order.  Returns numpy (verts, tris 1-based).
+    Scene generation only -- this is synthetic input data, not part of the render path."""
+    import torch
+
+    n = res // bricks
+    bx, by, bz = brick
+    h = extent / res
+    dd = torch.float64
+    ax = [(torch.arange(n + 1, device=device, dtype=dd) + b * n) * h for b in (bx, by)]
+    out = []
+    for z0 in range(0, n, slab):
+        nz = min(slab, n - z0)
+        az = (torch.arange(nz + 1, device=device, dtype=dd) + (bz * n + z0)) * h
+        X, Y, Z = torch.meshgrid(ax[0], ax[1], az, indexing="ij")
+        F = (torch.sin(X) * torch.cos(Y) + torch.sin(Y) * torch.cos(Z) + torch.sin(Z) * torch.cos(X)).to(torch.float32)
+        P = torch.stack([X, Y, Z], -1).to(torch.float32)
+        del X, Y, Z
+        cs = [(slice(c[0], c[0] + n), slice(c[1], c[1] + n), slice(c[2], c[2] + nz)) for c in _CORNERS]
+        fv = [F[s].reshape(-1) for s in cs]
+        pv = [P[s].reshape(-1, 3) for s in cs]
+
+        def interp(a, b, sel):
+            fa, fb = fv[a][sel], fv[b][sel]
+            t = (fa / (fa - fb))[:, None]
+            return pv[a][sel] + (pv[b][sel] - pv[a][sel]) * t
+
+        for tet in _MC_TETS:
+            inside = [(fv[k] < 0).to(torch.int32) for k in tet]
+            code = inside[0] + inside[1] * 2 + inside[2] * 4 + inside[3] * 8
+            for c in range(1, 15):
+                sel = torch.nonzero(code == c).reshape(-1)
+                if sel.numel() == 0:
+                    continue
+                ins = [k for k in range(4) if c >> k & 1]
+                outs = [k for k in range(4) if not (c >> k & 1)]
+                if len(ins) == 1 or len(ins) == 3:
+                    a = ins[0] if len(ins) == 1 else outs[0]
+                    others = outs if len(ins) == 1 else ins
+                    out.append(torch.stack([interp(tet[a], tet[o], sel) for o in others], 1).cpu())
+                else:
+                    a, b = ins
+                    c0, d0 = outs
+                    p0, p1 = interp(tet[a], tet[c0], sel), interp(tet[a], tet[d0], sel)
+                    p2, p3 = interp(tet[b], tet[d0], sel), interp(tet[b], tet[c0], sel)
+                    out.append(torch.stack([p0, p1, p2], 1).cpu())
+                    out.append(torch.stack([p0, p2, p3], 1).cpu())
+        del F, P, fv, pv
+    tris = torch.cat(out, 0).numpy() if out else np.zeros((0, 3, 3), np.float32)
+    verts = np.ascontiguousarray(tris.reshape(-1, 3), dtype=np.float32)
+    idx = (np.arange(len(verts), dtype=np.uint32) + 1).reshape(-1, 3)
+    return verts, idx
