@@ -177,6 +177,14 @@ def api():
         A.gvtapi_engine_scene.restype = vp
         A.gvtapi_instance_get.argtypes = [i32, vp, vp, vp, vp]
         A.gvtapi_mesh_get.argtypes = [s, vp, vp, vp, vp]
+        # scene ingestion (host/readers.cpp)
+        A.gvtapi_reader_last_error.restype = C.c_char_p
+        A.gvtapi_obj_read.argtypes = [s, i32, vp, vp, vp, vp, vp, vp, vp]
+        A.gvtapi_ply_read.argtypes = [s, vp, vp, vp, vp, vp]
+        A.gvtapi_parse_float.argtypes = [s, vp]
+        A.gvtapi_load_obj.argtypes = [s, i32, s]
+        A.gvtapi_load_ply_dir.argtypes = [s, i32, vp]
+        A.gvtapi_load_conf.argtypes = [s, vp]
         _api = A
     return _api
 
@@ -190,6 +198,59 @@ def check(rc):
 def acheck(rc):
     if rc != 0:
         raise EngineError(api().gvtapi_last_error().decode())
+
+
+def rcheck(rc):
+    if rc != 0:
+        raise EngineError(api().gvtapi_reader_last_error().decode())
+
+
+def read_obj(path, material_type=0):
+    """ObjReader (host/readers.cpp) without scene calls: dict of vertices, faces (0-based), face_mat, materials
+    (ka, kd, ks, type), normals as stored in the file, bounds."""
+    A = api()
+    n = np.zeros(5, np.uint32)
+    rcheck(A.gvtapi_obj_read(path.encode(), material_type, _fp(n), None, None, None, None, None, None))
+    v, f = np.zeros((n[0], 3), np.float32), np.zeros((n[1], 3), np.uint32)
+    fm, mats = np.zeros(n[1] if n[2] else 0, np.int32), np.zeros((n[2], 10), np.float32)
+    nr, b = np.zeros((n[3], 3), np.float32), np.zeros(6, np.float32)
+    rcheck(A.gvtapi_obj_read(path.encode(), material_type, _fp(n), _fp(v), _fp(f), _fp(fm), _fp(mats), _fp(nr), _fp(b)))
+    return dict(vertices=v, faces=f, face_mat=fm, materials=mats, normals=nr, bounds=b)
+
+
+def read_ply(path):
+    """PlyReader::readFile: vertices, faces (0-based, first three indices of every list), colors in [0,1] or empty."""
+    A = api()
+    n = np.zeros(5, np.uint32)
+    rcheck(A.gvtapi_ply_read(path.encode(), _fp(n), None, None, None, None))
+    v, f, c, b = np.zeros((n[0], 3), np.float32), np.zeros((n[1], 3), np.uint32), np.zeros((n[4], 3), np.float32), np.zeros(6, np.float32)
+    rcheck(A.gvtapi_ply_read(path.encode(), _fp(n), _fp(v), _fp(f), _fp(c), _fp(b)))
+    return dict(vertices=v, faces=f, colors=c, bounds=b)
+
+
+def parse_obj_float(text):
+    out = np.zeros(1, np.float32)
+    api().gvtapi_parse_float(text.encode(), _fp(out))
+    return out[0]
+
+
+def load_obj(path, meshname, material_type=0):
+    """ObjReader(path).addToScene(meshname): the mesh goes into the api:: database."""
+    rcheck(api().gvtapi_load_obj(path.encode(), material_type, meshname.encode()))
+
+
+def load_ply_dir(path, add_instances=True):
+    n = C.c_int(0)
+    rcheck(api().gvtapi_load_ply_dir(path.encode(), int(add_instances), C.byref(n)))
+    return n.value
+
+
+def load_conf(path):
+    """gvtapps::render::ConfigFileLoader: builds the whole scene (meshes, instances, lights, camera "Camera", film "Film",
+    renderer "Renderer") in the api:: database."""
+    info = np.zeros(7, np.int32)
+    rcheck(api().gvtapi_load_conf(path.encode(), _fp(info)))
+    return dict(zip(("scheduler_type", "domain_type", "accel_type", "width", "height", "n_instances", "n_lights"), (int(x) for x in info)))
 
 
 _inited = None

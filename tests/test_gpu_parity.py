@@ -439,3 +439,42 @@ def test_domain_scheduler_peer_exchange(gpu, world):
         assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref1)) >= 50.0
     for e in ranks:
         e.close()
+
+
+@pytest.mark.gpu
+def test_conf_file_scene_end_to_end(gpu, tmp_path):
+    """a data/*.conf style scene file (OBJ + MTL, two instances of one mesh, point light) loaded by the C++
+    ConfigFileLoader / ObjReader, rendered through api::render, equals the oracle fed with the same arrays; writeimage
+    round-trips through the PPM writer."""
+    import math
+
+    g = gpu
+    fx = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "readers")
+    A = g.api()
+    g.acheck(A.gvtapi_reset())
+    g.acheck(A.gvtapi_set_engine_flags(0, 0))
+    info = g.load_conf(os.path.join(fx, "scene.conf"))
+    W, H = info["width"], info["height"]
+    g.acheck(A.gvtapi_render(b"Renderer"))
+    fb = np.zeros((H, W, 4), np.float32)
+    g.acheck(A.gvtapi_framebuffer(g._fp(fb), fb.size, None, None))
+
+    m = g.read_obj(os.path.join(fx, "box.obj"))
+    mats = np.zeros((len(m["materials"]), 8), np.float32)
+    mats[:, 0], mats[:, 1:4], mats[:, 4:7], mats[:, 7] = m["materials"][:, 9], m["materials"][:, 3:6], m["materials"][:, 6:9], 1.0
+    o = po.OracleScene(flags=0)
+    mid = o.add_mesh(m["vertices"], m["faces"], one_based=False)
+    o.mesh_face_materials(mid, mats, m["face_mat"])
+    o.add_instance(mid, [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, np.float32(-0.8), 0, 0, 1])
+    o.add_instance(mid, [0.5, 0, 0, 0, 0, 1.5, 0, 0, 0, 0, 0.5, 0, np.float32(0.8), 0, 0, 1])
+    o.add_point_light((0.5, 2.5, 3.0), (1.0, 1.0, 1.0))
+    o.set_camera((0.2, 0.6, 3.5), (0.0, 0.2, 0.0), (0, 1, 0), float(np.float32(40.0 * math.pi / 180.0)), 1, 1, 0.0)
+    o.set_film(W, H)
+    o.commit()
+    ref, st = o.render(threads=4)
+    assert st["primary_hits"] > 500 and (ref[..., :3].reshape(-1, 3).max(0) > 0).all()
+    assert np.array_equal(fb, ref)
+    out = str(tmp_path / "conf_scene")
+    g.acheck(A.gvtapi_writeimage(b"Renderer", out.encode()))
+    assert open(out + ".ppm", "rb").read() == po.fb_to_ppm_bytes(ref)
+    g.acheck(A.gvtapi_reset())
