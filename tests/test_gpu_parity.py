@@ -3,6 +3,8 @@
 Bars (BASELINE.json north_star): Morton codes, routing and queue contents bit-exact; hit ids >= 99.9 % (here: all equal
 on these inputs), t within 1e-5 relative (here: bit-exact, the triangle test is the same IEEE sequence on both sides);
 images >= 50 dB PSNR against the oracle framebuffer and within the reference's own tolerance of its golden PPMs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -476,5 +478,6 @@ def test_conf_file_scene_end_to_end(gpu, tmp_path):
     assert np.array_equal(fb, ref)
     out = str(tmp_path / "conf_scene")
     g.acheck(A.gvtapi_writeimage(b"Renderer", out.encode()))
-    assert open(out + ".ppm", "rb").read() == po.fb_to_ppm_bytes(ref)
+    w, h, pix = po.read_ppm(open(out + ".ppm", "rb").read())
+    assert (w, h) == (W, H) and np.array_equal(pix, po.fb_to_ppm_bytes(ref))
     g.acheck(A.gvtapi_reset())
