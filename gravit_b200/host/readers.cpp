@@ -103,12 +103,6 @@ float next_float(const char *&tok) {
   tok = end;
   return (float)v;
 }
-int next_int(const char *&tok) {
-  tok += strspn(tok, " \t");
-  int i = atoi(tok);
-  tok += strcspn(tok, " \t\r");
-  return i;
-}
 std::string next_word(const char *tok) { // sscanf("%s")
   tok += strspn(tok, " \t\r\n");
   size_t n = strcspn(tok, " \t\r\n");
