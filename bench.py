@@ -23,7 +23,10 @@ N > 1 (torchrun, one rank per GPU).  ImageScheduler workloads: the film rows of 
 tiles, geometry replicated, and the rows are gathered into rank 0's framebuffer over the NVLink peer path (no collective;
 --no-p2p falls back to an NCCL reduce).  gyroid (BASELINE configs[3]): Tracer<DomainScheduler>, brick k of the 2x2x2 split
 lives on rank k mod N, the trace kernel stores migrating rays into the owner's queue over NVLink, one 8-byte all-reduce
-per exchange round.  Both are strong scaling of one frame.
+per exchange round (strong scaling of one frame: the 100 M-triangle mesh is the fixed job).  ImageScheduler workloads default to
+WEAK scaling (--scaling weak): the unit of work is a film tile, and with N ranks the film grows by sqrt(N) on each axis (same
+scene, camera and aspect: 1920x1080 -> 2715x1527 -> 3840x2160 -> 5431x3055), so every rank keeps the N = 1 ray count and the
+only cross-rank step is the row gather into rank 0.  --scaling strong deals the N = 1 film over the ranks instead.
 """
 import argparse
 import json
@@ -43,13 +46,13 @@ from scenes import library  # noqa: E402
 
 WORKLOADS = {
     # BASELINE.json configs[1]: sibenik 1080p, shadow + 1 bounce (rayMaxDepth 2)
-    "sibenik": dict(make=lambda: library.sibenik_scene(1920, 1080, depth=2), name="sibenik.obj 75,284 tris, 1920x1080, 1 point light, shadow + 1 bounce (configs[1])"),
+    "sibenik": dict(make=lambda w=1920, h=1080: library.sibenik_scene(w, h, depth=2), name="sibenik.obj 75,284 tris, 1920x1080, 1 point light, shadow + 1 bounce (configs[1])"),
     # north_star target: 70K bunny at 1080p, primary + shadow
-    "bunny": dict(make=lambda: library.bunny_scene(1920, 1080), name="bun_zipper 69,451 tris, 1920x1080, 1 point light, primary+shadow"),
+    "bunny": dict(make=lambda w=1920, h=1080: library.bunny_scene(w, h), name="bun_zipper 69,451 tris, 1920x1080, 1 point light, primary+shadow"),
     # configs[2]: 32x32 instanced bunnies at 4K
-    "grid": dict(make=lambda: library.bunny_grid_scene(32, 3840, 2160), name="32x32 bunny instances (71.1M effective tris), 3840x2160, primary+shadow (configs[2])"),
+    "grid": dict(make=lambda w=3840, h=2160: library.bunny_grid_scene(32, w, h), name="32x32 bunny instances (71.1M effective tris), 3840x2160, primary+shadow (configs[2])"),
     # configs[4]: incoherent stress
-    "incoherent": dict(make=lambda: library.incoherent_scene(3840, 2160), name="sibenik.obj 3840x2160, 9 spp, rayMaxDepth 5 (4 diffuse bounces) (configs[4])"),
+    "incoherent": dict(make=lambda w=3840, h=2160: library.incoherent_scene(w, h), name="sibenik.obj 3840x2160, 9 spp, rayMaxDepth 5 (4 diffuse bounces) (configs[4])"),
     # configs[3]: 100M-triangle gyroid isosurface in 8 bricks (built per rank in main(): geometry is generated on the GPU)
     "gyroid": dict(make=None, name="gyroid isosurface, 2x2x2 bricks, 3840x2160, primary+shadow (configs[3])"),
 }
@@ -139,26 +142,31 @@ def cpu_reference(desc, threads, target_s=12.0):
     so that one frame takes a few seconds; rays counted exactly as on the GPU."""
     from oracle import pyoracle as po
 
-    def run(w, h):
+    def run(w, h, budget_s=0.0):
         d = desc()
         d.width, d.height = w, h
         s = library.apply(d, po.OracleScene(flags=d.flags))
-        t0 = time.perf_counter()
-        fb, st = s.render(threads=threads)
-        dt = time.perf_counter() - t0
-        rays = st["camera_rays"] + st["shadow_generated"] + st["secondary_generated"]
-        return rays, dt
+        rays_all, dts = 0, []
+        while True:  # whole frames until the sample has used its budget; the rate is total rays / total time
+            t0 = time.perf_counter()
+            fb, st = s.render(threads=threads)
+            dts.append(time.perf_counter() - t0)
+            rays = st["camera_rays"] + st["shadow_generated"] + st["secondary_generated"]
+            rays_all += rays
+            if sum(dts) >= budget_s or len(dts) >= 64:
+                break
+        return rays_all, sum(dts), len(dts)
 
     d0 = desc()
     w, h = max(64, d0.width // 8), max(36, d0.height // 8)
-    rays, dt = run(w, h)
+    rays, dt, _ = run(w, h)
     rate = rays / dt
     scale = min(8.0, max(1.0, (target_s * rate / max(rays, 1)) ** 0.5))
     w2, h2 = int(w * scale), int(h * scale)
     if scale > 1.2:
-        rays, dt = run(w2, h2)
         w, h = w2, h2
-    return rays / dt / 1e6, f"{w}x{h} film of the same scene/camera, {rays} rays in {dt:.2f} s, {threads} threads", rays, dt
+    rays, dt, frames = run(w, h, budget_s=target_s)
+    return rays / dt / 1e6, f"{frames} frame(s) of the {w}x{h} film of the same scene/camera, {rays} rays in {dt:.2f} s, {threads} threads", rays, dt
 
 
 def main():
@@ -183,6 +191,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-p2p", action="store_true", help="N > 1: NCCL reduce / all-to-all instead of the NVLink peer path")
     ap.add_argument("--owner", default="mod", choices=["mod", "balanced"], help="gyroid: brick k on rank k mod N (the reference's map) or the view-balanced placement")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1, ImageScheduler workloads: weak = the film grows by sqrt(N) per axis so every rank keeps the N = 1 "
+                    "ray count (same scene, camera and aspect); strong = the N = 1 film split over the ranks")
     ap.add_argument("--gyroid-res", type=int, default=library.GYROID_RES_100M, help="grid cells per axis of the gyroid volume (946 = 100 M triangles)")
     a = ap.parse_args()
     a.warmup = max(3, a.warmup)
@@ -206,7 +216,8 @@ def main():
         d = wl["make"]()
         out = {
             "impl": "reference", "metric": "Mrays/s (primary+shadow+secondary)", "value": v, "unit": "Mrays/s", "n_gpus": a.gpus,
-            "steps": len(vals), "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "steps": len(vals), "warmup": 0, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "strong" if (a.gpus > 1 and (a.scaling == "strong" or a.workload == "gyroid")) else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "film": [d.width, d.height], "depth": d.depth, "note": "CPU port of the reference path (oracle/); Embree 2.15 is absent so the Embree adapter itself cannot be built"},
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
@@ -229,6 +240,9 @@ def main():
 
     domain = a.workload == "gyroid"
     p2p = world > 1 and not a.no_p2p
+    # ImageScheduler at N > 1: the unit of work is a film tile.  weak = N times the tiles of the N = 1 film (each axis x sqrt(N),
+    # same scene / camera / aspect), every rank keeps the N = 1 ray count; strong = the N = 1 film dealt over the ranks.
+    weak = world > 1 and not domain and a.scaling == "weak"
     build_s = [0.0]
 
     def setup(name):
@@ -249,7 +263,12 @@ def main():
                 m.verts = m.tris = None  # the host copies are not needed any more
             build_s[0] = time.perf_counter() - t0
             return d, None, e
-        d = WORKLOADS[name]["make"]()
+        if weak and name == a.workload:
+            d0 = WORKLOADS[name]["make"]()
+            f = world ** 0.5
+            d = WORKLOADS[name]["make"](int(round(d0.width * f)), int(round(d0.height * f)))
+        else:
+            d = WORKLOADS[name]["make"]()
         s = library.apply(d, g.GvtScene(flags=d.flags))
         e = s.engine()
         return d, s, e
@@ -439,10 +458,10 @@ def main():
             sched_desc = "ImageScheduler" + (f", {world} ranks, row tiles of {a.tile_rows} dealt round-robin, " + ("rows stored into rank 0's framebuffer over NVLink (CUDA IPC), no collective" if p2p else "NCCL reduce to rank 0") if world > 1 else "")
         out = {
             "metric": "Mrays/s (primary+shadow+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": wl["name"], "film": [W, H], "depth": d.depth, "samples": d.samples, "rays_per_frame": rays_frame, "bvh": "binned SAH, 8-wide, 128 B nodes",
+                "workload": wl["name"] + (f"; weak scaling: film {W}x{H} = {world} x the N=1 film's pixels, same camera and aspect" if weak else ""), "film": [W, H], "depth": d.depth, "samples": d.samples, "rays_per_frame": rays_frame, "bvh": "binned SAH, 8-wide, 128 B nodes",
                 "scheduler": sched_desc,
                 "l2": "256 MiB buffer rewritten between timed frames (L2 flush)", "timing": "CUDA events per frame on the launching stream, max over ranks",
             },

@@ -169,6 +169,11 @@ def api():
         A.gvtapi_add_film.argtypes = [s, i32, i32, s]
         A.gvtapi_modify_film.argtypes = [s, i32, i32, s]
         A.gvtapi_add_renderer.argtypes = [s, i32, i32, s, s]
+        A.gvtapi_modify_area_light.argtypes = [s, vp, vp, vp, f, f]
+        A.gvtapi_add_mesh_face_normals.argtypes = [s, u32, vp]
+        A.gvtapi_modify_renderer.argtypes = [s, i32, i32, s, s]
+        A.gvtapi_add_renderer_volume.argtypes = [s, i32, i32, s, s, i32]
+        A.gvtapi_modify_camera_pose.argtypes = [s, vp, vp, vp, f]
         A.gvtapi_render.argtypes = [s]
         A.gvtapi_writeimage.argtypes = [s, s]
         A.gvtapi_set_engine_flags.argtypes = [u32, u32]

@@ -266,7 +266,11 @@ gvtb200_scene device_scene(const RendererRec &r) {
   if (gvtb200_scene_set_camera(c.scene, cr.eye, cr.focus, cr.up, cr.fov, cr.depth, cr.samples, cr.jitter) != GVTB200_OK)
     engine_error("camera");
   if (gvtb200_scene_set_film(c.scene, film->second.w, film->second.h) != GVTB200_OK) engine_error("film");
-  if (gvtb200_scene_set_flags(c.scene, c.flags, c.seed) != GVTB200_OK) engine_error("flags");
+  // adapter::EmbreeStream (Types.h:44): EmbreeStreamMeshAdapter.cpp has no `#define FLAT_SHADING` (EmbreeMeshAdapter.cpp:75
+  // does), so its hits are shaded with interpolated vertex normals (:931-946); its explicit minv*ray transform (:308-309) and
+  // 1x64 ray streams (CMakeLists.txt:457-458) are what this engine does for every adapter type already.
+  const unsigned flags = c.flags | (r.adapter == gvt::render::adapter::EmbreeStream ? (unsigned)GVTB200_FLAG_SMOOTH : 0u);
+  if (gvtb200_scene_set_flags(c.scene, flags, c.seed) != GVTB200_OK) engine_error("flags");
   return c.scene;
 }
 
@@ -529,6 +533,20 @@ GAPI int gvtapi_add_area_light(const char *n, const float *p, const float *c, co
   return guard([&] { api::addAreaLight(n, p, c, nn, w, h); });
 }
 GAPI int gvtapi_modify_light(const char *n, const float *p, const float *c) { return guard([&] { api::modifyLight(n, p, c); }); }
+GAPI int gvtapi_modify_area_light(const char *n, const float *p, const float *c, const float *nn, float w, float h) {
+  return guard([&] { api::modifyLight(n, p, c, nn, w, h); });
+}
+GAPI int gvtapi_add_mesh_face_normals(const char *n, unsigned k, const float *v) { return guard([&] { api::addMeshFaceNormals(n, k, v); }); }
+GAPI int gvtapi_modify_renderer(const char *n, int adapter, int schedule, const char *cam, const char *film) {
+  return guard([&] { api::modifyRenderer(n, adapter, schedule, cam, film); });
+}
+GAPI int gvtapi_add_renderer_volume(const char *n, int adapter, int schedule, const char *cam, const char *film, int volume) {
+  return guard([&] { api::addRenderer(n, adapter, schedule, cam, film, volume != 0); });
+}
+GAPI int gvtapi_modify_camera_pose(const char *n, const float *p, const float *f, const float *u, float fov) {
+  return guard([&] { api::modifyCamera(n, p, f, u, fov); });
+}
+GAPI int gvtapi_gvtsync() { return guard([&] { api::gvtsync(); }); }
 GAPI int gvtapi_add_camera(const char *n, const float *p, const float *f, const float *u, float fov, int depth, int samples, float jitter) {
   return guard([&] { api::addCamera(n, p, f, u, fov, depth, samples, jitter); });
 }
