@@ -137,6 +137,38 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
+class cpu_frame_timer:
+    """The CPU oracle rendering whole frames of a reduced film (same scene and camera), the film chosen so that one frame
+    takes about `step_s` seconds on `threads` host threads; frame() returns (rays traced, seconds)."""
+
+    def __init__(self, desc, threads, step_s):
+        from oracle import pyoracle as po
+
+        self.po, self.desc, self.threads = po, desc, threads
+        d0 = desc()
+        self.w, self.h = max(64, d0.width // 8), max(36, d0.height // 8)
+        self._scene()
+        for _ in range(3):  # the cost is not proportional to the film at small sizes (per-frame set-up): iterate
+            rays, dt = self.frame()
+            scale = min(8.0 * max(64, d0.width // 8) / self.w, (step_s / dt) ** 0.5)
+            if scale < 1.2:
+                break
+            self.w, self.h = int(self.w * scale), int(self.h * scale)
+            self._scene()
+
+    def _scene(self):
+        d = self.desc()
+        d.width, d.height = self.w, self.h
+        self.scene = library.apply(d, self.po.OracleScene(flags=d.flags))
+        self.frame()  # first touch: acceleration-structure build, page faults, thread start-up
+
+    def frame(self):
+        t0 = time.perf_counter()
+        _, st = self.scene.render(threads=self.threads)
+        dt = time.perf_counter() - t0
+        return st["camera_rays"] + st["shadow_generated"] + st["secondary_generated"], dt
+
+
 def cpu_reference(desc, threads, target_s=12.0):
     """Times the CPU oracle on a bounded sample of the workload: the same scene and camera at a reduced film size chosen
     so that one frame takes a few seconds; rays counted exactly as on the GPU."""
@@ -207,16 +239,23 @@ def main():
             return 0
         if wl["make"] is None:  # a CPU-sized gyroid: the port builds its own BVH in seconds at this size
             wl = dict(wl, make=lambda: library.gyroid_scene(128, 2, 3840, 2160))
-        vals = []
-        sample = ""
-        for _ in range(max(1, min(a.steps, 3))):
-            v, sample, _, _ = cpu_reference(wl["make"], threads, target_s=8.0)
-            vals.append(v)
-        v = statistics.median(vals)
+        # one step = one whole frame of a reduced film of the same scene and camera (the bounded sample), sized so that the
+        # W + K frames take about half a minute; the rate is rays / time over the K timed frames
+        step_s = min(4.0, max(0.25, 24.0 / max(1, a.steps)))
+        timer = cpu_frame_timer(wl["make"], threads, step_s)
+        for _ in range(a.warmup):
+            timer.frame()
+        rays, dts = 0, []
+        for _ in range(a.steps):
+            r, dt = timer.frame()
+            rays += r
+            dts.append(dt)
+        v = rays / sum(dts) / 1e6
+        sample = f"{a.steps} frame(s) of the {timer.w}x{timer.h} film of the same scene/camera, {rays} rays in {sum(dts):.2f} s, {threads} threads"
         d = wl["make"]()
         out = {
             "impl": "reference", "metric": "Mrays/s (primary+shadow+secondary)", "value": v, "unit": "Mrays/s", "n_gpus": a.gpus,
-            "steps": len(vals), "warmup": 0, "ms_per_step": None, "higher_is_better": True,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(dts) / len(dts), "higher_is_better": True,
             "scaling": "strong" if (a.gpus > 1 and (a.scaling == "strong" or a.workload == "gyroid")) else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "film": [d.width, d.height], "depth": d.depth, "note": "CPU port of the reference path (oracle/); Embree 2.15 is absent so the Embree adapter itself cannot be built"},
