@@ -32,6 +32,10 @@ struct BuildCtx {
   float4 *wtris;  // 3 per triangle record slot (GVT_LEAF_MAX slots per leaf child)
   unsigned *node_count, *tri_count, *tri_real; // wide nodes, triangle record slots, triangles referenced
   unsigned wnode_cap;
+  // optimal widening (collapse_dp_node): per internal binary node, null = surface-area-greedy widening
+  float *dp_cost;         // [7 * node + i - 1] = C(node, i), i = 1..7
+  unsigned char *dp_pick; // [8 * node + j - 1], j = 2..8: left share k of the best distribution of j roots; [8 * node]: bit 0 =
+                          // "C(node,1) is a leaf", bits 1..6 = "C(node,i) is C(node,i-1)" for i = 2..7
 };
 
 // absolute padding of the leaf boxes: the canonical triangle test is evaluated in fp32, so a ray can be accepted while
@@ -126,8 +130,12 @@ GVT_HD void karras_node(const BuildCtx &c, int i) {
 // exactly instead of binning.  The output has the layout the Karras tree had (internal nodes 0..n-2 with root 0, leaf
 // n-1+k = sorted position k, bn_child / bn_range / bn_parent / bn_lo / bn_hi), so refit is not needed and the wide
 // collapse below is unchanged.  Replaces the SAH builder inside Embree's rtcCommit (EmbreeMeshAdapter.cpp:125-162).
+#ifndef GVT_SAH_BINS
 #define GVT_SAH_BINS 16
+#endif
+#ifndef GVT_SAH_SMALL
 #define GVT_SAH_SMALL 8
+#endif
 
 GVT_HD int fenc(float f) { // order-preserving float -> signed int
   int i = (int)f2u(f);
@@ -288,6 +296,87 @@ GVT_HD uint32_t quant_exponent(float ext) {
   return e;
 }
 
+// ---- optimal widening (Ylitie, Karras, Laine, HPG 2017, section 3.1) -------------------------------------------
+// C(n, i) = cheapest SAH cost of binary subtree n represented by at most i roots (wide nodes or leaves):
+//   C(n, 1) = A_n * P_n * C_prim if P_n <= GVT_LEAF_MAX (a leaf slot), else C_dist(n, 8) + A_n * C_node (a wide node)
+//   C(n, i) = min( C_dist(n, i), C(n, i - 1) )                      i = 2..7
+//   C_dist(n, j) = min over 0 < k < j of C(left, k) + C(right, j - k)
+// evaluated bottom-up (one thread climbs from every leaf, the second arrival at a node does its row), then followed
+// top-down by collapse_gather_dp.  C_node : C_prim is the measured cost ratio of a node visit (8 L1 wavefronts, ~130
+// instructions) to a triangle test (3 wavefronts, ~40 instructions).
+#define GVT_DP_CNODE 1.0f
+#if defined(__CUDA_ARCH__)
+#define GVT_LDCG1(p) __ldcg(p)
+#else
+#define GVT_LDCG1(p) (*(p))
+#endif
+#ifndef GVT_DP_CPRIM
+#define GVT_DP_CPRIM 0.35f
+#endif
+
+GVT_HD float dp_cost_of(const BuildCtx &c, int b, int i) { // C(b, i), i = 1..7 (more roots than 7 never help a leaf triangle)
+  if (b >= (int)c.n - 1) return box_area(c.bn_lo[b], c.bn_hi[b]) * GVT_DP_CPRIM;
+  return GVT_LDCG1(&c.dp_cost[7 * (size_t)b + (i > 7 ? 7 : i) - 1]); // written by another thread of the same launch: through L2
+}
+GVT_HD void collapse_dp_node(const BuildCtx &c, int b) {
+  const int2 ch = c.bn_child[b];
+  float cl[8], cr[8];
+  for (int i = 1; i <= 7; ++i) cl[i] = dp_cost_of(c, ch.x, i), cr[i] = dp_cost_of(c, ch.y, i);
+  float dist[9];
+  unsigned char *pick = c.dp_pick + 8 * (size_t)b;
+  for (int j = 2; j <= 8; ++j) {
+    float best = FLT_MAX;
+    int bk = 1;
+    for (int k = 1; k < j; ++k) {
+      float v = cl[k] + cr[j - k];
+      if (v < best) best = v, bk = k;
+    }
+    dist[j] = best;
+    pick[j - 1] = (unsigned char)bk;
+  }
+  const float area = box_area(c.bn_lo[b], c.bn_hi[b]);
+  const int cnt = bnode_count(c, b);
+  float c1 = dist[8] + area * GVT_DP_CNODE;
+  unsigned char flags = 0;
+  if (cnt <= GVT_LEAF_MAX) c1 = area * (float)cnt * GVT_DP_CPRIM, flags |= 1u; // as one root it is a leaf slot
+  float *out = c.dp_cost + 7 * (size_t)b;
+  out[0] = c1;
+  for (int i = 2; i <= 7; ++i) {
+    float v = dist[i];
+    if (out[i - 2] <= v) v = out[i - 2], flags |= (unsigned char)(1u << (i - 1));
+    out[i - 1] = v;
+  }
+  pick[0] = flags;
+}
+// children of the wide node rooted at binary node `root`, by the tables: expand (node, roots allowed) pairs, left first
+GVT_HD int collapse_gather_dp(const BuildCtx &c, int root, int *ch) {
+  int nch = 0, sp = 0;
+  int sn[16], sj[16];
+  sn[sp] = root, sj[sp] = 8, sp++;
+  while (sp) {
+    --sp;
+    const int b = sn[sp];
+    int j = sj[sp];
+    if (b >= (int)c.n - 1) { // a single triangle
+      ch[nch++] = b;
+      continue;
+    }
+    const unsigned char flags = c.dp_pick[8 * (size_t)b];
+    if (j < 8) { // j == 8 is the root of this wide node: it is a wide node, distribute 8
+      while (j >= 2 && ((flags >> (j - 1)) & 1u)) --j; // C(b, j) is C(b, j - 1)
+      if (j == 1) {
+        ch[nch++] = b;
+        continue;
+      }
+    }
+    const int k = c.dp_pick[8 * (size_t)b + j - 1];
+    const int2 kid = c.bn_child[b];
+    sn[sp] = kid.y, sj[sp] = j - k, sp++;
+    sn[sp] = kid.x, sj[sp] = k, sp++;
+  }
+  return nch;
+}
+
 struct CollapseTask {
   int bnode; // binary node to turn into a wide node
   int wnode; // index of the wide node to write
@@ -306,29 +395,31 @@ struct WideNode { // what collapse_node decides, before the output ranges are kn
 // Builds wide node t.wnode from binary subtree t.bnode.  Host emulation and the device kernel share this body; the
 // device kernel reserves the output ranges with atomicAdd.
 GVT_HD void collapse_node(const BuildCtx &c, CollapseTask t, WideNode &w) {
-  // 1. gather up to 8 children: repeatedly open the child with the largest surface area that holds more than
-  //    GVT_LEAF_MAX triangles
+  // 1. gather up to 8 children: by the optimal-widening tables, or by repeatedly opening the child with the largest
+  //    surface area that holds more than GVT_LEAF_MAX triangles
   int ch[8];
   int nch = 0;
   if (t.bnode >= (int)c.n - 1) {
     ch[nch++] = t.bnode; // single-triangle mesh: the root is a leaf
+  } else if (c.dp_cost) {
+    nch = collapse_gather_dp(c, t.bnode, ch);
   } else {
     int2 k = c.bn_child[t.bnode];
     ch[nch++] = k.x;
     ch[nch++] = k.y;
-  }
-  while (nch < 8) {
-    int best = -1;
-    float besta = -1.f;
-    for (int i = 0; i < nch; ++i) {
-      if (bnode_count(c, ch[i]) <= GVT_LEAF_MAX) continue;
-      float a = box_area(c.bn_lo[ch[i]], c.bn_hi[ch[i]]);
-      if (a > besta) besta = a, best = i;
+    while (nch < 8) {
+      int best = -1;
+      float besta = -1.f;
+      for (int i = 0; i < nch; ++i) {
+        if (bnode_count(c, ch[i]) <= GVT_LEAF_MAX) continue;
+        float a = box_area(c.bn_lo[ch[i]], c.bn_hi[ch[i]]);
+        if (a > besta) besta = a, best = i;
+      }
+      if (best < 0) break;
+      int2 k2 = c.bn_child[ch[best]];
+      ch[best] = k2.x;
+      ch[nch++] = k2.y;
     }
-    if (best < 0) break;
-    int2 k = c.bn_child[ch[best]];
-    ch[best] = k.x;
-    ch[nch++] = k.y;
   }
   // 2. node frame
   float4 lo = c.bn_lo[ch[0]], hi = c.bn_hi[ch[0]];

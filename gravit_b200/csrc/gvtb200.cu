@@ -487,12 +487,14 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
   int2 *bn_child = nullptr, *bn_range = nullptr;
   int *bn_parent = nullptr;
   CollapseTask *d_ta = nullptr, *d_tb = nullptr;
+  float *dp_cost = nullptr;
+  unsigned char *dp_pick = nullptr;
   std::vector<unsigned *> scan_levels, scan_levels_flag; // per-size scratch of the two device-wide scans (radix histogram, SAH flags)
   int rc = GVTB200_OK;
   auto cleanup = [&]() {
     dfree(d_verts), dfree(d_faces3), dfree(d_keys), dfree(d_vals), dfree(d_keys2), dfree(d_vals2), dfree(d_hist), dfree(d_flag);
     dfree(sah_tb_lo), dfree(sah_tb_hi), dfree(sah_idx2), dfree(sah_node_of), dfree(sah_node_of2), dfree(sah_act), dfree(sah_act2), dfree(sah_bins);
-    dfree(d_counts), dfree(bn_lo), dfree(bn_hi), dfree(wnodes), dfree(wtris), dfree(bn_child), dfree(bn_range), dfree(bn_parent), dfree(d_ta), dfree(d_tb);
+    dfree(d_counts), dfree(bn_lo), dfree(bn_hi), dfree(wnodes), dfree(wtris), dfree(bn_child), dfree(bn_range), dfree(bn_parent), dfree(d_ta), dfree(d_tb), dfree(dp_cost), dfree(dp_pick);
     for (auto *p : scan_levels) cudaFree(p);
     for (auto *p : scan_levels_flag) cudaFree(p);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
@@ -605,6 +607,16 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
         k_karras<<<blocks_for(n, 256), 256, 0, st>>>(c);
         k_refit<<<blocks_for(n, 256), 256, 0, st>>>(c);
       }
+    }
+    // optimal widening: which binary nodes become the children of a wide node (GVTB200_WIDEN=greedy keeps the
+    // surface-area-greedy rule)
+    const char *wmode = getenv("GVTB200_WIDEN");
+    if (nf > 1 && !(wmode && !strcmp(wmode, "greedy"))) {
+      CUB(dalloc(&dp_cost, 7 * n));
+      CUB(dalloc(&dp_pick, 8 * n));
+      CUB(cudaMemsetAsync(d_flag, 0, n * 4, st));
+      c.dp_cost = dp_cost, c.dp_pick = dp_pick;
+      k_collapse_dp<<<blocks_for(n, 256), 256, 0, st>>>(c);
     }
     // collapse into 8-wide compressed nodes, one level per launch
     // worst case: one wide node per face, GVT_LEAF_MAX record slots per single-triangle leaf; shrunk below

@@ -48,6 +48,20 @@ __global__ void k_refit(BuildCtx c) {
     node = c.bn_parent[node];
   }
 }
+// optimal-widening tables, bottom-up: the second thread to reach an internal node fills its row (both children's rows
+// are complete by then) and continues upwards
+__global__ void k_collapse_dp(BuildCtx c) {
+  unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.n || c.n < 2) return;
+  int node = c.bn_parent[c.n - 1 + k];
+  while (node >= 0) {
+    __threadfence();
+    unsigned old = atomicAdd(&c.bn_flag[node], 1u);
+    if (old == 0u) return;
+    collapse_dp_node(c, node);
+    node = c.bn_parent[node];
+  }
+}
 // one thread per wide node of the current level; children tasks are appended to `out`
 __global__ void k_collapse(BuildCtx c, const CollapseTask *in, unsigned n_in, CollapseTask *out, unsigned *n_out) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;

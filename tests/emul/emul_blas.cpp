@@ -162,6 +162,25 @@ EM_API void *emul_build(const float *verts, unsigned nv, const uint32_t *faces, 
     }
   }
   }
+  // optimal widening tables, bottom-up (children before parents)
+  std::vector<float> dp_cost;
+  std::vector<unsigned char> dp_pick;
+  const char *wmode = getenv("GVTB200_WIDEN");
+  if (nf > 1 && !(wmode && !strcmp(wmode, "greedy"))) {
+    dp_cost.assign(7 * (size_t)nf, 0.f), dp_pick.assign(8 * (size_t)nf, 0);
+    c.dp_cost = dp_cost.data(), c.dp_pick = dp_pick.data();
+    std::vector<int> stack, order;
+    stack.push_back(0);
+    while (!stack.empty()) {
+      int b = stack.back();
+      stack.pop_back();
+      order.push_back(b);
+      int2 ch = c.bn_child[b];
+      if (ch.x < (int)nf - 1) stack.push_back(ch.x);
+      if (ch.y < (int)nf - 1) stack.push_back(ch.y);
+    }
+    for (size_t i = order.size(); i-- > 0;) collapse_dp_node(c, order[i]);
+  }
   // collapse, level by level
   m->wnodes.assign(GVT_NODE_WORDS * (size_t)std::max(1u, nf), make_float4(0, 0, 0, 0));
   m->wtris.assign(3 * GVT_LEAF_MAX * (size_t)std::max(1u, nf), make_float4(0, 0, 0, 0));
@@ -237,6 +256,48 @@ EM_API void emul_intersect(void *p, const void *rays, size_t n, int any, void *h
     h[i].prim = hit.prim, h[i].t = hit.prim >= 0 ? hit.t : FLT_MAX, h[i].u = hit.u, h[i].v = hit.v;
   }
   if (counts) counts[0] += cn, counts[1] += ct;
+}
+
+// BVH-quality statistics (tools/bvh_eval.py): node visits split into bottom nodes (no internal child) and inner nodes,
+// and a histogram of children per wide node.  out[0] inner visits, out[1] bottom visits, out[2] triangles tested
+EM_API void emul_visit_stats(void *p, const void *rays, size_t n, int any, uint64_t *out) {
+  EmulMesh *m = (EmulMesh *)p;
+  const Ray80 *r = (const Ray80 *)rays;
+  for (size_t i = 0; i < n; ++i) {
+    V3 o = v3(r[i].o[0], r[i].o[1], r[i].o[2]), d = v3(r[i].d[0], r[i].d[1], r[i].d[2]);
+    RayLocal rl;
+    ray_local(rl, o, d);
+    Trav tv;
+    trav_begin(tv, m->blas.n_tris, FLT_MAX);
+    LocalStack stack;
+    TravCounters tc;
+    tc.nodes = tc.tris = 0;
+    bool more = trav_has_nodes(tv);
+    while (more) {
+      if (trav_has_nodes(tv)) {
+        node_step<true, false>(m->blas.nodes, rl, GVT_RAY_EPSILON, tv, stack, &tc);
+        out[(tv.ng.y & 0xFFu) ? 0 : 1]++;
+      }
+      bool done = false;
+      while (trav_has_tris(tv) && !done) done = tri_step<true>(m->blas.tris, rl, GVT_RAY_EPSILON, FLT_MAX, any != 0, tv, &tc);
+      if (done) break;
+      more = trav_next(tv, stack);
+    }
+    out[2] += tc.tris;
+  }
+}
+// hist[k] = wide nodes with k children (k = 0..8); hist[9 + k] = leaf slots with k triangles (k = 1..3); hist[13] = bottom nodes
+EM_API void emul_node_hist(void *p, uint64_t *hist) {
+  EmulMesh *m = (EmulMesh *)p;
+  for (unsigned i = 0; i < m->n_wnodes; ++i) {
+    const uint4 *nd = reinterpret_cast<const uint4 *>(m->wnodes.data()) + GVT_NODE_WORDS * (size_t)i;
+    uint32_t imask = nd[0].w >> 24, tmask = nd[1].z;
+    int k = popc32(imask) + popc32(tmask & 0xFFu);
+    hist[k]++;
+    if (!imask) hist[13]++;
+    for (int s = 0; s < 8; ++s)
+      if ((tmask >> s) & 1u) hist[9 + ((tmask >> (8 + s)) & 1u) + ((tmask >> (16 + s)) & 1u) + 1]++;
+  }
 }
 
 // camera rays through the product's camera_ray body
