@@ -456,7 +456,9 @@ __global__ void k_route(FrameParams fp, SceneDev sd, RayQueue in, unsigned n, in
 // DomainScheduler: a ray routed to an instance owned by another rank is parked in `exq` (inst column = instance).
 // ---------------------------------------------------------------------------------------------------------
 #define TRACE_THREADS 128
+#ifndef TRACE_SM_STACK
 #define TRACE_SM_STACK 12
+#endif
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 6 /* CTAs per SM the register allocation is bounded for */
 #endif

@@ -259,7 +259,8 @@ EM_API void emul_intersect(void *p, const void *rays, size_t n, int any, void *h
 }
 
 // BVH-quality statistics (tools/bvh_eval.py): node visits split into bottom nodes (no internal child) and inner nodes,
-// and a histogram of children per wide node.  out[0] inner visits, out[1] bottom visits, out[2] triangles tested
+// and a histogram of children per wide node.  out[0] inner visits, out[1] bottom visits, out[2] triangles tested,
+// out[3..6] visits to the first 9 / 73 / 200 / 585 nodes (the top levels: nodes are numbered level by level)
 EM_API void emul_visit_stats(void *p, const void *rays, size_t n, int any, uint64_t *out) {
   EmulMesh *m = (EmulMesh *)p;
   const Ray80 *r = (const Ray80 *)rays;
@@ -275,6 +276,12 @@ EM_API void emul_visit_stats(void *p, const void *rays, size_t n, int any, uint6
     bool more = trav_has_nodes(tv);
     while (more) {
       if (trav_has_nodes(tv)) {
+        { // index of the node about to be visited (what node_step computes): visits to the first K nodes -> out[3..6]
+          const uint32_t hits8 = tv.ng.y >> 24, imask = tv.ng.y & 0xFFu, sl = best_slot(hits8, rl.octinv);
+          const uint32_t ni = tv.ng.x + (uint32_t)popc32(imask & ((1u << sl) - 1u));
+          const uint32_t K[4] = { 9u, 73u, 200u, 585u };
+          for (int q = 0; q < 4; ++q) out[3 + q] += ni < K[q] ? 1u : 0u;
+        }
         node_step<true, false>(m->blas.nodes, rl, GVT_RAY_EPSILON, tv, stack, &tc);
         out[(tv.ng.y & 0xFFu) ? 0 : 1]++;
       }

@@ -72,12 +72,13 @@ def main():
           f"triangles per leaf slot 1..3: {hist[10:13].tolist()}")
     total = 0.0
     for nm, rays, any_ in sets:
-        out = np.zeros(3, np.uint64)
+        out = np.zeros(8, np.uint64)
         E.emul_visit_stats(h, po._fp(rays), len(rays), any_, po._fp(out))
-        inner, bottom, tt = (float(x) / len(rays) for x in out)
+        inner, bottom, tt = (float(x) / len(rays) for x in out[:3])
+        top = [float(x) / max(1.0, float(out[0] + out[1])) for x in out[3:7]]
         cost = 8 * (inner + bottom) + 3 * tt
         total += cost
-        print(f"  {nm:12s}: {inner + bottom:6.2f} nodes ({inner:5.2f} inner + {bottom:5.2f} bottom), {tt:5.2f} triangles, L1 wavefronts {cost:6.1f}")
+        print(f"  {nm:12s}: {inner + bottom:6.2f} nodes ({inner:5.2f} inner + {bottom:5.2f} bottom), {tt:5.2f} triangles, L1 wavefronts {cost:6.1f}; visits to the first 9/73/200/585 nodes: " + "/".join(f"{100 * x:.0f}%" for x in top))
     print(f"  total wavefronts per ray triple: {total:6.1f}")
     E.emul_destroy(h)
 
