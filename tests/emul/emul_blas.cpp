@@ -23,7 +23,7 @@ struct EmulMesh {
   std::vector<int2> bn_child, bn_range;
   std::vector<int> bn_parent;
   std::vector<float4> wnodes, wtris;
-  unsigned n_wnodes = 0, n_wtris = 0, depth = 0;
+  unsigned n_wnodes = 0, n_wtris = 0, depth = 0, bdepth = 0;
   Blas blas;
 };
 
@@ -208,6 +208,18 @@ EM_API void *emul_build(const float *verts, unsigned nv, const uint32_t *faces, 
     }
   }
   m->n_wnodes = node_count, m->n_wtris = tri_count;
+  if (nf > 1) { // depth of the binary tree = levels of the level-synchronous device build
+    std::vector<std::pair<int, int>> st2;
+    st2.push_back({ 0, 1 });
+    while (!st2.empty()) {
+      auto [b, dep] = st2.back();
+      st2.pop_back();
+      m->bdepth = std::max(m->bdepth, (unsigned)dep);
+      int2 ch = c.bn_child[b];
+      if (ch.x < (int)nf - 1) st2.push_back({ ch.x, dep + 1 });
+      if (ch.y < (int)nf - 1) st2.push_back({ ch.y, dep + 1 });
+    }
+  }
   memset(&m->blas, 0, sizeof(Blas));
   m->blas.nodes = m->wnodes.data();
   m->blas.tris = m->wtris.data();
@@ -223,7 +235,7 @@ EM_API void emul_morton(void *p, uint32_t *codes, uint32_t *sorted_faces) {
 }
 EM_API void emul_stats(void *p, uint64_t *st) {
   EmulMesh *m = (EmulMesh *)p;
-  st[0] = m->n_wnodes, st[1] = m->n_wtris, st[2] = m->depth, st[3] = 0;
+  st[0] = m->n_wnodes, st[1] = m->n_wtris, st[2] = m->depth, st[3] = m->bdepth;
 }
 struct Ray80 {
   float o[3], t_min, d[3], t_max, color[3], t;

@@ -68,7 +68,7 @@ def main():
     E.emul_stats(h, po._fp(st))
     hist = np.zeros(14, np.uint64)
     E.emul_node_hist(h, po._fp(hist))
-    print(f"wide nodes {int(st[0])} (bottom {int(hist[13])}), triangle refs {int(st[1])}, depth {int(st[2])}; children per node 0..8: {hist[:9].tolist()}; "
+    print(f"wide nodes {int(st[0])} (bottom {int(hist[13])}), triangle refs {int(st[1])}, depth {int(st[2])} (binary tree {int(st[3])} levels); children per node 0..8: {hist[:9].tolist()}; "
           f"triangles per leaf slot 1..3: {hist[10:13].tolist()}")
     total = 0.0
     for nm, rays, any_ in sets:
