@@ -58,7 +58,8 @@ C_ABI_SYMBOLS = (
     "gvtb200_render_frame_tiles gvtb200_scene_set_stream gvtb200_launch_count gvtb200_scene_sync gvtb200_scene_counters gvtb200_scene_profile_counters gvtb200_scene_profile_launches gvtb200_scene_launch_records gvtb200_scene_device_framebuffer "
     "gvtb200_framebuffer_clamp gvtb200_scene_last_timing gvtb200_domain_set_owner gvtb200_domain_begin_frame "
     "gvtb200_domain_drain_local gvtb200_domain_export gvtb200_domain_import gvtb200_domain_pending "
-    "gvtb200_p2p_export gvtb200_p2p_attach gvtb200_p2p_detach gvtb200_image_frame_p2p gvtb200_domain_round_p2p gvtb200_domain_composite_p2p"
+    "gvtb200_p2p_export gvtb200_p2p_attach gvtb200_p2p_detach gvtb200_image_frame_p2p gvtb200_domain_round_p2p gvtb200_domain_composite_p2p "
+    "gvtb200_domain_async_reset gvtb200_domain_async_step"
 ).split()
 PEER_DESC_BYTES = 64 * 4 + 8 * 4 + 8 + 8 + 4 + 4  # sizeof(gvtb200_peer_desc)
 
@@ -137,6 +138,8 @@ def lib():
         L.gvtb200_image_frame_p2p.argtypes = [vp, i32, i32, i32, i32, i32]
         L.gvtb200_domain_round_p2p.argtypes = [vp, i32, vp]
         L.gvtb200_domain_composite_p2p.argtypes = [vp, i32]
+        L.gvtb200_domain_async_reset.argtypes = [vp]
+        L.gvtb200_domain_async_step.argtypes = [vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -500,6 +503,15 @@ class EngineScene:
         p = C.c_void_p()
         check(lib().gvtb200_domain_round_p2p(self.h, rnd, C.byref(p)))
         return p.value
+
+    def domain_async_reset(self):
+        check(lib().gvtb200_domain_async_reset(self.h))
+
+    def domain_async_step(self):
+        """One non-blocking step of the asynchronous DomainScheduler: (busy, sent, received)."""
+        b, s_, r = C.c_int(0), C.c_uint64(0), C.c_uint64(0)
+        check(lib().gvtb200_domain_async_step(self.h, C.byref(b), C.byref(s_), C.byref(r)))
+        return bool(b.value), int(s_.value), int(r.value)
 
     def domain_composite_p2p(self, root=0):
         check(lib().gvtb200_domain_composite_p2p(self.h, root))

@@ -208,6 +208,13 @@ struct gvtb200_scene_s {
     QueueMem inbox[2];           // inbound ray queues, alternated by exchange rounds
     Mailbox *d_mail = nullptr;
     RayQueue *d_peer_inbox = nullptr; // [2][world]
+    // asynchronous DomainScheduler: the two inbound slabs are carved into one region per producer
+    unsigned *d_out_count = nullptr;  // [GVT_P2P_MAX] rays this rank has stored into its region at each peer (this frame)
+    RayQueue *d_async_peer = nullptr; // [world] this rank's region in rank r's inbound area; .count -> d_out_count[r]
+    RayQueue *d_async_mine = nullptr; // [world] rank p's region in this rank's inbound area
+    unsigned async_head[GVT_P2P_MAX] = {}; // rays consumed per producer (this frame)
+    unsigned async_region_cap = 0;
+    bool async_first = false;
     float *peer_fb[GVT_P2P_MAX] = {};
     PeerMail mail;
     void *opened[GVT_P2P_MAX][4] = {}; // cudaIpcOpenMemHandle results (closed on detach)
@@ -1534,6 +1541,18 @@ static RayQueue queue_at(void *slab, size_t cap) { // the layout QueueMem::ensur
   q.cap = (unsigned)cap;
   return q;
 }
+// asynchronous DomainScheduler: region r of an inbound area (two slabs of `cap` rays each): regions alternate between the
+// slabs, (world + 1) / 2 per slab, each laid out like a queue of its own
+static unsigned async_region_cap(size_t cap, int world) {
+  const size_t per_slab = ((size_t)world + 1) / 2, bytes = (cap * 68 / per_slab) / 256 * 256;
+  if (bytes < 256 + 68 * 32) return 0;
+  return (unsigned)((bytes - 256) / 68 / 32 * 32);
+}
+static RayQueue async_region(void *slab0, void *slab1, size_t cap, int world, int r) {
+  const size_t per_slab = ((size_t)world + 1) / 2, bytes = (cap * 68 / per_slab) / 256 * 256;
+  char *base = (char *)((r & 1) ? slab1 : slab0) + 256 + (size_t)(r >> 1) * bytes;
+  return queue_at(base, async_region_cap(cap, world));
+}
 int gvtb200_p2p_export(gvtb200_scene s, int world, gvtb200_peer_desc *out) {
   NEED_SCENE();
   if (!out) return fail(GVTB200_ERR_INVALID, "out is NULL");
@@ -1571,7 +1590,9 @@ int gvtb200_p2p_attach(gvtb200_scene s, int rank, int world, const gvtb200_peer_
   if (world < 1 || world > GVT_P2P_MAX || rank < 0 || rank >= world) return fail(GVTB200_ERR_INVALID, "bad rank/world %d/%d", rank, world);
   if (s->world > 1 && (s->world != world || s->rank != rank)) return fail(GVTB200_ERR_INVALID, "rank/world differ from gvtb200_domain_set_owner (%d/%d)", s->rank, s->world);
   if (s->p2p.attached) return fail(GVTB200_ERR_INVALID, "already attached");
-  std::vector<RayQueue> table(2 * (size_t)world);
+  std::vector<RayQueue> table(2 * (size_t)world), async_peer((size_t)world), async_mine((size_t)world);
+  if (!s->p2p.d_out_count) CU(dalloc(&s->p2p.d_out_count, GVT_P2P_MAX));
+  CU(cudaMemset(s->p2p.d_out_count, 0, GVT_P2P_MAX * sizeof(unsigned)));
   for (int r = 0; r < world; ++r) {
     const gvtb200_peer_desc &d = all[r];
     if (d.fb_pix != s->fb_pix) return fail(GVTB200_ERR_INVALID, "rank %d renders a different film (%llu vs %zu pixels)", r, (unsigned long long)d.fb_pix, s->fb_pix);
@@ -1598,11 +1619,20 @@ int gvtb200_p2p_attach(gvtb200_scene s, int rank, int world, const gvtb200_peer_
     }
     s->p2p.peer_fb[r] = (float *)ptrs[0];
     table[r] = queue_at(ptrs[1], d.inbox_cap), table[(size_t)world + r] = queue_at(ptrs[2], d.inbox_cap);
+    async_peer[r] = async_region(ptrs[1], ptrs[2], d.inbox_cap, world, rank); // where this rank writes at rank r
+    async_peer[r].count = s->p2p.d_out_count + r;                                // reserved with a local atomic
+    async_mine[r] = async_region(s->p2p.inbox[0].slab, s->p2p.inbox[1].slab, s->p2p.inbox[0].q.cap, world, r);
     s->p2p.mail.m[r] = (Mailbox *)ptrs[3];
   }
   dfree(s->p2p.d_peer_inbox);
   CU(dalloc(&s->p2p.d_peer_inbox, table.size()));
   CU(cudaMemcpy(s->p2p.d_peer_inbox, table.data(), table.size() * sizeof(RayQueue), cudaMemcpyHostToDevice));
+  dfree(s->p2p.d_async_peer), dfree(s->p2p.d_async_mine);
+  CU(dalloc(&s->p2p.d_async_peer, (size_t)world));
+  CU(dalloc(&s->p2p.d_async_mine, (size_t)world));
+  CU(cudaMemcpy(s->p2p.d_async_peer, async_peer.data(), (size_t)world * sizeof(RayQueue), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(s->p2p.d_async_mine, async_mine.data(), (size_t)world * sizeof(RayQueue), cudaMemcpyHostToDevice));
+  s->p2p.async_region_cap = async_region_cap(s->p2p.inbox[0].q.cap, world);
   s->p2p.rank = rank, s->p2p.world = world, s->p2p.seq = 0, s->p2p.attached = true;
   return GVTB200_OK;
 }
@@ -1614,7 +1644,7 @@ int gvtb200_p2p_detach(gvtb200_scene s) {
       if (p) cudaIpcCloseMemHandle(p);
       p = nullptr;
     }
-  dfree(s->p2p.d_peer_inbox), dfree(s->p2p.d_mail);
+  dfree(s->p2p.d_peer_inbox), dfree(s->p2p.d_mail), dfree(s->p2p.d_out_count), dfree(s->p2p.d_async_peer), dfree(s->p2p.d_async_mine);
   s->p2p.inbox[0].release(), s->p2p.inbox[1].release();
   s->p2p.exported = s->p2p.attached = false;
   return GVTB200_OK;
@@ -1644,6 +1674,79 @@ int gvtb200_domain_round_p2p(gvtb200_scene s, int round, void **d_exported_total
   if (round > 0) CU(cudaMemsetAsync(s->p2p.inbox[(round - 1) & 1].q.count, 0, 4, s->stream));
   CU(cudaGetLastError());
   if (d_exported_total) *d_exported_total = (void *)&s->d_ctr->rays_exported;
+  return GVTB200_OK;
+}
+int gvtb200_domain_async_reset(gvtb200_scene s) {
+  NEED_SCENE();
+  if (!s->p2p.attached || s->world < 2) return fail(GVTB200_ERR_INVALID, "needs gvtb200_domain_set_owner with world > 1 and gvtb200_p2p_attach");
+  if (!s->p2p.async_region_cap) return fail(GVTB200_ERR_CAPACITY, "film too small for %d inbound regions", s->p2p.world);
+  cudaStream_t st = s->stream;
+  CU(cudaMemsetAsync(s->p2p.d_out_count, 0, GVT_P2P_MAX * sizeof(unsigned), st));
+  CU(cudaMemsetAsync(s->p2p.d_mail->tail, 0, GVT_P2P_MAX * sizeof(unsigned), st));
+  memset(s->p2p.async_head, 0, sizeof(s->p2p.async_head));
+  s->p2p.async_first = true;
+  // both local queues take whatever can arrive in one step
+  const size_t cap = (size_t)s->p2p.async_region_cap * s->p2p.world, nl = std::max<size_t>(1, s->lights.size());
+  if (cap * nl > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "frame has too many rays for one queue");
+  const size_t frame = (size_t)s->W * s->H * s->samples * s->samples;
+  CU(s->q_a.ensure(std::max(cap, frame)));
+  CU(s->q_b.ensure(std::max(cap, frame)));
+  CU(s->q_sh.ensure(std::max(cap, frame) * nl));
+  CU(s->q_hit.ensure(std::max(cap, frame), true));
+  CU(cudaStreamSynchronize(st)); // the peers may publish into this rank's tails once every rank has returned from here
+  return GVTB200_OK;
+}
+int gvtb200_domain_async_step(gvtb200_scene s, int *busy, uint64_t *sent, uint64_t *received) {
+  NEED_SCENE();
+  if (!busy || !sent || !received) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  if (!s->p2p.attached || s->world < 2) return fail(GVTB200_ERR_INVALID, "needs gvtb200_domain_set_owner with world > 1 and gvtb200_p2p_attach");
+  cudaStream_t st = s->stream;
+  const int P = s->p2p.world, me = s->p2p.rank;
+  *busy = 1, *sent = 0, *received = 0;
+  FrameParams fp;
+  build_frame_params(*s, fp);
+  if (s->p2p.async_first) { // the rays gvtb200_domain_begin_frame kept are waiting in the local queue
+    s->p2p.async_first = false;
+    if (int rc = run_waves(s, fp, std::max(1, s->depth), false, nullptr, nullptr, s->p2p.d_async_peer)) return rc;
+    k_async_publish<<<1, GVT_P2P_MAX, 0, st>>>(s->p2p.mail, s->p2p.d_out_count, P, me);
+    LAUNCHED(1);
+    CU(cudaGetLastError());
+    return GVTB200_OK;
+  }
+  cudaError_t q = cudaStreamQuery(st);
+  if (q == cudaErrorNotReady) return GVTB200_OK; // the previous step is still running
+  CU(q);
+  unsigned tails[GVT_P2P_MAX], outc[GVT_P2P_MAX];
+  CU(cudaMemcpyAsync(tails, s->p2p.d_mail->tail, sizeof(tails), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(outc, s->p2p.d_out_count, sizeof(outc), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  AsyncGather g;
+  memset(&g, 0, sizeof(g));
+  const unsigned cap = s->p2p.async_region_cap;
+  unsigned total = 0;
+  for (int p = 0; p < P; ++p) { // rays beyond a region's capacity were counted by the producer but not stored
+    const unsigned h = std::min(s->p2p.async_head[p], cap), t = p == me ? h : std::min(tails[p], cap);
+    g.head[p] = h, g.prefix[p] = total;
+    total += t - h;
+  }
+  g.prefix[P] = total;
+  bool arrived = false;
+  for (int p = 0; p < P; ++p)
+    if (p != me && tails[p] != s->p2p.async_head[p]) arrived = true, s->p2p.async_head[p] = tails[p];
+  if (arrived) {
+    CU(cudaMemcpyAsync(s->q_a.q.count, &g.prefix[P], 4, cudaMemcpyHostToDevice, st)); // pageable source: staged before the call returns
+    if (total) {
+      k_async_gather<<<std::min<unsigned>(g_sms * 8, blocks_for(total, 256)), 256, 0, st>>>(s->p2p.d_async_mine, g, P, s->q_a.q);
+      LAUNCHED(1);
+      if (int rc = run_waves(s, fp, std::max(1, s->depth), false, nullptr, nullptr, s->p2p.d_async_peer)) return rc;
+      k_async_publish<<<1, GVT_P2P_MAX, 0, st>>>(s->p2p.mail, s->p2p.d_out_count, P, me);
+      LAUNCHED(1);
+    }
+    CU(cudaGetLastError());
+    return GVTB200_OK;
+  }
+  *busy = 0;
+  for (int p = 0; p < P; ++p) *sent += outc[p], *received += s->p2p.async_head[p];
   return GVTB200_OK;
 }
 int gvtb200_domain_composite_p2p(gvtb200_scene s, int root) {

@@ -949,7 +949,10 @@ __global__ void k_import(const uint4 *packed, unsigned n, RayQueue q, unsigned o
 #define GVT_P2P_MAX 16
 struct Mailbox {
   unsigned go, err, cta_done, pad;
-  unsigned done[60];
+  unsigned done[GVT_P2P_MAX];
+  unsigned tail[GVT_P2P_MAX]; // asynchronous DomainScheduler: tail[p] = rays rank p has finished storing into its region of
+                              // this rank's inbound area (cumulative over the frame)
+  unsigned reserved[60 - 2 * GVT_P2P_MAX];
 };
 struct PeerMail {
   Mailbox *m[GVT_P2P_MAX];
@@ -996,6 +999,34 @@ __device__ __forceinline__ void p2p_signal_done(Mailbox *mine, Mailbox *root_mai
     }
   }
 }
+// ---- asynchronous DomainScheduler (reference: tracer/Domain/DomainTracer.cpp:109-192) -------------------
+// Every rank owns one inbound REGION per producer, so a producer reserves slots with an atomic on its own memory and no
+// consumer ever sees a reserved-but-unwritten slot: after the kernels of one step the producer publishes how far it has
+// written (tail), and the consumer only touches rays below the published tail.  No kernel waits for another GPU.
+// thread c < world: tell rank c how many rays this rank has stored into its region there
+__global__ void k_async_publish(PeerMail pm, const unsigned *out_count, int world, int self) {
+  const int c = (int)threadIdx.x;
+  if (c >= world || c == self) return;
+  __threadfence_system(); // the rays were written by earlier kernels of this stream
+  st_release_sys(&pm.m[c]->tail[self], out_count[c]);
+}
+// copies rays [head[p], tail[p]) of every producer's region into `out` (this rank's local queue), region after region
+struct AsyncGather {
+  unsigned head[GVT_P2P_MAX];
+  unsigned prefix[GVT_P2P_MAX + 1]; // prefix[p] = rays of producers < p
+};
+__global__ void k_async_gather(const RayQueue *regions, AsyncGather g, int world, RayQueue out) {
+  const unsigned total = g.prefix[world];
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int p = 0;
+    while (i >= g.prefix[p + 1]) ++p;
+    const RayQueue src = regions[p];
+    const unsigned k = g.head[p] + (i - g.prefix[p]);
+    out.c0[i] = src.c0[k], out.c1[i] = src.c1[k], out.c2[i] = src.c2[k], out.c3[i] = src.c3[k];
+    out.inst[i] = src.inst[k];
+  }
+}
+
 // ImageScheduler: clamp this shard's film rows and store them into dst (the root's framebuffer; dst == src on the root)
 __global__ void k_rows_to_root(const float4 *src, float4 *dst, RowTiles tiles, int W, Mailbox *mine, Mailbox *root_mail, int rank, unsigned seq) {
   const size_t n = tiles_local_rows(tiles) * (size_t)W;

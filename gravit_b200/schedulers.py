@@ -129,6 +129,47 @@ def render_domain_schedule_p2p(engine, dist, rank, world, max_rounds=10000, root
     return log
 
 
+class AsyncTermination:
+    """Termination rule of the asynchronous DomainScheduler (Mattern's four-counter method; stands in for the two-phase
+    vote of core/comm/vote/vote.cpp).  Feed it the all-reduced (busy, sent, received) of every poll, in order; a poll's
+    values must have been read after the previous poll's all-reduce ended.  The frame is over when two consecutive polls
+    find no rank busy and the same totals with sent == received: nothing was in flight during the second poll."""
+
+    def __init__(self):
+        self.prev = None
+
+    def update(self, busy, sent, received):
+        quiet = busy == 0 and sent == received
+        done = quiet and self.prev == (sent, received)
+        self.prev = (sent, received) if quiet else None
+        return done
+
+
+def render_domain_schedule_async(engine, dist, rank, world, device, root=0, max_polls=1000000):
+    """One DomainScheduler frame without round barriers (scheduler::AsyncDomain, tracer/Domain/DomainTracer.cpp:109-192)
+    over the NVLink peer path (after p2p_connect).  Every rank free-runs: each poll it asks its engine to trace whatever its
+    peers have published (non-blocking) and joins a 24-byte all-reduce of (busy, sent, received) that only decides
+    termination; no rank waits for another rank's kernels.  The engine must run on its OWN stream (do not point it at torch's
+    current stream: the all-reduce would then queue behind the trace kernels).  Returns the number of polls."""
+    import torch
+
+    engine.domain_async_reset()
+    ready = torch.zeros(1, dtype=torch.int64, device=device)
+    dist.all_reduce(ready)  # every rank has cleared the tails its peers publish into
+    ready.item()
+    engine.domain_begin_frame()
+    term = AsyncTermination()
+    for poll in range(1, max_polls + 1):
+        busy, sent, received = engine.domain_async_step()
+        t = torch.tensor([int(busy), sent, received], dtype=torch.int64, device=device)
+        dist.all_reduce(t)
+        b, s_, r_ = (int(x) for x in t.tolist())
+        if term.update(b, s_, r_):
+            engine.domain_composite_p2p(root)
+            return poll
+    raise RuntimeError(f"asynchronous DomainScheduler: no termination after {max_polls} polls")
+
+
 def render_domain_schedule(engine, dist, rank, world, device, fb_tensor, max_rounds=10000):
     """One DomainScheduler frame (DomainTracer.h:185-368).  Returns per-round [sent-to-peer] count matrices rows."""
     import torch

@@ -271,6 +271,22 @@ GVTB200_API int gvtb200_image_frame_p2p(gvtb200_scene scene, int row0, int row1,
  * (may be NULL) receives the DEVICE address of the frame's cumulative exported-ray counter (uint64) for the termination
  * all-reduce: the frame is over when the sum over ranks did not grow during a round. */
 GVTB200_API int gvtb200_domain_round_p2p(gvtb200_scene scene, int round, void **d_exported_total);
+/* Asynchronous DomainScheduler (scheduler::AsyncDomain, Types.h:53-54; the loop of tracer/Domain/DomainTracer.cpp:109-192
+ * with SendRayList messages replaced by stores over NVLink and the two-phase vote of core/comm/vote/vote.cpp replaced by
+ * sent/received counters).  No round barrier: a rank traces whatever has arrived whenever its stream is idle.
+ *   gvtb200_domain_async_reset   once per frame, BEFORE a host barrier across the ranks: clears this rank's counters
+ *                                and the tails its peers publish into.
+ *   gvtb200_domain_begin_frame   (as for the round-synchronous schedule) camera rays, first routing.
+ *   gvtb200_domain_async_step    non-blocking.  If the previous step's kernels are still running: *busy = 1.  Else, if
+ *                                peers have published rays this rank has not consumed: gathers them, traces them (rays for
+ *                                other ranks go straight into this rank's region of the owner's inbound area), publishes
+ *                                its own tails; *busy = 1.  Else *busy = 0 and *sent / *received are this rank's cumulative
+ *                                ray counts.  The frame is over when two consecutive polls of ALL ranks (the second one
+ *                                started after the first one ended) find every rank idle with equal, unchanged totals
+ *                                sum(sent) == sum(received) (Mattern's four-counter rule).
+ *   gvtb200_domain_composite_p2p as for the round-synchronous schedule. */
+GVTB200_API int gvtb200_domain_async_reset(gvtb200_scene scene);
+GVTB200_API int gvtb200_domain_async_step(gvtb200_scene scene, int *busy, uint64_t *sent, uint64_t *received);
 /* end of a DomainScheduler frame: every rank adds the pixels it touched to the root's framebuffer; the root waits for all
  * of them, then clamps (IceTComposite::localAdd's clamp, composite/IceTComposite.cpp:113-114). */
 GVTB200_API int gvtb200_domain_composite_p2p(gvtb200_scene scene, int root);

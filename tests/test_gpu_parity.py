@@ -444,6 +444,51 @@ def test_domain_scheduler_peer_exchange(gpu, world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world,scene", [(2, "simple"), (3, "simple"), (4, "gyroid")])
+def test_domain_scheduler_async_peer(gpu, world, scene):
+    """scheduler::AsyncDomain (SURVEY 8(f) N3; tracer/Domain/DomainTracer.cpp:109-192): no exchange rounds -- every rank
+    traces whatever its peers have published whenever it is idle, termination by sent/received counters.  The rays that
+    change rank are the same rays as in the round-synchronous schedule (same total as the oracle's routing log), the
+    composited image equals the single-process image."""
+    from gravit_b200 import schedulers
+
+    d = library.simple_scene(256, 256) if scene == "simple" else library.gyroid_scene(48, 2, 320, 240)
+    flags = 1 if scene == "simple" else d.flags
+    o = oracle_scene(d, flags)
+    o.set_owner(np.arange(len(d.instances)) % world)
+    ref, st = o.render(schedule=1, world_size=world, threads=8)
+    exchanged_o = int(sum(m.sum() for m in o.route_log(world)))
+    ref1, _ = o.render(schedule=0, world_size=1, threads=8)
+    ranks, owner = _standalone_ranks(gpu, d, flags, world)
+    _connect(ranks)
+    for frame in range(2):  # twice: regions, tails and counters must be reusable
+        for e in ranks:
+            e.domain_async_reset()
+        for e in ranks:
+            e.domain_begin_frame()
+        term = schedulers.AsyncTermination()
+        polls = 0
+        while True:
+            res = [e.domain_async_step() for e in ranks]
+            polls += 1
+            assert polls < 200000
+            if term.update(sum(int(r[0]) for r in res), sum(r[1] for r in res), sum(r[2] for r in res)):
+                break
+        assert sum(r[1] for r in res) == exchanged_o and exchanged_o > 0
+        assert sum(e.counters()["rays_exported"] for e in ranks) == exchanged_o
+        assert all(e.counters()["queue_overflows"] == 0 for e in ranks)
+        for e in ranks[1:] + ranks[:1]:  # peers add their pixels, the root waits and clamps
+            e.domain_composite_p2p(0)
+        for e in ranks:
+            e.sync()
+        fb = ranks[0].fb_read(d.width, d.height)
+        assert np.allclose(fb, ref, atol=1e-6) and np.allclose(fb, ref1, atol=1e-6)
+        assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref1)) >= 50.0
+    for e in ranks:
+        e.close()
+
+
+@pytest.mark.gpu
 def test_conf_file_scene_end_to_end(gpu, tmp_path):
     """a data/*.conf style scene file (OBJ + MTL, two instances of one mesh, point light) loaded by the C++
     ConfigFileLoader / ObjReader, rendered through api::render, equals the oracle fed with the same arrays; writeimage

@@ -93,3 +93,102 @@ def test_exchange_and_termination_world2():
         assert p.exitcode == 0
     assert res[0][1] == res[1][1] == 2  # both ranks agree on the number of exchange rounds
     assert res[0][2] + res[1][2] > 0
+
+
+def test_async_termination_rule():
+    t = schedulers.AsyncTermination()
+    assert not t.update(1, 0, 0)       # somebody is busy
+    assert not t.update(0, 10, 7)      # rays in flight
+    assert not t.update(0, 10, 10)     # first quiet poll
+    assert not t.update(0, 12, 12)     # totals moved between the polls: something was in flight after all
+    assert not t.update(1, 0, 0)
+    assert not t.update(0, 12, 12)
+    assert t.update(0, 12, 12)         # second consecutive quiet poll with the same totals
+
+
+class _ScriptedEngine:
+    """Stands in for the engine in render_domain_schedule_async: two ranks pass 'rays' through a shared directory (one file
+    per published tail), so sent/received follow the real protocol: a rank is busy while it 'traces' for two polls after
+    new rays arrived, and forwards a shrinking share of them to its peer."""
+
+    def __init__(self, rank, world, root):
+        self.rank, self.world, self.root = rank, world, root
+        self.sent = self.received = 0
+        self.work = 0  # polls of tracing left
+        self.pending_out = 0
+        self.first = True
+        self.composited = False
+
+    def _tail_path(self, src, dst):
+        return os.path.join(self.root, f"tail_{src}_{dst}")
+
+    def _publish(self):
+        for dst in range(self.world):
+            if dst != self.rank:
+                tmp = self._tail_path(self.rank, dst) + ".tmp"
+                with open(tmp, "w") as f:
+                    f.write(str(self.sent))
+                os.replace(tmp, self._tail_path(self.rank, dst))
+
+    def domain_async_reset(self):
+        self._publish()
+
+    def domain_begin_frame(self):
+        pass
+
+    def domain_async_step(self):
+        if self.first:  # the camera rays this rank kept: rank r forwards 8 + 4 r rays
+            self.first = False
+            self.work, self.pending_out = 2, 8 + 4 * self.rank
+            return True, 0, 0
+        if self.work:
+            self.work -= 1
+            if self.work == 0:
+                self.sent += self.pending_out
+                self._publish()
+            return True, 0, 0
+        tails = 0
+        for src in range(self.world):
+            if src != self.rank:
+                try:
+                    tails += int(open(self._tail_path(src, self.rank)).read())
+                except (FileNotFoundError, ValueError):
+                    pass
+        if tails > self.received:
+            new = tails - self.received
+            self.received = tails
+            self.work, self.pending_out = 2, new // 2  # half of what arrives moves on
+            return True, 0, 0
+        return False, self.sent, self.received
+
+    def domain_composite_p2p(self, root):
+        self.composited = True
+
+
+def _async_worker(rank, world, port, root, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        e = _ScriptedEngine(rank, world, root)
+        polls = schedulers.render_domain_schedule_async(e, dist, rank, world, "cpu")
+        out.put((rank, polls, e.sent, e.received, e.composited))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_async_domain_schedule_world2(tmp_path):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_async_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1]                      # both ranks stop at the same poll
+    assert all(r[4] for r in res)                      # and composite
+    assert res[0][2] == res[1][3] and res[1][2] == res[0][3]  # everything that was sent was received: nothing was cut off
+    assert res[0][2] >= 8 and res[1][2] >= 12
