@@ -225,6 +225,8 @@ def main():
     ap.add_argument("--owner", default="mod", choices=["mod", "balanced"], help="gyroid: brick k on rank k mod N (the reference's map) or the view-balanced placement")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1, ImageScheduler workloads: weak = the film grows by sqrt(N) per axis so every rank keeps the N = 1 "
                     "ray count (same scene, camera and aspect); strong = the N = 1 film split over the ranks")
+    ap.add_argument("--domain-schedule", default="async", choices=["async", "rounds"], help="gyroid, N > 1, peer path: free-running ranks with counter termination (scheduler::AsyncDomain) or "
+                    "exchange rounds ended by an all-reduce (Tracer<DomainScheduler>); the other one is timed as well and reported in config")
     ap.add_argument("--gyroid-res", type=int, default=library.GYROID_RES_100M, help="grid cells per axis of the gyroid volume (946 = 100 M triangles)")
     a = ap.parse_args()
     a.warmup = max(3, a.warmup)
@@ -325,12 +327,18 @@ def main():
     if p2p:
         schedulers.p2p_connect(e, dist, rank, world, dev)
     rounds = [0]
+    board = schedulers.AsyncBoard.connect(dist, rank, world) if (domain and p2p) else None  # control plane of the asynchronous schedule
+    use_async = [a.domain_schedule == "async"]
+    frame_no = [0]
 
     def step():
         if not domain:
             schedulers.render_image_schedule(e, W, H, dist if world > 1 else None, rank, world, a.tile_rows, fb_t, p2p=p2p)
         elif world == 1:
             e.render_async(H)  # one rank owns every brick: Tracer<DomainScheduler> degenerates to the local drain loop
+        elif p2p and use_async[0]:
+            frame_no[0] += 1
+            rounds[0] = schedulers.render_domain_schedule_async(e, board, rank, world, frame_no[0])
         elif p2p:
             rounds[0] = len(schedulers.render_domain_schedule_p2p(e, dist, rank, world))
         else:
@@ -381,6 +389,27 @@ def main():
     total_ms = float(ms_t.item())
     ms_per_step = total_ms / a.steps
     value = rays_frame / (ms_per_step * 1e-3) / 1e6
+    polls_main = rounds[0]
+
+    other_sched = None
+    if domain and p2p:  # the other DomainScheduler schedule on the same scene, same protocol (reported beside the headline)
+        use_async[0] = not use_async[0]
+        for _ in range(2):
+            step()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        dist.barrier()
+        torch.cuda.synchronize()
+        for i in range(a.steps):
+            flush.fill_(i & 0xFF)
+            ev2[i][0].record()
+            step()
+            ev2[i][1].record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        o_t = torch.tensor([sum(x.elapsed_time(y) for x, y in ev2)], dtype=torch.float64, device=dev)
+        dist.all_reduce(o_t, op=dist.ReduceOp.MAX)
+        other_sched = {"schedule": "async" if use_async[0] else "rounds", "ms_per_step": float(o_t.item()) / a.steps, "rounds_or_polls": rounds[0]}
+        use_async[0] = not use_async[0]
 
     # ---- end to end through the public frame call, host buffers (N = 1: gvtb200_render_frame; N > 1: + gather) ----
     host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
@@ -491,8 +520,17 @@ def main():
                         extra[name] = {"error": str(ex)}
         if domain:
             wl = dict(wl, name=f"gyroid isosurface {d.n_tris:,} tris in 2x2x2 bricks (res {a.gyroid_res}), 3840x2160, 1 point light, primary+shadow (configs[3])")
-            sched_desc = "DomainScheduler" + (f", {world} ranks, brick -> rank {d.owner}, " + ("rays stored into the owner's queue over NVLink (CUDA IPC) by the trace kernel, "
-                         f"8-byte all-reduce per round, {rounds[0]} rounds, framebuffer accumulated into rank 0 over NVLink" if p2p else f"NCCL all-to-all of 80-byte ray records, {rounds[0]} rounds, NCCL reduce") if world > 1 else ", 1 rank owns all bricks")
+            if world == 1:
+                sched_desc = "DomainScheduler, 1 rank owns all bricks"
+            elif not p2p:
+                sched_desc = f"DomainScheduler, {world} ranks, brick -> rank {d.owner}, NCCL all-to-all of 80-byte ray records, {polls_main} rounds, NCCL reduce"
+            elif a.domain_schedule == "async":
+                sched_desc = (f"asynchronous DomainScheduler (scheduler::AsyncDomain), {world} ranks, brick -> rank {d.owner}, rays stored into the owner's inbound region over NVLink "
+                              f"(CUDA IPC) by the trace kernel, no exchange rounds: free-running ranks, sent/received counters on a shared-memory board for termination ({polls_main} polls on rank 0), "
+                              "framebuffer accumulated into rank 0 over NVLink")
+            else:
+                sched_desc = (f"DomainScheduler, {world} ranks, brick -> rank {d.owner}, rays stored into the owner's queue over NVLink (CUDA IPC) by the trace kernel, "
+                              f"8-byte all-reduce per round, {polls_main} rounds, framebuffer accumulated into rank 0 over NVLink")
         else:
             sched_desc = "ImageScheduler" + (f", {world} ranks, row tiles of {a.tile_rows} dealt round-robin, " + ("rows stored into rank 0's framebuffer over NVLink (CUDA IPC), no collective" if p2p else "NCCL reduce to rank 0") if world > 1 else "")
         out = {
@@ -511,6 +549,8 @@ def main():
         }
         if domain:
             out["config"]["scene_build_s"] = round(build_s[0], 2)
+        if other_sched:
+            out["config"]["other_schedule"] = other_sched
         if roof:
             out["roofline"] = roof
         if cpu:

@@ -215,6 +215,8 @@ struct gvtb200_scene_s {
     unsigned async_head[GVT_P2P_MAX] = {}; // rays consumed per producer (this frame)
     unsigned async_region_cap = 0;
     bool async_first = false;
+    QueueMem q_local;                 // the camera rays this rank kept (gvtb200_domain_begin_frame), consumed in slices
+    unsigned local_total = 0, local_done = 0, async_chunk = 262144;
     float *peer_fb[GVT_P2P_MAX] = {};
     PeerMail mail;
     void *opened[GVT_P2P_MAX][4] = {}; // cudaIpcOpenMemHandle results (closed on detach)
@@ -1590,7 +1592,7 @@ int gvtb200_p2p_attach(gvtb200_scene s, int rank, int world, const gvtb200_peer_
   if (world < 1 || world > GVT_P2P_MAX || rank < 0 || rank >= world) return fail(GVTB200_ERR_INVALID, "bad rank/world %d/%d", rank, world);
   if (s->world > 1 && (s->world != world || s->rank != rank)) return fail(GVTB200_ERR_INVALID, "rank/world differ from gvtb200_domain_set_owner (%d/%d)", s->rank, s->world);
   if (s->p2p.attached) return fail(GVTB200_ERR_INVALID, "already attached");
-  std::vector<RayQueue> table(2 * (size_t)world), async_peer((size_t)world), async_mine((size_t)world);
+  std::vector<RayQueue> table(2 * (size_t)world), async_peer((size_t)world), async_mine((size_t)world + 1);
   if (!s->p2p.d_out_count) CU(dalloc(&s->p2p.d_out_count, GVT_P2P_MAX));
   CU(cudaMemset(s->p2p.d_out_count, 0, GVT_P2P_MAX * sizeof(unsigned)));
   for (int r = 0; r < world; ++r) {
@@ -1629,9 +1631,11 @@ int gvtb200_p2p_attach(gvtb200_scene s, int rank, int world, const gvtb200_peer_
   CU(cudaMemcpy(s->p2p.d_peer_inbox, table.data(), table.size() * sizeof(RayQueue), cudaMemcpyHostToDevice));
   dfree(s->p2p.d_async_peer), dfree(s->p2p.d_async_mine);
   CU(dalloc(&s->p2p.d_async_peer, (size_t)world));
-  CU(dalloc(&s->p2p.d_async_mine, (size_t)world));
+  CU(dalloc(&s->p2p.d_async_mine, (size_t)world + 1)); // entry `world`: q_local, set every frame
+  memset(&async_mine[(size_t)world], 0, sizeof(RayQueue));
   CU(cudaMemcpy(s->p2p.d_async_peer, async_peer.data(), (size_t)world * sizeof(RayQueue), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(s->p2p.d_async_mine, async_mine.data(), (size_t)world * sizeof(RayQueue), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(s->p2p.d_async_mine, async_mine.data(), ((size_t)world + 1) * sizeof(RayQueue), cudaMemcpyHostToDevice));
+  if (const char *e = getenv("GVTB200_ASYNC_CHUNK")) s->p2p.async_chunk = (unsigned)std::max(1024, atoi(e));
   s->p2p.async_region_cap = async_region_cap(s->p2p.inbox[0].q.cap, world);
   s->p2p.rank = rank, s->p2p.world = world, s->p2p.seq = 0, s->p2p.attached = true;
   return GVTB200_OK;
@@ -1645,7 +1649,7 @@ int gvtb200_p2p_detach(gvtb200_scene s) {
       p = nullptr;
     }
   dfree(s->p2p.d_peer_inbox), dfree(s->p2p.d_mail), dfree(s->p2p.d_out_count), dfree(s->p2p.d_async_peer), dfree(s->p2p.d_async_mine);
-  s->p2p.inbox[0].release(), s->p2p.inbox[1].release();
+  s->p2p.inbox[0].release(), s->p2p.inbox[1].release(), s->p2p.q_local.release();
   s->p2p.exported = s->p2p.attached = false;
   return GVTB200_OK;
 }
@@ -1689,10 +1693,11 @@ int gvtb200_domain_async_reset(gvtb200_scene s) {
   const size_t cap = (size_t)s->p2p.async_region_cap * s->p2p.world, nl = std::max<size_t>(1, s->lights.size());
   if (cap * nl > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "frame has too many rays for one queue");
   const size_t frame = (size_t)s->W * s->H * s->samples * s->samples;
-  CU(s->q_a.ensure(std::max(cap, frame)));
-  CU(s->q_b.ensure(std::max(cap, frame)));
-  CU(s->q_sh.ensure(std::max(cap, frame) * nl));
-  CU(s->q_hit.ensure(std::max(cap, frame), true));
+  CU(s->q_a.ensure(std::max(cap, frame) + s->p2p.async_chunk));
+  CU(s->p2p.q_local.ensure(std::max(cap, frame) + s->p2p.async_chunk));
+  CU(s->q_b.ensure(std::max(cap, frame) + s->p2p.async_chunk)); // run_waves swaps q_a and q_b after every wave
+  CU(s->q_sh.ensure((std::max(cap, frame) + s->p2p.async_chunk) * nl));
+  CU(s->q_hit.ensure(std::max(cap, frame) + s->p2p.async_chunk, true));
   CU(cudaStreamSynchronize(st)); // the peers may publish into this rank's tails once every rank has returned from here
   return GVTB200_OK;
 }
@@ -1705,17 +1710,19 @@ int gvtb200_domain_async_step(gvtb200_scene s, int *busy, uint64_t *sent, uint64
   *busy = 1, *sent = 0, *received = 0;
   FrameParams fp;
   build_frame_params(*s, fp);
-  if (s->p2p.async_first) { // the rays gvtb200_domain_begin_frame kept are waiting in the local queue
+  if (s->p2p.async_first) { // the camera rays gvtb200_domain_begin_frame kept: set them aside, they are consumed in slices
     s->p2p.async_first = false;
-    if (int rc = run_waves(s, fp, std::max(1, s->depth), false, nullptr, nullptr, s->p2p.d_async_peer)) return rc;
-    k_async_publish<<<1, GVT_P2P_MAX, 0, st>>>(s->p2p.mail, s->p2p.d_out_count, P, me);
-    LAUNCHED(1);
-    CU(cudaGetLastError());
-    return GVTB200_OK;
+    std::swap(s->q_a, s->p2p.q_local);
+    unsigned n_local = 0;
+    CU(cudaMemcpyAsync(&n_local, s->p2p.q_local.q.count, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s->p2p.d_async_mine + P, &s->p2p.q_local.q, sizeof(RayQueue), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    s->p2p.local_total = std::min(n_local, s->p2p.q_local.q.cap), s->p2p.local_done = 0;
+  } else {
+    cudaError_t q = cudaStreamQuery(st);
+    if (q == cudaErrorNotReady) return GVTB200_OK; // the previous step is still running
+    CU(q);
   }
-  cudaError_t q = cudaStreamQuery(st);
-  if (q == cudaErrorNotReady) return GVTB200_OK; // the previous step is still running
-  CU(q);
   unsigned tails[GVT_P2P_MAX], outc[GVT_P2P_MAX];
   CU(cudaMemcpyAsync(tails, s->p2p.d_mail->tail, sizeof(tails), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(outc, s->p2p.d_out_count, sizeof(outc), cudaMemcpyDeviceToHost, st));
@@ -1724,19 +1731,22 @@ int gvtb200_domain_async_step(gvtb200_scene s, int *busy, uint64_t *sent, uint64
   memset(&g, 0, sizeof(g));
   const unsigned cap = s->p2p.async_region_cap;
   unsigned total = 0;
+  bool work = false;
   for (int p = 0; p < P; ++p) { // rays beyond a region's capacity were counted by the producer but not stored
     const unsigned h = std::min(s->p2p.async_head[p], cap), t = p == me ? h : std::min(tails[p], cap);
     g.head[p] = h, g.prefix[p] = total;
     total += t - h;
+    if (p != me && tails[p] != s->p2p.async_head[p]) work = true, s->p2p.async_head[p] = tails[p];
   }
-  g.prefix[P] = total;
-  bool arrived = false;
-  for (int p = 0; p < P; ++p)
-    if (p != me && tails[p] != s->p2p.async_head[p]) arrived = true, s->p2p.async_head[p] = tails[p];
-  if (arrived) {
-    CU(cudaMemcpyAsync(s->q_a.q.count, &g.prefix[P], 4, cudaMemcpyHostToDevice, st)); // pageable source: staged before the call returns
+  const unsigned slice = std::min(s->p2p.async_chunk, s->p2p.local_total - s->p2p.local_done);
+  g.head[P] = s->p2p.local_done, g.prefix[P] = total;
+  total += slice, s->p2p.local_done += slice;
+  g.prefix[P + 1] = total;
+  if (slice) work = true;
+  if (work) {
+    CU(cudaMemcpyAsync(s->q_a.q.count, &total, 4, cudaMemcpyHostToDevice, st)); // pageable source: staged before the call returns
     if (total) {
-      k_async_gather<<<std::min<unsigned>(g_sms * 8, blocks_for(total, 256)), 256, 0, st>>>(s->p2p.d_async_mine, g, P, s->q_a.q);
+      k_async_gather<<<std::min<unsigned>(g_sms * 8, blocks_for(total, 256)), 256, 0, st>>>(s->p2p.d_async_mine, g, P + 1, s->q_a.q);
       LAUNCHED(1);
       if (int rc = run_waves(s, fp, std::max(1, s->depth), false, nullptr, nullptr, s->p2p.d_async_peer)) return rc;
       k_async_publish<<<1, GVT_P2P_MAX, 0, st>>>(s->p2p.mail, s->p2p.d_out_count, P, me);

@@ -1011,12 +1011,14 @@ __global__ void k_async_publish(PeerMail pm, const unsigned *out_count, int worl
   st_release_sys(&pm.m[c]->tail[self], out_count[c]);
 }
 // copies rays [head[p], tail[p]) of every producer's region into `out` (this rank's local queue), region after region
+// source `world` is this rank's own queue of camera rays (handed out in slices, so that what they export reaches the peers
+// while the rest is still waiting)
 struct AsyncGather {
-  unsigned head[GVT_P2P_MAX];
-  unsigned prefix[GVT_P2P_MAX + 1]; // prefix[p] = rays of producers < p
+  unsigned head[GVT_P2P_MAX + 1];
+  unsigned prefix[GVT_P2P_MAX + 2]; // prefix[p] = rays of sources < p
 };
-__global__ void k_async_gather(const RayQueue *regions, AsyncGather g, int world, RayQueue out) {
-  const unsigned total = g.prefix[world];
+__global__ void k_async_gather(const RayQueue *regions, AsyncGather g, int n_src, RayQueue out) {
+  const unsigned total = g.prefix[n_src];
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int p = 0;
     while (i >= g.prefix[p + 1]) ++p;

@@ -145,26 +145,119 @@ class AsyncTermination:
         return done
 
 
-def render_domain_schedule_async(engine, dist, rank, world, device, root=0, max_polls=1000000):
-    """One DomainScheduler frame without round barriers (scheduler::AsyncDomain, tracer/Domain/DomainTracer.cpp:109-192)
-    over the NVLink peer path (after p2p_connect).  Every rank free-runs: each poll it asks its engine to trace whatever its
-    peers have published (non-blocking) and joins a 24-byte all-reduce of (busy, sent, received) that only decides
-    termination; no rank waits for another rank's kernels.  The engine must run on its OWN stream (do not point it at torch's
-    current stream: the all-reduce would then queue behind the trace kernels).  Returns the number of polls."""
-    import torch
+class AsyncBoard:
+    """Control plane of the asynchronous DomainScheduler on one box: a few words per rank in POSIX shared memory (a file under
+    /dev/shm mapped by every rank).  It carries no rays -- those go over NVLink -- only what the reference's vote messages
+    carry (core/comm/vote/vote.cpp): who is idle and how many rays each rank has sent and received.  A collective cannot do
+    this job: an NCCL kernel queues behind a rank's persistent trace kernel (every SM is taken), so one busy rank would stall
+    the polls of all the others.  Words are int64; each rank writes only its own entry (seqlock: the sequence word is odd while
+    the entry is being written), rank 0 alone writes the header."""
 
+    HDR = 8                 # header words: [0] wave (coordinator), [1] frame whose rendering is over (coordinator)
+    ENT = 8                 # entry words: seq, wave_seen, busy, sent, received, frame, ready_frame, -
+
+    def __init__(self, path, rank, world, create):
+        self.path, self.rank, self.world = path, rank, world
+        n = self.HDR + self.ENT * world
+        if create:
+            np.zeros(n, np.int64).tofile(path)
+        self.a = np.memmap(path, dtype=np.int64, mode="r+", shape=(n,))
+        self.wave = 0       # coordinator only: the wave being collected
+        self.term = AsyncTermination()
+
+    @classmethod
+    def connect(cls, dist, rank, world):
+        """Rank 0 creates the board, the others map it (the path travels through torch.distributed)."""
+        import os
+        import tempfile
+
+        box = [None]
+        if rank == 0:
+            root = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+            fd, box[0] = tempfile.mkstemp(prefix="gvtb200_board_", dir=root)
+            os.close(fd)
+            board = cls(box[0], rank, world, True)
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            board = cls(box[0], rank, world, False)
+        if world > 1:
+            dist.barrier()
+        return board
+
+    def close(self):
+        import os
+
+        del self.a
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+    def _e(self, r):
+        return self.HDR + self.ENT * r
+
+    def publish(self, wave_seen, busy, sent, received, frame):
+        a, e = self.a, self._e(self.rank)
+        a[e] += 1  # odd: being written
+        a[e + 1], a[e + 2], a[e + 3], a[e + 4], a[e + 5] = wave_seen, int(busy), sent, received, frame
+        a[e] += 1
+
+    def read(self, r):
+        a, e = self.a, self._e(r)
+        while True:
+            s1 = int(a[e])
+            v = [int(x) for x in a[e + 1:e + 6]]
+            if not (s1 & 1) and int(a[e]) == s1:
+                return v
+
+    def frame_barrier(self, frame, spin=None):
+        """Every rank has finished gvtb200_domain_async_reset for `frame` (nobody publishes tails into a rank that has not
+        cleared them yet)."""
+        self.a[self._e(self.rank) + 6] = frame
+        while any(int(self.a[self._e(r) + 6]) < frame for r in range(self.world)):
+            if spin:
+                spin()
+
+    def current_wave(self):
+        return int(self.a[0])
+
+    def finished(self, frame):
+        return int(self.a[1]) >= frame
+
+    def coordinate(self, frame):
+        """Rank 0, once per poll: when every rank has published a snapshot taken after the current wave started, apply the
+        four-counter rule to the wave and start the next one."""
+        ents = [self.read(r) for r in range(self.world)]
+        if any(e[4] != frame or e[0] != self.wave for e in ents):
+            return
+        if self.term.update(sum(e[1] for e in ents), sum(e[2] for e in ents), sum(e[3] for e in ents)):
+            self.a[1] = frame
+            self.term = AsyncTermination()
+        self.wave += 1
+        self.a[0] = self.wave
+
+
+def render_domain_schedule_async(engine, board, rank, world, frame, root=0, max_polls=100000000):
+    """One DomainScheduler frame without exchange rounds (scheduler::AsyncDomain, tracer/Domain/DomainTracer.cpp:109-192)
+    over the NVLink peer path (after p2p_connect).  Every rank free-runs: each poll it asks its engine to trace whatever its
+    peers have published (non-blocking: nothing happens while its previous kernels are still running) and posts (busy, sent,
+    received) on the shared-memory board; rank 0 also plays the coordinator of the termination waves.  `frame` is a counter
+    that is the same on every rank and grows by one per call (starting at 1).  Returns the number of polls."""
     engine.domain_async_reset()
-    ready = torch.zeros(1, dtype=torch.int64, device=device)
-    dist.all_reduce(ready)  # every rank has cleared the tails its peers publish into
-    ready.item()
+    board.frame_barrier(frame)
     engine.domain_begin_frame()
-    term = AsyncTermination()
+    if rank == 0:
+        board.wave += 1  # a wave that starts inside this frame: snapshots of the previous frame cannot satisfy it
+        board.a[0] = board.wave
     for poll in range(1, max_polls + 1):
+        wave = board.current_wave()  # read BEFORE the snapshot: a snapshot tagged w was taken after wave w started
         busy, sent, received = engine.domain_async_step()
-        t = torch.tensor([int(busy), sent, received], dtype=torch.int64, device=device)
-        dist.all_reduce(t)
-        b, s_, r_ = (int(x) for x in t.tolist())
-        if term.update(b, s_, r_):
+        board.publish(wave, busy, sent, received, frame)
+        if rank == 0:
+            board.coordinate(frame)
+        if board.finished(frame):
             engine.domain_composite_p2p(root)
             return poll
     raise RuntimeError(f"asynchronous DomainScheduler: no termination after {max_polls} polls")

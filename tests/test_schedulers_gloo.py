@@ -112,6 +112,7 @@ class _ScriptedEngine:
     new rays arrived, and forwards a shrinking share of them to its peer."""
 
     def __init__(self, rank, world, root):
+        os.makedirs(root, exist_ok=True)
         self.rank, self.world, self.root = rank, world, root
         self.sent = self.received = 0
         self.work = 0  # polls of tracing left
@@ -169,9 +170,15 @@ def _async_worker(rank, world, port, root, out):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        e = _ScriptedEngine(rank, world, root)
-        polls = schedulers.render_domain_schedule_async(e, dist, rank, world, "cpu")
-        out.put((rank, polls, e.sent, e.received, e.composited))
+        board = schedulers.AsyncBoard.connect(dist, rank, world)
+        res = []
+        for frame in (1, 2):  # twice: the board is reused from frame to frame
+            e = _ScriptedEngine(rank, world, os.path.join(root, f"f{frame}"))
+            polls = schedulers.render_domain_schedule_async(e, board, rank, world, frame)
+            res.append((polls, e.sent, e.received, e.composited))
+        dist.barrier()
+        board.close()
+        out.put((rank, res))
     finally:
         dist.destroy_process_group()
 
@@ -188,7 +195,8 @@ def test_async_domain_schedule_world2(tmp_path):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert res[0][1] == res[1][1]                      # both ranks stop at the same poll
-    assert all(r[4] for r in res)                      # and composite
-    assert res[0][2] == res[1][3] and res[1][2] == res[0][3]  # everything that was sent was received: nothing was cut off
-    assert res[0][2] >= 8 and res[1][2] >= 12
+    for f in range(2):
+        (_, s0, r0, c0), (_, s1, r1, c1) = res[0][1][f], res[1][1][f]
+        assert c0 and c1                    # both ranks left the loop and composited
+        assert s0 == r1 and s1 == r0        # everything that was sent was received: the frame was not cut off early
+        assert s0 >= 8 and s1 >= 12
