@@ -225,7 +225,7 @@ def main():
     ap.add_argument("--owner", default="mod", choices=["mod", "balanced"], help="gyroid: brick k on rank k mod N (the reference's map) or the view-balanced placement")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1, ImageScheduler workloads: weak = the film grows by sqrt(N) per axis so every rank keeps the N = 1 "
                     "ray count (same scene, camera and aspect); strong = the N = 1 film split over the ranks")
-    ap.add_argument("--domain-schedule", default="async", choices=["async", "rounds"], help="gyroid, N > 1, peer path: free-running ranks with counter termination (scheduler::AsyncDomain) or "
+    ap.add_argument("--domain-schedule", default="rounds", choices=["async", "rounds"], help="gyroid, N > 1, peer path: free-running ranks with counter termination (scheduler::AsyncDomain) or "
                     "exchange rounds ended by an all-reduce (Tracer<DomainScheduler>); the other one is timed as well and reported in config")
     ap.add_argument("--gyroid-res", type=int, default=library.GYROID_RES_100M, help="grid cells per axis of the gyroid volume (946 = 100 M triangles)")
     a = ap.parse_args()
