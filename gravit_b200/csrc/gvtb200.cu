@@ -505,7 +505,6 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
   int *sah_node_of = nullptr, *sah_node_of2 = nullptr;
   SahNode *sah_act = nullptr, *sah_act2 = nullptr;
   SahBin *sah_bins = nullptr;
-  unsigned sah_levels = 0;
   int2 *bn_child = nullptr, *bn_range = nullptr;
   int *bn_parent = nullptr;
   CollapseTask *d_ta = nullptr, *d_tb = nullptr;
@@ -620,8 +619,6 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
       if (sc.idx != va) CUB(cudaMemcpyAsync(va, sc.idx, n * 4, cudaMemcpyDeviceToDevice, st));
       CUB(cudaMemsetAsync(d_counts, 0, 16, st));
       k_leaf_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
-      (void)sah_levels;
-      sah_levels = levels;
     } else {
       k_leaf_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
       if (nf > 1) {
