@@ -107,3 +107,29 @@ def test_grazing_rays_near_faces(E):
         E.emul_intersect(h, po._fp(rays), len(rays), 0, po._fp(he), None)
         assert np.array_equal(ho, he)
         E.emul_destroy(h)
+
+
+def test_optimal_widening_beats_greedy(E, monkeypatch):
+    """The SAH dynamic program (bvh_build.h collapse_dp_node, Ylitie-Karras-Laine 3.1) must give fewer wide nodes and fewer
+    node visits than the area-greedy widening on the same binary tree, with identical hits."""
+    d = library.sibenik_scene(96, 54)
+    o = oracle_scene(d)
+    rays = np.concatenate([o.camera_rays(), random_rays(o.mesh_get(0, len(np.asarray(d.meshes[0].verts).reshape(-1, 3)))[2], 6000, seed=3)])
+    res = {}
+    for mode in ("greedy", "dp"):
+        if mode == "greedy":
+            monkeypatch.setenv("GVTB200_WIDEN", "greedy")
+        else:
+            monkeypatch.delenv("GVTB200_WIDEN", raising=False)
+        h, nf, _ = _mesh(E, o, d, 0)
+        st = np.zeros(4, np.uint64)
+        E.emul_stats(h, po._fp(st))
+        he = np.zeros(len(rays), po.HIT_DTYPE)
+        cnt = np.zeros(2, np.uint64)
+        E.emul_intersect(h, po._fp(rays), len(rays), 0, po._fp(he), po._fp(cnt))
+        res[mode] = (int(st[0]), int(st[1]), int(cnt[0]), he.copy())
+        E.emul_destroy(h)
+    assert res["dp"][1] == res["greedy"][1] == nf          # every triangle referenced exactly once either way
+    assert res["dp"][0] < 0.9 * res["greedy"][0]          # at least 10 % fewer wide nodes
+    assert res["dp"][2] < res["greedy"][2]                 # and fewer node visits
+    assert np.array_equal(res["dp"][3], res["greedy"][3])  # hits are BVH-independent
