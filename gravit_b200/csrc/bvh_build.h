@@ -13,6 +13,13 @@
 
 namespace gvt {
 
+// a value written by another thread of the same launch: read through L2
+#if defined(__CUDA_ARCH__)
+#define GVT_LDCG1(p) __ldcg(p)
+#else
+#define GVT_LDCG1(p) (*(p))
+#endif
+
 struct BuildCtx {
   const float *verts;    // 3 per vertex
   const uint32_t *faces; // 3 per face, 0-based
@@ -32,6 +39,11 @@ struct BuildCtx {
   float4 *wtris;  // 3 per triangle record slot (GVT_LEAF_MAX slots per leaf child)
   unsigned *node_count, *tri_count, *tri_real; // wide nodes, triangle record slots, triangles referenced
   unsigned wnode_cap;
+  // insertion-based optimisation (reinsert_*): per binary node
+  int4 *ri_pick;                  // {target y, pivot, gain bits, 0}; y < 0: no improving move
+  unsigned long long *ri_lock;    // highest (gain, node) key that wants to touch this node in the current iteration
+  unsigned *ri_go;                // 1: the node's move is carried out in this iteration
+  unsigned *ri_cnt;               // triangles below an internal node (relayout)
   // optimal widening (collapse_dp_node): per internal binary node, null = surface-area-greedy widening
   float *dp_cost;         // [7 * node + i - 1] = C(node, i), i = 1..7
   unsigned char *dp_pick; // [8 * node + j - 1], j = 2..8: left share k of the best distribution of j roots; [8 * node]: bit 0 =
@@ -296,6 +308,183 @@ GVT_HD uint32_t quant_exponent(float ext) {
   return e;
 }
 
+// ---- insertion-based optimisation of the binary tree -----------------------------------------------------------
+// Top-down SAH decides every split once, with what it knows at that moment; on architectural meshes (big walls next to
+// fine detail) a node often ends up in a subtree where it drags boxes open.  Bittner, Hapala and Havran (2013) repair
+// that by taking nodes out and re-inserting them where the surface-area cost grows least; Meister and Bittner (2018)
+// give the parallel form used here.  One iteration:
+//   reinsert_search  every node x looks for the node y that it would best become the sibling of.  Walking up from x,
+//                    each ancestor ("pivot") contributes the subtree on its other side as a search region; d is the
+//                    area freed so far: x's parent p disappears (its sibling takes its place) and every ancestor between
+//                    p and the pivot shrinks to the box of what is left below it.  Inside a region the cost of reaching y
+//                    is the growth of every box on the way down plus the new parent box A(x u y); branches that cannot
+//                    beat the best gain so far are cut.
+//   reinsert_lock    a move rewrites pointers of six nodes (x, p, its sibling, its grandparent, y, y's parent); each move
+//                    bids for them with atomicMax of (gain, x).
+//   reinsert_check   a move that holds all six is a candidate;
+//   reinsert_confirm it is dropped if a node on its way up to the pivot moves as well (two such moves could carry each
+//                    other's subtree: a cycle);
+//   reinsert_apply   the confirmed moves rewire their pointers; nobody else reads or writes them in that phase.  Boxes
+//                    are re-fitted bottom-up afterwards (k_refit).  Every phase only reads what the previous one wrote, so
+//                    the outcome does not depend on thread order.
+// Moves change the left-to-right order of the leaves, which the widening relies on (a leaf slot is a contiguous run of
+// sorted positions), so the last step renumbers the leaves in depth-first order (relayout_*).  Hits do not depend on the
+// tree; Morton keys are taken before.
+#define GVT_RI_STACK 96
+// iterations for a mesh of n faces: GVTB200_REINSERT overrides; by default small and medium meshes get 8 (a search is
+// cheap there and architectural models gain 8-14 % fewer node visits), very large ones none (uniform tessellations such as
+// an isosurface gain nothing and every iteration is a pass over the whole tree)
+static inline int reinsert_iterations(size_t n) {
+  const char *e = getenv("GVTB200_REINSERT");
+  if (e) return atoi(e) < 0 ? 0 : atoi(e);
+  return n <= 4000000 ? 8 : 0;
+}
+GVT_HD float box_area4(float4 lo, float4 hi) {
+  float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+GVT_HD float union_area4(float4 al, float4 ah, float4 bl, float4 bh) {
+  float dx = fmaxf(ah.x, bh.x) - fminf(al.x, bl.x), dy = fmaxf(ah.y, bh.y) - fminf(al.y, bl.y), dz = fmaxf(ah.z, bh.z) - fminf(al.z, bl.z);
+  return dx * dy + dy * dz + dz * dx;
+}
+GVT_HD int bn_sibling(const BuildCtx &c, int parent, int child) {
+  const int2 k = c.bn_child[parent];
+  return k.x == child ? k.y : k.x;
+}
+// explores one region (the subtree of `root`) for the best sibling of x; d = area freed if x leaves its place
+GVT_HD void reinsert_region(const BuildCtx &c, int root, int pivot, int skip, float4 xl, float4 xh, float ax, float d,
+                            float &best_gain, int &best_y, int &best_pivot) {
+  int sn[GVT_RI_STACK];
+  float si[GVT_RI_STACK];
+  int sp = 0;
+  sn[sp] = root, si[sp] = 0.f, sp++;
+  const int first_leaf = (int)c.n - 1;
+  while (sp) {
+    --sp;
+    const int y = sn[sp];
+    const float ind = si[sp];
+    const float4 yl = c.bn_lo[y], yh = c.bn_hi[y];
+    const float direct = union_area4(xl, xh, yl, yh);
+    const float gain = d - direct - ind;
+    if (gain > best_gain && y != skip) best_gain = gain, best_y = y, best_pivot = pivot;
+    if (y < first_leaf) {
+      const float ind2 = ind + direct - box_area4(yl, yh); // y grows to x u y when x goes somewhere below it
+      if (d - ax - ind2 > best_gain && sp + 2 <= GVT_RI_STACK) {
+        const int2 k = c.bn_child[y];
+        sn[sp] = k.x, si[sp] = ind2, sp++;
+        sn[sp] = k.y, si[sp] = ind2, sp++;
+      }
+    }
+  }
+}
+GVT_HD void reinsert_search(const BuildCtx &c, int x) {
+  int4 pick = make_int4(-1, -1, 0, 0);
+  const int p = c.bn_parent[x];
+  const int g = p >= 0 ? c.bn_parent[p] : -1;
+  if (g >= 0) { // the root and its children stay where they are
+    const float4 xl = c.bn_lo[x], xh = c.bn_hi[x];
+    const float ax = box_area4(xl, xh);
+    const int s = bn_sibling(c, p, x);
+    float d = box_area4(c.bn_lo[p], c.bn_hi[p]);
+    float best_gain = d * 1e-4f; // a move must pay for itself
+    int best_y = -1, best_pivot = -1;
+    reinsert_region(c, s, p, s, xl, xh, ax, d, best_gain, best_y, best_pivot); // below the sibling (the sibling itself = no move)
+    float4 sl = c.bn_lo[s], sh = c.bn_hi[s]; // box of what is left below the pivot's child on x's side
+    int cur = p, piv = g;
+    while (piv >= 0) {
+      const int other = bn_sibling(c, piv, cur);
+      reinsert_region(c, other, piv, -1, xl, xh, ax, d, best_gain, best_y, best_pivot);
+      const float4 ol = c.bn_lo[other], oh = c.bn_hi[other];
+      sl = make_float4(fminf(sl.x, ol.x), fminf(sl.y, ol.y), fminf(sl.z, ol.z), 0.f);
+      sh = make_float4(fmaxf(sh.x, oh.x), fmaxf(sh.y, oh.y), fmaxf(sh.z, oh.z), 0.f);
+      d += box_area4(c.bn_lo[piv], c.bn_hi[piv]) - box_area4(sl, sh); // above here the pivot loses x as well
+      cur = piv, piv = c.bn_parent[piv];
+    }
+    if (best_y >= 0) pick = make_int4(best_y, best_pivot, (int)f2u(best_gain), 0);
+  }
+  c.ri_pick[x] = pick;
+}
+GVT_HD unsigned long long reinsert_key(int4 pick, int x) { return ((unsigned long long)(uint32_t)pick.z << 32) | (uint32_t)x; }
+#if defined(__CUDA_ARCH__)
+#define GVT_ATOMIC_MAX64(p, v) atomicMax((p), (v))
+#else
+#define GVT_ATOMIC_MAX64(p, v) (*(p) = *(p) < (v) ? (v) : *(p))
+#endif
+// the nodes whose pointers a move of x rewrites: x, its parent p, its sibling s, its grandparent g, the target y and y's parent q
+GVT_HD void reinsert_nodes(const BuildCtx &c, int x, int4 pick, int out[6]) {
+  const int p = c.bn_parent[x];
+  out[0] = x, out[1] = p, out[2] = bn_sibling(c, p, x), out[3] = c.bn_parent[p], out[4] = pick.x, out[5] = c.bn_parent[pick.x];
+}
+GVT_HD void reinsert_lock(const BuildCtx &c, int x) {
+  const int4 pick = c.ri_pick[x];
+  if (pick.x < 0) return;
+  const unsigned long long key = reinsert_key(pick, x);
+  int nd[6];
+  reinsert_nodes(c, x, pick, nd);
+  for (int i = 0; i < 6; ++i) GVT_ATOMIC_MAX64(&c.ri_lock[nd[i]], key);
+}
+// after every bid is in: does x hold all six nodes?  (the answer goes into pick.w; the tree is still untouched)
+GVT_HD void reinsert_check(const BuildCtx &c, int x) {
+  const int4 pick = c.ri_pick[x];
+  if (pick.x < 0) return;
+  const unsigned long long key = reinsert_key(pick, x);
+  int nd[6];
+  reinsert_nodes(c, x, pick, nd);
+  bool mine = true;
+  for (int i = 0; i < 6; ++i) mine = mine && c.ri_lock[nd[i]] == key;
+  c.ri_pick[x].w = mine ? 1 : 0;
+}
+// Two moves with disjoint node sets can still carry each other's subtree (x goes below x'' while x'' goes below x: a cycle cut
+// off from the root).  A move is therefore dropped when any node on its way -- from p up to the pivot and from y up to
+// the pivot -- is itself a node that moves in this iteration.  Reads only the verdicts of reinsert_check, writes ri_go.
+GVT_HD void reinsert_confirm(const BuildCtx &c, int x) {
+  const int4 pick = c.ri_pick[x];
+  unsigned go = 0;
+  if (pick.x >= 0 && pick.w == 1) {
+    go = 1;
+    int steps = 0;
+    for (int a = c.bn_parent[x]; a != pick.y && go; a = c.bn_parent[a])
+      if (a < 0 || ++steps > 4096 || c.ri_pick[a].w == 1) go = 0;
+    for (int a = pick.x; a != pick.y && go; a = c.bn_parent[a])
+      if (a < 0 || ++steps > 8192 || c.ri_pick[a].w == 1) go = 0;
+    if (go && c.ri_pick[pick.y].w == 1) go = 0;
+  }
+  c.ri_go[x] = go;
+}
+GVT_HD bool reinsert_apply(const BuildCtx &c, int x) {
+  if (!c.ri_go[x]) return false;
+  const int4 pick = c.ri_pick[x];
+  const int y = pick.x, p = c.bn_parent[x], g = c.bn_parent[p], s = bn_sibling(c, p, x);
+  // take p out: its sibling-side child moves up
+  if (c.bn_child[g].x == p) c.bn_child[g].x = s; else c.bn_child[g].y = s;
+  c.bn_parent[s] = g;
+  // put p in above y
+  const int q = c.bn_parent[y];
+  if (c.bn_child[q].x == y) c.bn_child[q].x = p; else c.bn_child[q].y = p;
+  c.bn_parent[p] = q;
+  c.bn_child[p] = make_int2(y, x);
+  c.bn_parent[y] = p;
+  return true;
+}
+// triangles below internal node b (bottom-up: both children are done)
+GVT_HD void relayout_count_node(const BuildCtx &c, int b) {
+  const int2 k = c.bn_child[b];
+  const int first_leaf = (int)c.n - 1;
+  c.ri_cnt[b] = (k.x >= first_leaf ? 1u : GVT_LDCG1(&c.ri_cnt[k.x])) + (k.y >= first_leaf ? 1u : GVT_LDCG1(&c.ri_cnt[k.y]));
+}
+// relayout: sorted position of a leaf / first position of an internal node = triangles to the left of it in depth-first
+// order = sum, over the ancestors entered through their right child, of the left child's triangle count
+GVT_HD unsigned relayout_first(const BuildCtx &c, int node) {
+  unsigned first = 0;
+  const int first_leaf = (int)c.n - 1;
+  int cur = node;
+  for (int a = c.bn_parent[cur]; a >= 0; cur = a, a = c.bn_parent[a]) {
+    const int2 k = c.bn_child[a];
+    if (k.y == cur) first += k.x >= first_leaf ? 1u : c.ri_cnt[k.x];
+  }
+  return first;
+}
+
 // ---- optimal widening (Ylitie, Karras, Laine, HPG 2017, section 3.1) -------------------------------------------
 // C(n, i) = cheapest SAH cost of binary subtree n represented by at most i roots (wide nodes or leaves):
 //   C(n, 1) = A_n * P_n * C_prim if P_n <= GVT_LEAF_MAX (a leaf slot), else C_dist(n, 8) + A_n * C_node (a wide node)
@@ -305,11 +494,6 @@ GVT_HD uint32_t quant_exponent(float ext) {
 // top-down by collapse_gather_dp.  C_node : C_prim is the measured cost ratio of a node visit (8 L1 wavefronts, ~130
 // instructions) to a triangle test (3 wavefronts, ~40 instructions).
 #define GVT_DP_CNODE 1.0f
-#if defined(__CUDA_ARCH__)
-#define GVT_LDCG1(p) __ldcg(p)
-#else
-#define GVT_LDCG1(p) (*(p))
-#endif
 #ifndef GVT_DP_CPRIM
 #define GVT_DP_CPRIM 0.35f
 #endif

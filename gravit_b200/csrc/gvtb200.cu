@@ -510,12 +510,17 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
   CollapseTask *d_ta = nullptr, *d_tb = nullptr;
   float *dp_cost = nullptr;
   unsigned char *dp_pick = nullptr;
+  int4 *ri_pick = nullptr;
+  unsigned long long *ri_lock = nullptr;
+  unsigned *ri_go = nullptr, *ri_cnt = nullptr, *ri_newpos = nullptr;
+  int *ri_lpar = nullptr, *ri_lslot = nullptr;
   std::vector<unsigned *> scan_levels, scan_levels_flag; // per-size scratch of the two device-wide scans (radix histogram, SAH flags)
   int rc = GVTB200_OK;
   auto cleanup = [&]() {
     sfree(d_verts, st), sfree(d_faces3, st), sfree(d_keys, st), sfree(d_vals, st), sfree(d_keys2, st), sfree(d_vals2, st), sfree(d_hist, st), sfree(d_flag, st);
     sfree(sah_tb_lo, st), sfree(sah_tb_hi, st), sfree(sah_idx2, st), sfree(sah_node_of, st), sfree(sah_node_of2, st), sfree(sah_act, st), sfree(sah_act2, st), sfree(sah_bins, st);
     sfree(d_counts, st), sfree(bn_lo, st), sfree(bn_hi, st), sfree(wnodes, st), sfree(wtris, st), sfree(bn_child, st), sfree(bn_range, st), sfree(bn_parent, st), sfree(d_ta, st), sfree(d_tb, st), sfree(dp_cost, st), sfree(dp_pick, st);
+    sfree(ri_pick, st), sfree(ri_lock, st), sfree(ri_go, st), sfree(ri_cnt, st), sfree(ri_newpos, st), sfree(ri_lpar, st), sfree(ri_lslot, st);
     for (auto *p : scan_levels) cudaFreeAsync(p, st);
     for (auto *p : scan_levels_flag) cudaFreeAsync(p, st);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
@@ -619,6 +624,33 @@ static int mesh_build(gvtb200_mesh m, const float *vertices, uint32_t nv, const 
       if (sc.idx != va) CUB(cudaMemcpyAsync(va, sc.idx, n * 4, cudaMemcpyDeviceToDevice, st));
       CUB(cudaMemsetAsync(d_counts, 0, 16, st));
       k_leaf_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
+      // insertion-based optimisation: nodes move to where the surface-area cost grows least (bvh_build.h reinsert_*)
+      const int ri_iters = reinsert_iterations(n);
+      if (nf >= 4 && ri_iters > 0) {
+        const size_t total = 2 * n - 1;
+        const unsigned nb = blocks_for(total, 128);
+        CUB(salloc(&ri_pick, total, st)); CUB(salloc(&ri_lock, total, st)); CUB(salloc(&ri_go, total, st)); CUB(salloc(&ri_cnt, n, st));
+        CUB(salloc(&ri_newpos, n, st)); CUB(salloc(&ri_lpar, n, st)); CUB(salloc(&ri_lslot, n, st));
+        c.ri_pick = ri_pick, c.ri_lock = ri_lock, c.ri_go = ri_go, c.ri_cnt = ri_cnt;
+        for (int it = 0; it < ri_iters; ++it) {
+          CUB(cudaMemsetAsync(ri_lock, 0, total * sizeof(unsigned long long), st));
+          k_ri_search<<<nb, 128, 0, st>>>(c);
+          k_ri_lock<<<nb, 128, 0, st>>>(c);
+          k_ri_check<<<nb, 128, 0, st>>>(c);
+          k_ri_confirm<<<nb, 128, 0, st>>>(c);
+          k_ri_apply<<<nb, 128, 0, st>>>(c);
+          CUB(cudaMemsetAsync(d_flag, 0, n * 4, st));
+          k_refit<<<blocks_for(n, 256), 256, 0, st>>>(c);
+        }
+        // the moves changed the depth-first order of the leaves: renumber them, re-order the elements
+        CUB(cudaMemsetAsync(d_flag, 0, n * 4, st));
+        k_ri_count<<<blocks_for(n, 256), 256, 0, st>>>(c);
+        k_ri_layout_a<<<nb, 128, 0, st>>>(c, ri_newpos, ri_lpar, ri_lslot);
+        uint32_t *vals_out = (va == d_vals) ? d_vals2 : d_vals;
+        k_ri_layout_b<<<blocks_for(n, 256), 256, 0, st>>>(c, ri_newpos, ri_lpar, ri_lslot, vals_out);
+        va = vals_out, c.vals = va;
+        k_leaf_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
+      }
     } else {
       k_leaf_setup<<<blocks_for(n, 256), 256, 0, st>>>(c);
       if (nf > 1) {

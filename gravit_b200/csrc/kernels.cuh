@@ -48,6 +48,65 @@ __global__ void k_refit(BuildCtx c) {
     node = c.bn_parent[node];
   }
 }
+// ---- insertion-based optimisation of the binary tree (bodies and the algorithm: bvh_build.h reinsert_*) ------------------
+// one thread per binary node (internal nodes 0..n-2, leaves n-1..2n-2; node 0 is the root and never moves)
+__global__ void k_ri_search(BuildCtx c) {
+  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x == 0) c.ri_pick[0] = make_int4(-1, -1, 0, 0);
+  if (x >= 1 && x < 2 * c.n - 1) reinsert_search(c, (int)x);
+}
+__global__ void k_ri_lock(BuildCtx c) {
+  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= 1 && x < 2 * c.n - 1) reinsert_lock(c, (int)x);
+}
+__global__ void k_ri_check(BuildCtx c) {
+  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= 1 && x < 2 * c.n - 1) reinsert_check(c, (int)x);
+}
+__global__ void k_ri_confirm(BuildCtx c) {
+  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x == 0) c.ri_go[0] = 0;
+  if (x >= 1 && x < 2 * c.n - 1) reinsert_confirm(c, (int)x);
+}
+__global__ void k_ri_apply(BuildCtx c) {
+  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= 1 && x < 2 * c.n - 1) reinsert_apply(c, (int)x);
+}
+// triangles below every internal node, bottom-up (same climbing rule as k_refit)
+__global__ void k_ri_count(BuildCtx c) {
+  unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.n || c.n < 2) return;
+  int node = c.bn_parent[c.n - 1 + k];
+  while (node >= 0) {
+    __threadfence();
+    unsigned old = atomicAdd(&c.bn_flag[node], 1u);
+    if (old == 0u) return;
+    relayout_count_node(c, node);
+    node = c.bn_parent[node];
+  }
+}
+// relayout, step 1 (reads only): new sorted position, parent and child slot of every leaf; ranges of the internal nodes
+__global__ void k_ri_layout_a(BuildCtx c, unsigned *newpos, int *leaf_parent, int *leaf_slot) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c.n) {
+    const int id = (int)(c.n - 1 + i), p = c.bn_parent[id];
+    newpos[i] = relayout_first(c, id), leaf_parent[i] = p, leaf_slot[i] = c.bn_child[p].y == id ? 1 : 0;
+  } else if (i < 2 * c.n - 1) {
+    const int b = (int)(i - c.n);
+    const unsigned f = relayout_first(c, b);
+    c.bn_range[b] = make_int2((int)f, (int)(f + c.ri_cnt[b] - 1u));
+  }
+}
+// step 2: leaves take their new numbers (n - 1 + position); the element order follows
+__global__ void k_ri_layout_b(BuildCtx c, const unsigned *newpos, const int *leaf_parent, const int *leaf_slot, uint32_t *vals_out) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.n) return;
+  const unsigned np = newpos[k];
+  const int nid = (int)(c.n - 1 + np), p = leaf_parent[k];
+  vals_out[np] = c.vals[k];
+  c.bn_parent[nid] = p;
+  if (leaf_slot[k]) c.bn_child[p].y = nid; else c.bn_child[p].x = nid;
+}
 // optimal-widening tables, bottom-up: the second thread to reach an internal node fills its row (both children's rows
 // are complete by then) and continues upwards
 __global__ void k_collapse_dp(BuildCtx c) {

@@ -27,6 +27,82 @@ struct EmulMesh {
   Blas blas;
 };
 
+
+// The product's insertion-based optimisation (bvh_build.h reinsert_*), phases in the order the device runs them; every
+// phase is a loop over nodes here and a kernel there.  The lock winners do not depend on the order of the bids, so the
+// result is the device's.
+static void emul_refit(BuildCtx &c) {
+  const int n = (int)c.n;
+  std::vector<int> stack, order;
+  stack.push_back(0);
+  while (!stack.empty()) {
+    int b = stack.back();
+    stack.pop_back();
+    order.push_back(b);
+    int2 ch = c.bn_child[b];
+    if (ch.x < n - 1) stack.push_back(ch.x);
+    if (ch.y < n - 1) stack.push_back(ch.y);
+  }
+  for (size_t i = order.size(); i-- > 0;) {
+    int b = order[i];
+    int2 ch = c.bn_child[b];
+    float4 l0 = c.bn_lo[ch.x], h0 = c.bn_hi[ch.x], l1 = c.bn_lo[ch.y], h1 = c.bn_hi[ch.y];
+    c.bn_lo[b] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
+    c.bn_hi[b] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+    if (c.ri_cnt) relayout_count_node(c, b);
+  }
+}
+static void reinsert_optimise(BuildCtx &c, std::vector<uint32_t> &vals, int iterations) {
+  const int n = (int)c.n, total = 2 * n - 1;
+  if (n < 4 || iterations <= 0) return;
+  std::vector<int4> pick(total);
+  std::vector<unsigned long long> lock(total);
+  std::vector<unsigned> cnt(total, 0), go(total, 0);
+  c.ri_pick = pick.data(), c.ri_lock = lock.data(), c.ri_go = go.data(), c.ri_cnt = nullptr;
+  for (int it = 0; it < iterations; ++it) {
+    std::fill(lock.begin(), lock.end(), 0ull);
+    for (int x = 1; x < total; ++x) reinsert_search(c, x);
+    pick[0] = make_int4(-1, -1, 0, 0);
+    for (int x = 1; x < total; ++x) reinsert_lock(c, x);
+    for (int x = 1; x < total; ++x) reinsert_check(c, x);
+    go[0] = 0;
+    for (int x = 1; x < total; ++x) reinsert_confirm(c, x);
+    size_t moved = 0;
+    for (int x = 1; x < total; ++x) moved += reinsert_apply(c, x) ? 1 : 0;
+    emul_refit(c);
+    if (getenv("GVT_EMUL_VERBOSE")) {
+      double sah = 0;
+      for (int b = 0; b < n - 1; ++b) sah += box_area4(c.bn_lo[b], c.bn_hi[b]);
+      fprintf(stderr, "reinsert iteration %d: %zu moves, inner-node SAH %.3f\n", it, moved, sah / box_area4(c.bn_lo[0], c.bn_hi[0]));
+    }
+    if (!moved) break;
+  }
+  // relayout: leaves renumbered in depth-first order
+  c.ri_cnt = cnt.data();
+  emul_refit(c);
+  std::vector<uint32_t> nvals(n);
+  std::vector<unsigned> npos(n);
+  std::vector<int> lpar(n), lslot(n);
+  for (int k = 0; k < n; ++k) {
+    const int id = n - 1 + k;
+    npos[k] = relayout_first(c, id), lpar[k] = c.bn_parent[id], lslot[k] = c.bn_child[lpar[k]].y == id ? 1 : 0;
+  }
+  for (int b = 0; b < n - 1; ++b) {
+    const unsigned f = relayout_first(c, b);
+    c.bn_range[b] = make_int2((int)f, (int)(f + cnt[b] - 1));
+  }
+  for (int k = 0; k < n; ++k) {
+    nvals[npos[k]] = vals[k];
+    const int nid = n - 1 + (int)npos[k];
+    c.bn_parent[nid] = lpar[k];
+    if (lslot[k]) c.bn_child[lpar[k]].y = nid; else c.bn_child[lpar[k]].x = nid;
+  }
+  vals = nvals;
+  c.vals = vals.data();
+  for (int k = 0; k < n; ++k) leaf_setup(c, (unsigned)k);
+  c.ri_pick = nullptr, c.ri_lock = nullptr, c.ri_go = nullptr, c.ri_cnt = nullptr;
+}
+
 #define EM_API extern "C" __attribute__((visibility("default")))
 
 EM_API void *emul_build(const float *verts, unsigned nv, const uint32_t *faces, unsigned nf) {
@@ -137,6 +213,7 @@ EM_API void *emul_build(const float *verts, unsigned nv, const uint32_t *faces, 
     m->vals = idx;
     c.vals = m->vals.data();
     for (unsigned k = 0; k < nf; ++k) leaf_setup(c, k);
+    reinsert_optimise(c, m->vals, reinsert_iterations(nf));
   } else {
   for (unsigned k = 0; k < nf; ++k) leaf_setup(c, k);
   for (unsigned i = 0; i + 1 < nf; ++i) karras_node(c, (int)i);

@@ -133,3 +133,26 @@ def test_optimal_widening_beats_greedy(E, monkeypatch):
     assert res["dp"][0] < 0.9 * res["greedy"][0]          # at least 10 % fewer wide nodes
     assert res["dp"][2] < res["greedy"][2]                 # and fewer node visits
     assert np.array_equal(res["dp"][3], res["greedy"][3])  # hits are BVH-independent
+
+
+def test_reinsertion_fewer_node_visits(E, monkeypatch):
+    """Insertion-based optimisation of the binary tree (bvh_build.h reinsert_*): every triangle is still referenced exactly
+    once, hits are unchanged (they are BVH-independent) and an architectural mesh needs clearly fewer node visits."""
+    d = library.sibenik_scene(96, 54)
+    o = oracle_scene(d)
+    nv = len(np.asarray(d.meshes[0].verts).reshape(-1, 3))
+    rays = np.concatenate([o.camera_rays(), random_rays(o.mesh_get(0, nv)[2], 6000, seed=5)])
+    res = {}
+    for iters in ("0", "8"):
+        monkeypatch.setenv("GVTB200_REINSERT", iters)
+        h, nf, _ = _mesh(E, o, d, 0)
+        st = np.zeros(4, np.uint64)
+        E.emul_stats(h, po._fp(st))
+        he = np.zeros(len(rays), po.HIT_DTYPE)
+        cnt = np.zeros(2, np.uint64)
+        E.emul_intersect(h, po._fp(rays), len(rays), 0, po._fp(he), po._fp(cnt))
+        res[iters] = (int(st[1]), int(cnt[0]), he.copy())
+        E.emul_destroy(h)
+    assert res["0"][0] == res["8"][0] == nf
+    assert np.array_equal(res["0"][2], res["8"][2])
+    assert res["8"][1] < 0.93 * res["0"][1]  # at least 7 % fewer node visits (measured: 12-16 %)
