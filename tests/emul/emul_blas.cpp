@@ -373,6 +373,7 @@ EM_API void emul_visit_stats(void *p, const void *rays, size_t n, int any, uint6
         }
         node_step<true, false>(m->blas.nodes, rl, GVT_RAY_EPSILON, tv, stack, &tc);
         out[(tv.ng.y & 0xFFu) ? 0 : 1]++;
+        if ((tv.ng.y >> 24) == 0u && (tv.tg.y & 0x00FFFFFFu) == 0u) out[7]++; // nothing inside was hit: a stale or empty visit
       }
       bool done = false;
       while (trav_has_tris(tv) && !done) done = tri_step<true>(m->blas.tris, rl, GVT_RAY_EPSILON, FLT_MAX, any != 0, tv, &tc);
@@ -393,6 +394,69 @@ EM_API void emul_node_hist(void *p, uint64_t *hist) {
     if (!imask) hist[13]++;
     for (int s = 0; s < 8; ++s)
       if ((tmask >> s) & 1u) hist[9 + ((tmask >> (8 + s)) & 1u) + ((tmask >> (16 + s)) & 1u) + 1]++;
+  }
+}
+
+// EXPLORATION (tools/bvh_eval.py): node visits of a closest-hit traversal that always opens the globally nearest pending
+// child and drops entries behind the closest hit found so far -- the lower bound for this BVH that the octant-ordered,
+// distance-free stack of the product (traverse.h) is compared with.  Child entry distances are decoded exactly like node_step.
+#include <queue>
+EM_API void emul_ideal_visits(void *p, const void *rays, size_t n, uint64_t *out) {
+  EmulMesh *m = (EmulMesh *)p;
+  const Ray80 *r = (const Ray80 *)rays;
+  const float4 *nodes = m->blas.nodes, *tris = m->blas.tris;
+  for (size_t i = 0; i < n; ++i) {
+    V3 o = v3(r[i].o[0], r[i].o[1], r[i].o[2]), d = v3(r[i].d[0], r[i].d[1], r[i].d[2]);
+    RayLocal rl;
+    ray_local(rl, o, d);
+    float tmax = FLT_MAX;
+    const float tnear = GVT_RAY_EPSILON;
+    typedef std::pair<float, uint32_t> QE; // (-entry distance, node index)
+    std::priority_queue<QE> pq;
+    if (m->blas.n_tris) pq.push(QE(0.f, 0u));
+    while (!pq.empty()) {
+      QE e = pq.top();
+      pq.pop();
+      if (-e.first > tmax) break;
+      out[0]++;
+      const float4 *np = nodes + GVT_NODE_WORDS * (size_t)e.second;
+      const uint32_t sx = (rl.octinv >> 2) & 1u, sy = (rl.octinv >> 1) & 1u, sz = rl.octinv & 1u;
+      const float4 h0 = np[0], h1 = np[1];
+      const float4 nx = np[3 - sx], fx = np[2 + sx], ny = np[5 - sy], fy = np[4 + sy], nz = np[7 - sz], fz = np[6 + sz];
+      const uint32_t ew = f2u(h0.w);
+      const float ax = u2f((ew & 0xFFu) << 23) * rl.rdx, ay = u2f(((ew >> 8) & 0xFFu) << 23) * rl.rdy, az = u2f(((ew >> 16) & 0xFFu) << 23) * rl.rdz;
+      const float bx = fmaf(h0.x - rl.o.x, rl.rdx, -ax), by = fmaf(h0.y - rl.o.y, rl.rdy, -ay), bz = fmaf(h0.z - rl.o.z, rl.rdz, -az);
+      const uint32_t imask = ew >> 24, tmask = f2u(h1.z);
+      float tn[8], tf[8];
+      for (int j = 0; j < 4; ++j) {
+        const float *cnx = &nx.x, *cfx = &fx.x, *cny = &ny.x, *cfy = &fy.x, *cnz = &nz.x, *cfz = &fz.x;
+        auto hi16 = [](float w) { return u2f(f2u(w) & 0xFFFF0000u); };
+        auto lo16 = [](float w) { return u2f(f2u(w) << 16); };
+        tn[j] = fmaxf(fmaxf(fmaf(hi16(cnx[j]), ax, bx), fmaf(hi16(cny[j]), ay, by)), fmaxf(fmaf(hi16(cnz[j]), az, bz), tnear));
+        tf[j] = fminf(fminf(fmaf(hi16(cfx[j]), ax, bx), fmaf(hi16(cfy[j]), ay, by)), fminf(fmaf(hi16(cfz[j]), az, bz), tmax));
+        tn[j + 4] = fmaxf(fmaxf(fmaf(lo16(cnx[j]), ax, bx), fmaf(lo16(cny[j]), ay, by)), fmaxf(fmaf(lo16(cnz[j]), az, bz), tnear));
+        tf[j + 4] = fminf(fminf(fmaf(lo16(cfx[j]), ax, bx), fmaf(lo16(cfy[j]), ay, by)), fminf(fmaf(lo16(cfz[j]), az, bz), tmax));
+      }
+      const uint32_t child_base = f2u(h1.x), tri_base = f2u(h1.y);
+      int rank_i = 0, rank_l = 0;
+      for (int sl = 0; sl < 8; ++sl) {
+        const bool hit = tn[sl] <= tf[sl];
+        if ((imask >> sl) & 1u) {
+          if (hit) pq.push(QE(-tn[sl], child_base + (uint32_t)rank_i));
+          rank_i++;
+        } else if ((tmask >> sl) & 1u) {
+          if (hit)
+            for (int k = 0; k < 3; ++k)
+              if ((tmask >> (8 * k + sl)) & 1u) {
+                const float4 *tp = tris + 3 * (size_t)(tri_base + 3u * (uint32_t)rank_l + (uint32_t)k);
+                out[1]++;
+                float t, u, v;
+                if (tri_test(rl.o, rl.d, v3(tp[0].x, tp[0].y, tp[0].z), v3(tp[1].x, tp[1].y, tp[1].z), v3(tp[2].x, tp[2].y, tp[2].z), tnear, FLT_MAX, t, u, v) && t < tmax) tmax = t;
+              }
+          rank_l++;
+        }
+      }
+    }
   }
 }
 

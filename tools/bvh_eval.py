@@ -62,6 +62,7 @@ def main():
     sets = [("camera", cam, 0), ("shadow(any)", shadow, 1), ("bounce", bounce, 0)]
     E.emul_visit_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
     E.emul_node_hist.argtypes = [C.c_void_p] * 2
+    E.emul_ideal_visits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     print(f"{scene}: {len(f)} faces; rays: " + ", ".join(f"{nm} {len(r_)}" for nm, r_, _ in sets))
     h = C.c_void_p(E.emul_build(po._fp(v), len(v), po._fp(f), len(f)))
     st = np.zeros(4, np.uint64)
@@ -78,7 +79,12 @@ def main():
         top = [float(x) / max(1.0, float(out[0] + out[1])) for x in out[3:7]]
         cost = 8 * (inner + bottom) + 3 * tt
         total += cost
-        print(f"  {nm:12s}: {inner + bottom:6.2f} nodes ({inner:5.2f} inner + {bottom:5.2f} bottom), {tt:5.2f} triangles, L1 wavefronts {cost:6.1f}; visits to the first 9/73/200/585 nodes: " + "/".join(f"{100 * x:.0f}%" for x in top))
+        ideal = f"; visits that hit nothing inside: {100.0 * float(out[7]) / max(1.0, float(out[0] + out[1])):.1f}%"
+        if not any_:
+            io = np.zeros(2, np.uint64)
+            E.emul_ideal_visits(h, po._fp(rays), len(rays), po._fp(io))
+            ideal += f"; nearest-first with distance culling would need {float(io[0]) / len(rays):.2f} nodes, {float(io[1]) / len(rays):.2f} triangles"
+        print(f"  {nm:12s}: {inner + bottom:6.2f} nodes ({inner:5.2f} inner + {bottom:5.2f} bottom), {tt:5.2f} triangles, L1 wavefronts {cost:6.1f}; visits to the first 9/73/200/585 nodes: " + "/".join(f"{100 * x:.0f}%" for x in top) + ideal)
     print(f"  total wavefronts per ray triple: {total:6.1f}")
     E.emul_destroy(h)
 
