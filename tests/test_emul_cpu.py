@@ -156,3 +156,43 @@ def test_reinsertion_fewer_node_visits(E, monkeypatch):
     assert res["0"][0] == res["8"][0] == nf
     assert np.array_equal(res["0"][2], res["8"][2])
     assert res["8"][1] < 0.93 * res["0"][1]  # at least 7 % fewer node visits (measured: 12-16 %)
+
+
+@pytest.mark.parametrize("kind", ["soup", "slivers_and_dust", "coincident"])
+def test_build_pipeline_on_hostile_meshes(E, kind):
+    """Binned SAH + insertion-based optimisation + optimal widening on meshes that stress them: a random triangle soup (boxes
+    overlap everywhere, many moves), long slivers mixed with tiny triangles (the case the optimisation exists for), and many
+    copies of one triangle (zero gains, ties on every comparison).  Hits must equal the oracle's bit for bit."""
+    rng = np.random.default_rng(42)
+    if kind == "soup":
+        c = rng.random((3000, 1, 3)).astype(np.float32)
+        tri = c + (rng.random((3000, 3, 3)).astype(np.float32) - 0.5) * 0.2
+    elif kind == "slivers_and_dust":
+        a = rng.random((300, 3)).astype(np.float32)
+        d = rng.normal(size=(300, 3)).astype(np.float32)
+        sl = np.stack([a, a + d * 0.8, a + d * 0.8 + rng.normal(size=(300, 3)).astype(np.float32) * 0.01], axis=1)
+        c = rng.random((3000, 1, 3)).astype(np.float32)
+        dust = c + (rng.random((3000, 3, 3)).astype(np.float32) - 0.5) * 0.01
+        tri = np.concatenate([sl, dust]).astype(np.float32)
+    else:
+        one = np.array([[0.1, 0.1, 0.5], [0.9, 0.2, 0.5], [0.4, 0.8, 0.5]], np.float32)
+        tri = np.repeat(one[None], 700, axis=0)
+    verts = tri.reshape(-1, 3)
+    faces1 = (np.arange(len(verts), dtype=np.uint32).reshape(-1, 3) + 1)
+    d = library.SceneDesc(kind, width=32, height=32)
+    d.meshes.append(library.MeshDesc(verts, faces1, True, None))
+    d.instances.append((0, np.eye(4, dtype=np.float32).T.reshape(-1)))
+    d.lights.append(((0.5, 0.5, 2.0), (1.0, 1.0, 1.0)))
+    d.eye, d.focus = (0.5, 0.5, 3.0), (0.5, 0.5, 0.0)
+    o = oracle_scene(d)
+    h, nf, bbox = _mesh(E, o, d, 0)
+    st = np.zeros(4, np.uint64)
+    E.emul_stats(h, po._fp(st))
+    assert st[1] == nf
+    rays = np.concatenate([o.camera_rays(), random_rays(bbox, 20000, seed=9)])
+    ho = o.intersect(0, rays, threads=4)
+    he = np.zeros(len(rays), po.HIT_DTYPE)
+    E.emul_intersect(h, po._fp(rays), len(rays), 0, po._fp(he), None)
+    assert np.array_equal(ho, he)
+    assert (ho["prim"] >= 0).sum() > 20
+    E.emul_destroy(h)
