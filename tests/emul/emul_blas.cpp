@@ -371,9 +371,12 @@ EM_API void emul_visit_stats(void *p, const void *rays, size_t n, int any, uint6
           const uint32_t K[4] = { 9u, 73u, 200u, 585u };
           for (int q = 0; q < 4; ++q) out[3 + q] += ni < K[q] ? 1u : 0u;
         }
+        const unsigned before = tc.nodes;
         node_step<true, false>(m->blas.nodes, rl, GVT_RAY_EPSILON, tv, stack, &tc);
-        out[(tv.ng.y & 0xFFu) ? 0 : 1]++;
-        if ((tv.ng.y >> 24) == 0u && (tv.tg.y & 0x00FFFFFFu) == 0u) out[7]++; // nothing inside was hit: a stale or empty visit
+        if (tc.nodes != before) { // (a group dropped without a fetch is not a visit)
+          out[(tv.ng.y & 0xFFu) ? 0 : 1]++;
+          if ((tv.ng.y >> 24) == 0u && (tv.tg.y & 0x00FFFFFFu) == 0u) out[7]++; // nothing inside was hit: a stale or empty visit
+        }
       }
       bool done = false;
       while (trav_has_tris(tv) && !done) done = tri_step<true>(m->blas.tris, rl, GVT_RAY_EPSILON, FLT_MAX, any != 0, tv, &tc);
