@@ -239,19 +239,32 @@ class AsyncBoard:
         self.a[0] = self.wave
 
 
-def render_domain_schedule_async(engine, board, rank, world, frame, root=0, max_polls=100000000):
+def render_domain_schedule_async(engine, board, rank, world, frame, root=0, timeout_s=120.0):
     """One DomainScheduler frame without exchange rounds (scheduler::AsyncDomain, tracer/Domain/DomainTracer.cpp:109-192)
     over the NVLink peer path (after p2p_connect).  Every rank free-runs: each poll it asks its engine to trace whatever its
     peers have published (non-blocking: nothing happens while its previous kernels are still running) and posts (busy, sent,
     received) on the shared-memory board; rank 0 also plays the coordinator of the termination waves.  `frame` is a counter
-    that is the same on every rank and grows by one per call (starting at 1).  Returns the number of polls."""
+    that is the same on every rank and grows by one per call (starting at 1).  Returns the number of polls.  A rank that
+    waits longer than timeout_s for the others (one of them died) raises instead of spinning for ever."""
+    import time
+
+    t0 = time.monotonic()
+
+    def check_time():
+        if time.monotonic() - t0 > timeout_s:
+            raise RuntimeError(f"asynchronous DomainScheduler: rank {rank} gave up after {timeout_s:.0f} s (frame {frame})")
+
     engine.domain_async_reset()
-    board.frame_barrier(frame)
+    board.frame_barrier(frame, spin=check_time)
     engine.domain_begin_frame()
     if rank == 0:
         board.wave += 1  # a wave that starts inside this frame: snapshots of the previous frame cannot satisfy it
         board.a[0] = board.wave
-    for poll in range(1, max_polls + 1):
+    poll = 0
+    while True:
+        poll += 1
+        if (poll & 1023) == 0:
+            check_time()
         wave = board.current_wave()  # read BEFORE the snapshot: a snapshot tagged w was taken after wave w started
         busy, sent, received = engine.domain_async_step()
         board.publish(wave, busy, sent, received, frame)
@@ -260,7 +273,6 @@ def render_domain_schedule_async(engine, board, rank, world, frame, root=0, max_
         if board.finished(frame):
             engine.domain_composite_p2p(root)
             return poll
-    raise RuntimeError(f"asynchronous DomainScheduler: no termination after {max_polls} polls")
 
 
 def render_domain_schedule(engine, dist, rank, world, device, fb_tensor, max_rounds=10000):
