@@ -531,6 +531,62 @@ def test_domain_scheduler_async_peer(gpu, world, scene):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("schedule", ["rounds", "async"])
+def test_domain_scheduler_with_bounces(gpu, schedule):
+    """Both DomainScheduler schedules with rayMaxDepth 2 on 3 simulated ranks: secondary rays migrate as well (their random
+    numbers are a function of ray id and depth, not of who traces them), so the number of rays that change rank equals the
+    oracle's and the image matches the single-process image to fp32 reassociation."""
+    from gravit_b200 import schedulers
+
+    world = 3
+    d = library.simple_scene(192, 192)
+    d.depth = 2
+    flags = 1
+    o = oracle_scene(d, flags)
+    o.set_owner(np.arange(len(d.instances)) % world)
+    ref, st = o.render(schedule=1, world_size=world, threads=8)
+    exchanged_o = int(sum(m.sum() for m in o.route_log(world)))
+    ref1, _ = o.render(schedule=0, world_size=1, threads=8)
+    ranks, owner = _standalone_ranks(gpu, d, flags, world)
+    _connect(ranks)
+    if schedule == "async":
+        for e in ranks:
+            e.domain_async_reset()
+    for e in ranks:
+        e.domain_begin_frame()
+    if schedule == "async":
+        term = schedulers.AsyncTermination()
+        for polls in range(200000):
+            res = [e.domain_async_step() for e in ranks]
+            if term.update(sum(int(r[0]) for r in res), sum(r[1] for r in res), sum(r[2] for r in res)):
+                break
+        else:
+            raise AssertionError("no termination")
+    else:
+        log = []
+        for rnd in range(100):
+            for e in ranks:
+                e.domain_round_p2p(rnd)
+            for e in ranks:
+                e.sync()
+            log.append(sum(e.counters()["rays_exported"] for e in ranks))
+            if schedulers.domain_terminated(log):
+                break
+    assert sum(e.counters()["rays_exported"] for e in ranks) == exchanged_o and exchanged_o > 0
+    assert sum(e.counters()["secondary_generated"] for e in ranks) == st["secondary_generated"] > 0
+    assert all(e.counters()["queue_overflows"] == 0 for e in ranks)
+    for e in ranks[1:] + ranks[:1]:
+        e.domain_composite_p2p(0)
+    for e in ranks:
+        e.sync()
+    fb = ranks[0].fb_read(d.width, d.height)
+    assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref1)) >= 50.0
+    assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref)) >= 50.0
+    for e in ranks:
+        e.close()
+
+
+@pytest.mark.gpu
 def test_conf_file_scene_end_to_end(gpu, tmp_path):
     """a data/*.conf style scene file (OBJ + MTL, two instances of one mesh, point light) loaded by the C++
     ConfigFileLoader / ObjReader, rendered through api::render, equals the oracle fed with the same arrays; writeimage
