@@ -50,18 +50,21 @@ ADAPTER_B200 = 8  # gvt::render::adapter::B200 (gravit_b200/host/api.h)
 
 # every symbol include/gvtb200.h declares (tests check that the library exports all of them)
 C_ABI_SYMBOLS = (
-    "gvtb200_init gvtb200_last_error gvtb200_current_device gvtb200_device_info gvtb200_set_tuning gvtb200_mesh_create gvtb200_mesh_destroy gvtb200_mesh_morton "
+    "gvtb200_init gvtb200_last_error gvtb200_current_device gvtb200_device_info gvtb200_set_tuning gvtb200_set_peer_timeout_ms gvtb200_mesh_create gvtb200_mesh_destroy gvtb200_mesh_morton "
     "gvtb200_mesh_stats gvtb200_trace gvtb200_intersect gvtb200_occluded gvtb200_scene_create gvtb200_scene_destroy "
     "gvtb200_scene_add_instance gvtb200_scene_set_lights gvtb200_scene_set_camera gvtb200_scene_set_film "
-    "gvtb200_scene_set_flags gvtb200_scene_commit gvtb200_scene_tlas_order gvtb200_camera_rays gvtb200_route "
-    "gvtb200_shuffle gvtb200_framebuffer_clear gvtb200_framebuffer_read gvtb200_render_frame gvtb200_render_frame_async "
+    "gvtb200_scene_set_flags gvtb200_scene_set_queue_limit gvtb200_scene_commit gvtb200_scene_tlas_order gvtb200_camera_rays gvtb200_route "
+    "gvtb200_shuffle gvtb200_framebuffer_clear gvtb200_framebuffer_read gvtb200_framebuffer_read_rows gvtb200_render_frame gvtb200_render_frame_async "
     "gvtb200_render_frame_tiles gvtb200_scene_set_stream gvtb200_launch_count gvtb200_scene_sync gvtb200_scene_counters gvtb200_scene_profile_counters gvtb200_scene_profile_launches gvtb200_scene_launch_records gvtb200_scene_device_framebuffer "
     "gvtb200_framebuffer_clamp gvtb200_scene_last_timing gvtb200_domain_set_owner gvtb200_domain_begin_frame "
     "gvtb200_domain_drain_local gvtb200_domain_export gvtb200_domain_import gvtb200_domain_pending "
     "gvtb200_p2p_export gvtb200_p2p_attach gvtb200_p2p_detach gvtb200_image_frame_p2p gvtb200_domain_round_p2p gvtb200_domain_composite_p2p "
-    "gvtb200_domain_async_reset gvtb200_domain_async_step"
+    "gvtb200_domain_frame_persist gvtb200_domain_persist_config gvtb200_domain_persist_stats gvtb200_domain_set_servers "
+    "gvtb200_scene_set_instance_mesh gvtb200_mesh_export gvtb200_mesh_import"
 ).split()
-PEER_DESC_BYTES = 64 * 4 + 8 * 4 + 8 + 8 + 4 + 4  # sizeof(gvtb200_peer_desc)
+PEER_DESC_BYTES = 64 * 4 + 8 * 4 + 8 + 8 + 8 + 4 + 4  # sizeof(gvtb200_peer_desc)
+MESH_DESC_BYTES = 6 * 64 + 6 * 8 + 6 * 8 + 8 + 32 + 16 + 8  # sizeof(gvtb200_mesh_desc)
+IMPORT_COPY, IMPORT_MAP = 0, 1
 
 
 class EngineError(RuntimeError):
@@ -107,6 +110,7 @@ def lib():
         L.gvtb200_scene_set_film.argtypes = [vp, i32, i32]
         L.gvtb200_scene_set_flags.argtypes = [vp, u32, u32]
         L.gvtb200_scene_commit.argtypes = [vp]
+        L.gvtb200_scene_set_queue_limit.argtypes = [vp, sz]
         L.gvtb200_scene_tlas_order.argtypes = [vp, vp, vp]
         L.gvtb200_camera_rays.argtypes = [vp, vp, sz]
         L.gvtb200_route.argtypes = [vp, vp, sz, i32, vp, vp]
@@ -114,6 +118,7 @@ def lib():
         L.gvtb200_framebuffer_clear.argtypes = [vp]
         L.gvtb200_framebuffer_read.argtypes = [vp, vp, sz]
         L.gvtb200_framebuffer_clamp.argtypes = [vp]
+        L.gvtb200_framebuffer_read_rows.argtypes = [vp, vp, i32, i32, i32, i32]
         L.gvtb200_render_frame.argtypes = [vp, i32, i32, vp, vp]
         L.gvtb200_render_frame_async.argtypes = [vp, i32, i32]
         L.gvtb200_scene_sync.argtypes = [vp]
@@ -138,8 +143,14 @@ def lib():
         L.gvtb200_image_frame_p2p.argtypes = [vp, i32, i32, i32, i32, i32]
         L.gvtb200_domain_round_p2p.argtypes = [vp, i32, vp]
         L.gvtb200_domain_composite_p2p.argtypes = [vp, i32]
-        L.gvtb200_domain_async_reset.argtypes = [vp]
-        L.gvtb200_domain_async_step.argtypes = [vp, vp, vp, vp]
+        L.gvtb200_set_peer_timeout_ms.argtypes = [i32]
+        L.gvtb200_domain_frame_persist.argtypes = [vp, i32, i32]
+        L.gvtb200_domain_persist_config.argtypes = [vp, i32, i32]
+        L.gvtb200_domain_persist_stats.argtypes = [vp, vp, vp, vp, i32]
+        L.gvtb200_domain_set_servers.argtypes = [vp, vp, vp, i32]
+        L.gvtb200_scene_set_instance_mesh.argtypes = [vp, i32, vp]
+        L.gvtb200_mesh_export.argtypes = [vp, vp]
+        L.gvtb200_mesh_import.argtypes = [vp, i32, vp]
         _lib = L
     return _lib
 
@@ -313,6 +324,24 @@ class Mesh:
         except Exception:
             pass
 
+    def export(self):
+        """gvtb200_mesh_desc as bytes: lets another rank import this mesh's BLAS (replica or NVLink mapping)."""
+        buf = C.create_string_buffer(MESH_DESC_BYTES)
+        check(lib().gvtb200_mesh_export(self.h, buf))
+        return buf.raw
+
+    @classmethod
+    def from_desc(cls, desc, mode=IMPORT_COPY):
+        """The BLAS another rank built: mode IMPORT_COPY = replica in this GPU's HBM, IMPORT_MAP = traverse the owner's arrays."""
+        desc = bytes(desc)
+        if len(desc) != MESH_DESC_BYTES:
+            raise EngineError(f"expected a {MESH_DESC_BYTES}-byte mesh descriptor, got {len(desc)} bytes")
+        m = cls.__new__(cls)
+        m.h = C.c_void_p()
+        m.nv = m.nf = 0
+        check(lib().gvtb200_mesh_import(C.c_char_p(desc), mode, C.byref(m.h)))
+        return m
+
     def morton(self):
         codes, order = np.zeros(self.nf, np.uint32), np.zeros(self.nf, np.uint32)
         check(lib().gvtb200_mesh_morton(self.h, _fp(codes), _fp(order)))
@@ -393,6 +422,13 @@ class EngineScene:
 
     def fb_clear(self):
         check(lib().gvtb200_framebuffer_clear(self.h))
+
+    def fb_read_rows(self, host_ptr, tile_rows, index, stride, src_rank=-1):
+        """This rank's row tiles of the final image into a full-size host image (asynchronous)."""
+        check(lib().gvtb200_framebuffer_read_rows(self.h, C.c_void_p(host_ptr), tile_rows, index, stride, src_rank))
+
+    def set_queue_limit(self, max_rays):
+        check(lib().gvtb200_scene_set_queue_limit(self.h, max_rays))
 
     def fb_clamp(self):
         check(lib().gvtb200_framebuffer_clamp(self.h))
@@ -504,14 +540,40 @@ class EngineScene:
         check(lib().gvtb200_domain_round_p2p(self.h, rnd, C.byref(p)))
         return p.value
 
-    def domain_async_reset(self):
-        check(lib().gvtb200_domain_async_reset(self.h))
+    def domain_frame_persist(self, root=0, tile_rows=8):
+        """One whole DomainScheduler frame as one persistent kernel per rank (asynchronous; sync() reports errors)."""
+        check(lib().gvtb200_domain_frame_persist(self.h, root, tile_rows))
 
-    def domain_async_step(self):
-        """One non-blocking step of the asynchronous DomainScheduler: (busy, sent, received)."""
-        b, s_, r = C.c_int(0), C.c_uint64(0), C.c_uint64(0)
-        check(lib().gvtb200_domain_async_step(self.h, C.byref(b), C.byref(s_), C.byref(r)))
-        return bool(b.value), int(s_.value), int(r.value)
+    def domain_persist_config(self, grid_ctas=0, shade_at=8):
+        check(lib().gvtb200_domain_persist_config(self.h, grid_ctas, shade_at))
+
+    def domain_persist_stats(self, n_instances=0):
+        """(busy ms of this rank, rays its inbox received, per-instance wide-node visits of a counted frame or None)."""
+        busy, rays = C.c_double(0), C.c_uint64(0)
+        load = np.zeros(n_instances, np.uint64) if n_instances else None
+        check(lib().gvtb200_domain_persist_stats(self.h, C.byref(busy), C.byref(rays), _fp(load), n_instances))
+        return busy.value, int(rays.value), load
+
+    def domain_set_servers(self, ranks=None, weights=None):
+        """ranks: (n_instances, <= 4) serving ranks per instance (-1 = unused), weights: the same shape or None."""
+        if ranks is None:
+            check(lib().gvtb200_domain_set_servers(self.h, None, None, 0))
+            return
+        r = np.full((len(ranks), 4), -1, np.int32)
+        w = np.zeros((len(ranks), 4), np.float32)
+        for i, row in enumerate(ranks):
+            for j, x in enumerate(row):
+                r[i, j] = x
+                w[i, j] = 1.0 if weights is None else weights[i][j]
+        check(lib().gvtb200_domain_set_servers(self.h, _fp(r), _fp(w), len(r)))
+
+    def set_instance_mesh(self, instance, mesh):
+        check(lib().gvtb200_scene_set_instance_mesh(self.h, instance, mesh.h if mesh is not None else None))
+        if mesh is not None:
+            self._keep_extra = getattr(self, "_keep_extra", []) + [mesh]
+
+    def commit(self):
+        check(lib().gvtb200_scene_commit(self.h))
 
     def domain_composite_p2p(self, root=0):
         check(lib().gvtb200_domain_composite_p2p(self.h, root))

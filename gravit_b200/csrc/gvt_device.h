@@ -110,6 +110,7 @@ struct RayQueue {
   int4 *c3;        // id, depth, w (bits), type
   int *inst;       // instance the ray is queued for
   unsigned *count; // device counter
+  unsigned *ready; // inbound queues of the persistent DomainScheduler only: slot i holds the frame number once its ray is complete
   unsigned cap;
 };
 

@@ -2,6 +2,7 @@
 // order, the top-level instance BVH build (a restatement of data/accel/BVH.cpp, it is O(instances) setup work) and
 // the camera basis (gvtCamera.cpp:89-171).  There is NO CPU ray-tracing path in this library.
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -20,11 +21,23 @@ static_assert(sizeof(gvtb200_ray) == 80, "gvtb200_ray must match gvt::render::ac
 namespace {
 
 thread_local std::string t_err;
-int g_device = -1;
-int g_sms = 0;
-int g_trace_blocks_per_sm[2] = { 0, 0 };
-unsigned long long g_launches = 0; // kernels launched by this library (bench.py reports it)
+// One process may drive several GPUs (one host thread per GPU: the C++ multi-GPU tracers of host/api.cpp): gvtb200_init
+// selects the device of the CALLING THREAD, every handle remembers the device it was created on, and every call on a
+// handle switches to that device first.
+#define GVT_MAX_DEVICES 16
+struct DevState {
+  bool ready = false;
+  int sms = 0;
+  int trace_bps[2] = { 0, 0 };   // CTAs per SM of k_trace<false/true>
+  int persist_bps[2] = { 0, 0 }; // CTAs per SM of k_persist<false/true>
+};
+DevState g_dev[GVT_MAX_DEVICES];
+int g_device = -1;                 // the device of the last successful gvtb200_init of the process
+thread_local int t_device = -1;    // the device of this thread's last gvtb200_init
+inline int cur_device() { return t_device >= 0 ? t_device : g_device; }
+std::atomic<unsigned long long> g_launches{ 0 }; // kernels launched by this library (bench.py reports it)
 #define LAUNCHED(n) (g_launches += (n))
+unsigned long long g_peer_timeout_ns = 4000000000ull; // gvtb200_set_peer_timeout_ms
 
 int fail(int code, const char *fmt, ...) {
   char buf[512];
@@ -44,7 +57,7 @@ int fail(int code, const char *fmt, ...) {
   } while (0)
 #define NEED_INIT()                                                                                                      \
   do {                                                                                                                   \
-    if (g_device < 0) return fail(GVTB200_ERR_NO_DEVICE, "gvtb200_init has not succeeded: no CUDA device (no CPU fallback)"); \
+    if (cur_device() < 0) return fail(GVTB200_ERR_NO_DEVICE, "gvtb200_init has not succeeded: no CUDA device (no CPU fallback)"); \
   } while (0)
 
 inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)std::max<size_t>(1, (n + threads - 1) / threads); }
@@ -69,11 +82,11 @@ struct QueueMem {
   int4 *hit = nullptr; // extra 16-byte column (hit queues only)
   void *slab = nullptr;
   QueueMem() { memset(&q, 0, sizeof(q)); }
-  cudaError_t ensure(size_t cap, bool with_hit = false) {
+  cudaError_t ensure(size_t cap, bool with_hit = false, bool with_ready = false) {
     if (cap < 32) cap = 32;
-    if (slab && q.cap >= cap && (!with_hit || hit)) return cudaSuccess;
+    if (slab && q.cap >= cap && (!with_hit || hit) && (!with_ready || q.ready)) return cudaSuccess;
     release();
-    size_t bytes = cap * (with_hit ? 84 : 68) + 256;
+    size_t bytes = cap * ((with_hit ? 84 : 68) + (with_ready ? 4 : 0)) + 256;
     cudaError_t e = cudaMalloc(&slab, bytes);
     if (e != cudaSuccess) {
       slab = nullptr;
@@ -86,7 +99,12 @@ struct QueueMem {
     q.c2 = (float4 *)p, p += cap * 16;
     q.c3 = (int4 *)p, p += cap * 16;
     if (with_hit) hit = (int4 *)p, p += cap * 16;
-    q.inst = (int *)p;
+    q.inst = (int *)p, p += cap * 4;
+    if (with_ready) {
+      q.ready = (unsigned *)p;
+      e = cudaMemset(q.ready, 0, cap * 4); // frame numbers start at 1
+      if (e != cudaSuccess) return e;
+    }
     q.cap = (unsigned)cap;
     return cudaMemset(q.count, 0, 256);
   }
@@ -126,7 +144,11 @@ struct HBox {
 // handles
 // =============================================================================================================
 struct gvtb200_mesh_s {
-  unsigned nv = 0, nf = 0;
+  int device = 0;
+  unsigned nv = 0, nf = 0, n_mats = 0;
+  bool imported = false;           // gvtb200_mesh_import: a replica (own copy) or a mapping of another rank's BLAS
+  void *ipc_opened[6] = {};        // cudaIpcOpenMemHandle results kept open (mapped import)
+  bool borrowed[6] = {};           // arrays that belong to another mesh of this process (mapped import by pointer)
   float4 *d_nodes = nullptr, *d_tris = nullptr, *d_normals = nullptr, *d_vcolors = nullptr, *d_mats = nullptr;
   int4 *d_faces = nullptr;
   uint32_t *d_keys_unsorted = nullptr, *d_sorted_faces = nullptr;
@@ -161,6 +183,7 @@ struct TNodeHost {
 } // namespace
 
 struct gvtb200_scene_s {
+  int device = 0;
   std::vector<InstHost> inst;
   std::vector<gvtb200_light> lights;
   float eye[3] = { 0, 0, 1 }, focus[3] = { 0, 0, 0 }, up[3] = { 0, 1, 0 };
@@ -170,6 +193,7 @@ struct gvtb200_scene_s {
   uint32_t flags = 0, seed = 0;
   int rank = 0, world = 1;
   bool committed = false, profile = false;
+  size_t queue_limit = 0; // gvtb200_scene_set_queue_limit: rays per queue (0 = sized for the frame)
   // TLAS
   std::vector<TNodeHost> tnodes;
   std::vector<int> work, sorted_ids;
@@ -198,6 +222,8 @@ struct gvtb200_scene_s {
   float *d_t = nullptr;
   uint4 *d_aos = nullptr;
   size_t aos_cap = 0, route_cap = 0;
+  float4 *d_rows = nullptr; // staging of gvtb200_framebuffer_read_rows
+  size_t rows_cap = 0;
   float last_frame_ms = 0.f, last_kernel_ms[3] = { 0, 0, 0 };
   bool timing_valid = false;
   // NVLink peer path (gvtb200_p2p_*): this rank's shared objects and the peers' objects mapped with CUDA IPC
@@ -208,15 +234,16 @@ struct gvtb200_scene_s {
     QueueMem inbox[2];           // inbound ray queues, alternated by exchange rounds
     Mailbox *d_mail = nullptr;
     RayQueue *d_peer_inbox = nullptr; // [2][world]
-    // asynchronous DomainScheduler: the two inbound slabs are carved into one region per producer
-    unsigned *d_out_count = nullptr;  // [GVT_P2P_MAX] rays this rank has stored into its region at each peer (this frame)
-    RayQueue *d_async_peer = nullptr; // [world] this rank's region in rank r's inbound area; .count -> d_out_count[r]
-    RayQueue *d_async_mine = nullptr; // [world] rank p's region in this rank's inbound area
-    unsigned async_head[GVT_P2P_MAX] = {}; // rays consumed per producer (this frame)
-    unsigned async_region_cap = 0;
-    bool async_first = false;
-    QueueMem q_local;                 // the camera rays this rank kept (gvtb200_domain_begin_frame), consumed in slices
-    unsigned local_total = 0, local_done = 0, async_chunk = 262144;
+    bool private_box = false;         // mailbox + inbox made for a single-rank persistent frame (nothing exported)
+    // persistent DomainScheduler (gvtb200_domain_frame_persist)
+    float4 *d_scr2 = nullptr;         // per-thread backing store of rays made inside the kernel
+    int4 *d_scr3 = nullptr;
+    size_t scr_cap = 0;
+    uint4 *d_servers = nullptr;       // per instance: serving ranks + cumulative weights (gvtb200_domain_set_servers)
+    std::vector<uint4> servers;
+    unsigned long long *d_inst_load = nullptr; // wide nodes visited per instance (counted frames)
+    int grid_limit = 0;               // CTAs of the persistent kernel (0 = fill the GPU); the single-GPU tests run several ranks on one device
+    int shade_at = 8;
     float *peer_fb[GVT_P2P_MAX] = {};
     PeerMail mail;
     void *opened[GVT_P2P_MAX][4] = {}; // cudaIpcOpenMemHandle results (closed on detach)
@@ -246,31 +273,46 @@ int scan_inplace(unsigned *d, size_t n, std::vector<unsigned *> &levels, size_t 
 
 TraceTune g_tune = { 16, 20, 2, 2 };
 
-int trace_grid(bool count) {
+int trace_grid(int dev, bool count) {
+  DevState &D = g_dev[dev];
   int idx = count ? 1 : 0;
-  if (!g_trace_blocks_per_sm[idx]) {
+  if (!D.trace_bps[idx]) {
     int nb = 0;
     if (count)
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true>, TRACE_THREADS, 0);
     else
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false>, TRACE_THREADS, 0);
-    g_trace_blocks_per_sm[idx] = std::max(1, nb);
-    if (const char *e = getenv("GVTB200_TRACE_BLOCKS_PER_SM")) g_trace_blocks_per_sm[idx] = std::max(1, std::min(nb, atoi(e)));
+    D.trace_bps[idx] = std::max(1, nb);
+    if (const char *e = getenv("GVTB200_TRACE_BLOCKS_PER_SM")) D.trace_bps[idx] = std::max(1, std::min(nb, atoi(e)));
   }
-  return g_sms * g_trace_blocks_per_sm[idx];
+  return D.sms * D.trace_bps[idx];
+}
+int persist_grid(int dev, bool count) {
+  DevState &D = g_dev[dev];
+  int idx = count ? 1 : 0;
+  if (!D.persist_bps[idx]) {
+    int nb = 0;
+    if (count)
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_persist<true>, TRACE_THREADS, 0);
+    else
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_persist<false>, TRACE_THREADS, 0);
+    D.persist_bps[idx] = std::max(1, nb);
+    if (const char *e = getenv("GVTB200_PERSIST_BLOCKS_PER_SM")) D.persist_bps[idx] = std::max(1, std::min(nb, atoi(e)));
+  }
+  return D.sms * D.persist_bps[idx];
 }
 
-void launch_trace(bool count, const FrameParams &fp, const SceneDev &sd, const TraceQueues &tq, int mode, cudaStream_t st) {
-  int grid = trace_grid(count);
+void launch_trace(int dev, bool count, const FrameParams &fp, const SceneDev &sd, const TraceQueues &tq, int mode, cudaStream_t st) {
+  int grid = trace_grid(dev, count);
   LAUNCHED(1);
   if (count)
     k_trace<true><<<grid, TRACE_THREADS, 0, st>>>(fp, sd, tq, mode, g_tune);
   else
     k_trace<false><<<grid, TRACE_THREADS, 0, st>>>(fp, sd, tq, mode, g_tune);
 }
-void launch_shade(const FrameParams &fp, const SceneDev &sd, const ShadeQueues &sq, int mode, cudaStream_t st) {
+void launch_shade(int dev, const FrameParams &fp, const SceneDev &sd, const ShadeQueues &sq, int mode, cudaStream_t st) {
   LAUNCHED(1);
-  k_shade<<<g_sms * 8, 256, 0, st>>>(fp, sd, sq, mode);
+  k_shade<<<g_dev[dev].sms * 8, 256, 0, st>>>(fp, sd, sq, mode);
 }
 
 RayQueue null_queue(unsigned *count) {
@@ -431,33 +473,42 @@ int gvtb200_init(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {
-    g_device = -1;
+    t_device = -1;
     return fail(GVTB200_ERR_NO_DEVICE, "no CUDA device: %s (this library has no CPU fallback)",
                 e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
   }
-  if (device < 0 || device >= n) return fail(GVTB200_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  if (device < 0 || device >= n || device >= GVT_MAX_DEVICES) return fail(GVTB200_ERR_INVALID, "device %d out of range (0..%d)", device, std::min(n, GVT_MAX_DEVICES) - 1);
   CU(cudaSetDevice(device));
   cudaDeviceProp p;
   CU(cudaGetDeviceProperties(&p, device));
   if (p.major < 10) return fail(GVTB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
-  g_sms = p.multiProcessorCount;
-  g_device = device;
-  g_trace_blocks_per_sm[0] = g_trace_blocks_per_sm[1] = 0;
+  DevState &D = g_dev[device];
+  D = DevState();
+  D.sms = p.multiProcessorCount;
   if (const char *e = getenv("GVTB200_TUNE")) { // "refill_at,exit_at,postpone_num" (measurement hook)
     int a = 0, b = 0, c = 0, d = 1;
     if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &d) >= 3 && gvtb200_set_tuning(a, b, c, d)) return GVTB200_ERR_INVALID;
   }
+  if (const char *e = getenv("GVTB200_PEER_TIMEOUT_MS")) gvtb200_set_peer_timeout_ms(atoi(e));
   CU(cudaFree(0));
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { // keep up to 8 GiB of freed build scratch in the pool
     unsigned long long keep = 8ull << 30;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
+  D.ready = true;
+  t_device = device;
+  g_device = device;
   return GVTB200_OK;
 }
 
 const char *gvtb200_last_error(void) { return t_err.c_str(); }
-int gvtb200_current_device(void) { return g_device; }
+int gvtb200_current_device(void) { return cur_device(); }
+int gvtb200_set_peer_timeout_ms(int ms) {
+  if (ms < 1) return fail(GVTB200_ERR_INVALID, "timeout %d ms", ms);
+  g_peer_timeout_ns = (unsigned long long)ms * 1000000ull;
+  return GVTB200_OK;
+}
 
 int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num, int node_burst) {
   if (refill_at < 1 || refill_at > 32 || exit_at < 1 || exit_at > 32 || postpone_num < 0 || postpone_num > 8 || node_burst < 1 || node_burst > 64)
@@ -470,7 +521,7 @@ int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num, int node_bu
 int gvtb200_device_info(int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor) {
   NEED_INIT();
   cudaDeviceProp p;
-  CU(cudaGetDeviceProperties(&p, g_device));
+  CU(cudaGetDeviceProperties(&p, cur_device()));
   if (sm_count) *sm_count = p.multiProcessorCount;
   if (hbm_bytes) *hbm_bytes = p.totalGlobalMem;
   if (cc_major) *cc_major = p.major;
@@ -483,6 +534,14 @@ int gvtb200_device_info(int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc
 // =============================================================================================================
 int gvtb200_mesh_destroy(gvtb200_mesh m) {
   if (!m) return GVTB200_OK;
+  cudaSetDevice(m->device);
+  { // arrays of an imported mesh may belong to the owner (mapped by pointer or by IPC handle)
+    void **arr[6] = { (void **)&m->d_nodes, (void **)&m->d_tris, (void **)&m->d_faces, (void **)&m->d_normals, (void **)&m->d_vcolors, (void **)&m->d_mats };
+    for (int k = 0; k < 6; ++k) {
+      if (m->ipc_opened[k]) cudaIpcCloseMemHandle(m->ipc_opened[k]), *arr[k] = nullptr;
+      if (m->borrowed[k]) *arr[k] = nullptr;
+    }
+  }
   dfree(m->d_nodes), dfree(m->d_tris), dfree(m->d_normals), dfree(m->d_vcolors), dfree(m->d_mats), dfree(m->d_faces);
   dfree(m->d_keys_unsorted), dfree(m->d_sorted_faces);
   dfree(m->d_inst), dfree(m->d_blas), dfree(m->d_ctr), dfree(m->d_work), dfree(m->d_aos), dfree(m->d_hits);
@@ -729,10 +788,11 @@ int gvtb200_mesh_create(const float *vertices, uint32_t n_vertices, const uint32
   if (face_mat)
     for (uint32_t i = 0; i < n_faces; ++i)
       if (face_mat[i] >= (int32_t)n_mats) return fail(GVTB200_ERR_INVALID, "face %u references material %d >= %u", i, face_mat[i], n_mats);
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(cur_device()));
   gvtb200_mesh m = new gvtb200_mesh_s();
   memset(&m->blas, 0, sizeof(Blas));
-  m->nv = n_vertices, m->nf = n_faces;
+  m->device = cur_device();
+  m->nv = n_vertices, m->nf = n_faces, m->n_mats = (mats && n_mats && face_mat) ? n_mats : 0;
   int rc;
 #define CUM(expr)                                                                                                        \
   do {                                                                                                                   \
@@ -790,6 +850,7 @@ int gvtb200_mesh_create(const float *vertices, uint32_t n_vertices, const uint32
 int gvtb200_mesh_morton(gvtb200_mesh m, uint32_t *codes, uint32_t *sorted_faces) {
   NEED_INIT();
   if (!m) return fail(GVTB200_ERR_INVALID, "mesh is NULL");
+  if (m->imported) return fail(GVTB200_ERR_INVALID, "an imported mesh holds no build records");
   if (codes && m->nf) CU(cudaMemcpy(codes, m->d_keys_unsorted, (size_t)m->nf * 4, cudaMemcpyDeviceToHost));
   if (sorted_faces && m->nf) CU(cudaMemcpy(sorted_faces, m->d_sorted_faces, (size_t)m->nf * 4, cudaMemcpyDeviceToHost));
   return GVTB200_OK;
@@ -816,7 +877,7 @@ static int gvtb200_intersect_impl(gvtb200_mesh m, const gvtb200_ray *rays, size_
   if (!m) return fail(GVTB200_ERR_INVALID, "mesh is NULL");
   if (n == 0) return GVTB200_OK;
   if (n > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "too many rays");
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(m->device));
   if (int rc = mesh_adapter_ctx(m)) return rc;
   if (int rc = upload_rays(rays, n, m->d_aos, m->aos_cap, m->q_in, 0, m->stream)) return rc;
   if (m->hits_cap < n) {
@@ -858,7 +919,7 @@ int gvtb200_trace(gvtb200_mesh m, gvtb200_ray *rays, size_t n_rays, size_t begin
   if (n == 0) return GVTB200_OK;
   if (!rays || (moved_cap && !moved)) return fail(GVTB200_ERR_INVALID, "NULL rays/moved");
   if (n * (size_t)(1 + n_lights) > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "too many rays in one call");
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(m->device));
   if (int rc = mesh_adapter_ctx(m)) return rc;
   cudaStream_t st = m->stream;
   int max_depth = 1;
@@ -896,13 +957,13 @@ int gvtb200_trace(gvtb200_mesh m, gvtb200_ray *rays, size_t n_rays, size_t begin
     // closest-hit wave: misses -> moved, hits -> hit queue
     tq.in = qa->q, tq.hq = m->q_hit.q, tq.hit = m->q_hit.hit, tq.mvq = m->q_mv.q, tq.exq = null_queue(m->d_work + 2), tq.fin = m->q_fin.q;
     tq.work = m->d_work;
-    launch_trace(false, fp, sd, tq, 1, st);
+    launch_trace(m->device, false, fp, sd, tq, 1, st);
     // shading: shadow rays -> q_sh, bounces -> qb, final states -> fin
     sq.hq = m->q_hit.q, sq.hit = m->q_hit.hit, sq.shq = m->q_sh.q, sq.nxq = qb->q, sq.fin = m->q_fin.q;
-    launch_shade(fp, sd, sq, 1, st);
+    launch_shade(m->device, fp, sd, sq, 1, st);
     // shadow wave: unoccluded -> moved
     tq.in = m->q_sh.q, tq.hq = null_queue(m->d_work + 3), tq.hit = nullptr, tq.work = m->d_work + 1;
-    launch_trace(false, fp, sd, tq, 1, st);
+    launch_trace(m->device, false, fp, sd, tq, 1, st);
     std::swap(qa, qb);
   }
   unsigned n_mv = 0;
@@ -937,8 +998,9 @@ int gvtb200_trace(gvtb200_mesh m, gvtb200_ray *rays, size_t n_rays, size_t begin
 int gvtb200_scene_create(gvtb200_scene *out) {
   NEED_INIT();
   if (!out) return fail(GVTB200_ERR_INVALID, "out is NULL");
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(cur_device()));
   gvtb200_scene s = new gvtb200_scene_s();
+  s->device = cur_device();
   memset(&s->tlas, 0, sizeof(Tlas));
   cudaError_t e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
   s->stream = s->own_stream;
@@ -959,7 +1021,7 @@ int gvtb200_scene_destroy(gvtb200_scene s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   gvtb200_p2p_detach(s);
   dfree(s->d_inst), dfree(s->d_blas), dfree(s->d_tnodes), dfree(s->d_tboxes), dfree(s->d_fb), dfree(s->d_ctr), dfree(s->d_work), dfree(s->d_peer);
-  dfree(s->d_export), dfree(s->d_next), dfree(s->d_t), dfree(s->d_aos);
+  dfree(s->d_export), dfree(s->d_next), dfree(s->d_t), dfree(s->d_aos), dfree(s->d_rows);
   s->q_a.release(), s->q_b.release(), s->q_sh.release(), s->q_ex.release(), s->q_tmp.release(), s->q_hit.release();
   for (auto &e : s->ev)
     if (e) cudaEventDestroy(e);
@@ -1004,6 +1066,11 @@ int gvtb200_scene_set_film(gvtb200_scene s, int w, int h) {
   s->W = w, s->H = h;
   return GVTB200_OK;
 }
+int gvtb200_scene_set_queue_limit(gvtb200_scene s, size_t max_rays) {
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  s->queue_limit = max_rays;
+  return GVTB200_OK;
+}
 int gvtb200_scene_set_flags(gvtb200_scene s, uint32_t flags, uint32_t seed) {
   if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
   s->flags = flags, s->seed = seed;
@@ -1013,7 +1080,7 @@ int gvtb200_scene_set_flags(gvtb200_scene s, uint32_t flags, uint32_t seed) {
 int gvtb200_scene_commit(gvtb200_scene s) {
   NEED_INIT();
   if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(s->device));
   const int n = (int)s->inst.size();
   s->tnodes.clear(), s->sorted_ids.clear();
   s->work.resize(n);
@@ -1094,13 +1161,13 @@ static int scene_fb(gvtb200_scene s) {
     NEED_INIT();                                                                                                         \
     if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");                                                          \
     if (!s->committed) return fail(GVTB200_ERR_INVALID, "scene not committed (gvtb200_scene_commit)");                  \
-    CU(cudaSetDevice(g_device));                                                                                         \
+    CU(cudaSetDevice(s->device));                                                                                         \
   } while (0)
 
 int gvtb200_camera_rays(gvtb200_scene s, gvtb200_ray *out, size_t cap) {
   NEED_INIT();
   if (!s || !out) return fail(GVTB200_ERR_INVALID, "NULL argument");
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(s->device));
   size_t n = (size_t)s->W * s->H * s->samples * s->samples;
   if (cap < n) return fail(GVTB200_ERR_CAPACITY, "need room for %zu rays", n);
   if (n > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "too many rays");
@@ -1182,7 +1249,7 @@ int gvtb200_shuffle(gvtb200_scene s, const gvtb200_ray *rays, size_t n, int from
 int gvtb200_framebuffer_clear(gvtb200_scene s) {
   NEED_INIT();
   if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(s->device));
   if (int rc = scene_fb(s)) return rc;
   CU(cudaMemsetAsync(s->d_fb, 0, s->fb_pix * 16, s->stream));
   CU(cudaStreamSynchronize(s->stream));
@@ -1191,7 +1258,7 @@ int gvtb200_framebuffer_clear(gvtb200_scene s) {
 int gvtb200_framebuffer_clamp(gvtb200_scene s) {
   NEED_INIT();
   if (!s || !s->d_fb) return fail(GVTB200_ERR_INVALID, "no framebuffer");
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(s->device));
   k_fb_clamp<<<blocks_for(s->fb_pix, 256), 256, 0, s->stream>>>(s->d_fb, s->fb_pix);
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaGetLastError());
@@ -1201,9 +1268,44 @@ int gvtb200_framebuffer_read(gvtb200_scene s, float *rgba, size_t n_floats) {
   NEED_INIT();
   if (!s || !s->d_fb || !rgba) return fail(GVTB200_ERR_INVALID, "no framebuffer / NULL argument");
   if (n_floats < s->fb_pix * 4) return fail(GVTB200_ERR_CAPACITY, "need %zu floats", s->fb_pix * 4);
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(s->device));
   CU(cudaMemcpyAsync(rgba, s->d_fb, s->fb_pix * 16, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
+  return GVTB200_OK;
+}
+
+// Parallel read-back: this rank's row tiles of the final image -- its own framebuffer (ImageScheduler: the rows it rendered)
+// or rank `src_rank`'s (DomainScheduler: the root's composited image, read over NVLink) -- go to the same rows of a full-size
+// host image over this rank's own PCIe link.  With one call per rank the host image (e.g. one shared pinned mapping) is
+// complete without funnelling the film through one GPU.
+int gvtb200_framebuffer_read_rows(gvtb200_scene s, float *rgba_image, int tile_rows, int tile_index, int tile_stride, int src_rank) {
+  NEED_SCENE();
+  if (!rgba_image || !s->d_fb) return fail(GVTB200_ERR_INVALID, "NULL image / no framebuffer");
+  if (tile_rows < 1 || tile_stride < 1 || tile_index < 0 || tile_index >= tile_stride)
+    return fail(GVTB200_ERR_INVALID, "bad tiling rows=%d index=%d stride=%d", tile_rows, tile_index, tile_stride);
+  const float4 *src = (const float4 *)s->d_fb;
+  if (src_rank >= 0) {
+    if (!s->p2p.attached || src_rank >= s->p2p.world) return fail(GVTB200_ERR_INVALID, "rank %d is not an attached peer", src_rank);
+    src = (const float4 *)s->p2p.peer_fb[src_rank];
+  }
+  RowTiles tiles;
+  tiles.row0 = 0, tiles.row1 = s->H, tiles.tile_rows = tile_rows, tiles.index = tile_index, tiles.stride = tile_stride;
+  const size_t rows = tiles_local_rows(tiles), n = rows * (size_t)s->W;
+  if (!n) return GVTB200_OK;
+  if (s->rows_cap < n) {
+    dfree(s->d_rows);
+    CU(dalloc(&s->d_rows, n));
+    s->rows_cap = n;
+  }
+  cudaStream_t st = s->stream;
+  k_rows_pack<<<std::min<unsigned>(g_dev[s->device].sms * 8, blocks_for(n, 256)), 256, 0, st>>>(src, s->d_rows, tiles, s->W);
+  LAUNCHED(1);
+  const size_t row_bytes = (size_t)s->W * 16, tile_bytes = row_bytes * tile_rows;
+  const size_t full = rows / tile_rows, rem = rows - full * tile_rows;
+  char *dst0 = (char *)rgba_image + (size_t)tile_index * tile_bytes;
+  if (full) CU(cudaMemcpy2DAsync(dst0, tile_bytes * tile_stride, s->d_rows, tile_bytes, tile_bytes, full, cudaMemcpyDeviceToHost, st));
+  if (rem) CU(cudaMemcpyAsync(dst0 + full * tile_bytes * tile_stride, (char *)s->d_rows + full * tile_bytes, rem * row_bytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaGetLastError());
   return GVTB200_OK;
 }
 
@@ -1243,17 +1345,17 @@ static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool tim
     tq.fin = null_queue(s->d_work + 5), tq.work = s->d_work;
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[2], s->stream));
     int rk = launch_rec_begin(s, 1);
-    launch_trace(s->profile, fp, sd, tq, 0, s->stream);
+    launch_trace(s->device, s->profile, fp, sd, tq, 0, s->stream);
     launch_rec_end(s, rk);
     sq.hq = s->q_hit.q, sq.hit = s->q_hit.hit, sq.shq = s->q_sh.q, sq.nxq = s->q_b.q, sq.fin = null_queue(s->d_work + 5);
     rk = launch_rec_begin(s, 2);
-    launch_shade(fp, sd, sq, 0, s->stream);
+    launch_shade(s->device, fp, sd, sq, 0, s->stream);
     launch_rec_end(s, rk);
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[3], s->stream));
     tq.gen.enabled = 0;
     tq.in = s->q_sh.q, tq.hq = null_queue(s->d_work + 3), tq.hit = nullptr, tq.work = s->d_work + 1;
     rk = launch_rec_begin(s, 3);
-    launch_trace(s->profile, fp, sd, tq, 0, s->stream);
+    launch_trace(s->device, s->profile, fp, sd, tq, 0, s->stream);
     launch_rec_end(s, rk);
     if (timed && wave == waves - 1) CU(cudaEventRecord(s->ev[4], s->stream));
     std::swap(s->q_a, s->q_b);
@@ -1264,11 +1366,15 @@ static int run_waves(gvtb200_scene s, const FrameParams &fp, int waves, bool tim
 static int frame_queues(gvtb200_scene s, size_t count) {
   size_t nl = std::max<size_t>(1, s->lights.size());
   if (count * nl > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "frame has too many rays for one queue");
-  CU(s->q_a.ensure(count));
-  CU(s->q_b.ensure(s->depth > 1 ? count : 32));
-  CU(s->q_sh.ensure(count * nl));
-  CU(s->q_hit.ensure(count, true));
-  CU(s->q_ex.ensure(s->world > 1 ? count : 32));
+  auto lim = [&](size_t n) { return s->queue_limit ? std::min(n, s->queue_limit) : n; };
+  if (s->queue_limit) // a smaller budget than what is allocated: start over
+    for (QueueMem *q : { &s->q_a, &s->q_b, &s->q_sh, &s->q_hit, &s->q_ex })
+      if (q->slab && q->q.cap > std::max<size_t>(32, s->queue_limit * nl)) q->release();
+  CU(s->q_a.ensure(lim(count)));
+  CU(s->q_b.ensure(s->depth > 1 ? lim(count) : 32));
+  CU(s->q_sh.ensure(lim(count * nl)));
+  CU(s->q_hit.ensure(lim(count), true));
+  CU(s->q_ex.ensure(s->world > 1 ? lim(count) : 32));
   return 0;
 }
 
@@ -1317,7 +1423,7 @@ static int frame_tiles(gvtb200_scene s, int row0, int row1, int tile_rows, int t
       if (int rc = run_waves(s, fp, std::max(1, s->depth), true, &gen)) return rc;
     } else {
       int rk = launch_rec_begin(s, 0);
-      k_camera_route<<<g_sms * 8, 256, 0, st>>>(fp, scene_dev(*s), tiles, count, s->q_a.q);
+      k_camera_route<<<g_dev[s->device].sms * 8, 256, 0, st>>>(fp, scene_dev(*s), tiles, count, s->q_a.q);
       LAUNCHED(1);
       launch_rec_end(s, rk);
       if (int rc = run_waves(s, fp, std::max(1, s->depth), true)) return rc;
@@ -1329,18 +1435,18 @@ static int frame_tiles(gvtb200_scene s, int row0, int row1, int tile_rows, int t
   } else {
     const int rank = s->p2p.rank;
     Mailbox *mine = s->p2p.d_mail, *root_mail = s->p2p.mail.m[p2p_root];
-    const unsigned grid = (unsigned)std::min<size_t>((size_t)g_sms * 8, std::max<size_t>(1, (count / std::max<size_t>(1, s2) + 255) / 256));
+    const unsigned grid = (unsigned)std::min<size_t>((size_t)g_dev[s->device].sms * 8, std::max<size_t>(1, (count / std::max<size_t>(1, s2) + 255) / 256));
     if (rank == p2p_root) {
       if (count && (phases & 2)) {
         k_rows_to_root<<<grid, 256, 0, st>>>((const float4 *)s->d_fb, (float4 *)s->d_fb, tiles, s->W, mine, nullptr, rank, seq);
         LAUNCHED(1);
       }
       if (phases & 4) {
-        k_p2p_wait<<<1, GVT_P2P_MAX, 0, st>>>(mine->done, s->p2p.world, rank, seq, &mine->err);
+        k_p2p_wait<<<1, GVT_P2P_MAX, 0, st>>>(mine->done, s->p2p.world, rank, seq, &mine->err, g_peer_timeout_ns);
         LAUNCHED(1);
       }
     } else if (phases & 2) {
-      k_p2p_wait<<<1, 32, 0, st>>>(&mine->go, 1, -1, seq, &mine->err);
+      k_p2p_wait<<<1, 32, 0, st>>>(&mine->go, 1, -1, seq, &mine->err, g_peer_timeout_ns);
       k_rows_to_root<<<grid, 256, 0, st>>>((const float4 *)s->d_fb, (float4 *)s->p2p.peer_fb[p2p_root], tiles, s->W, mine, root_mail, rank, seq);
       LAUNCHED(2);
     }
@@ -1364,20 +1470,35 @@ int gvtb200_scene_set_stream(gvtb200_scene s, void *cuda_stream) {
   return GVTB200_OK;
 }
 unsigned long long gvtb200_launch_count(void) { return g_launches; }
+// The reference never drops a ray (TracerBase.h:403-409 grows its queues): a frame during which any queue append found its
+// queue full, or a traversal stack overflowed, is reported as an error instead of a silently incomplete image.
+static int check_frame_errors(gvtb200_scene s) {
+  unsigned long long ov[2] = { 0, 0 }; // stack_overflows, queue_overflows are adjacent
+  CU(cudaMemcpyAsync(ov, &s->d_ctr->stack_overflows, sizeof(ov), cudaMemcpyDeviceToHost, s->stream));
+  unsigned perr = 0, merr = 0;
+  if (s->p2p.d_mail) {
+    CU(cudaMemcpyAsync(&perr, &s->p2p.d_mail->pc.err, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(&merr, &s->p2p.d_mail->err, 4, cudaMemcpyDeviceToHost, s->stream));
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  if (merr || (perr & 1u)) {
+    if (merr) CU(cudaMemset(&s->p2p.d_mail->err, 0, 4));
+    if (perr) CU(cudaMemset(&s->p2p.d_mail->pc.err, 0, 4));
+    return fail(GVTB200_ERR_CUDA, "NVLink peer path: rank %d waited more than %.1f s for a peer (frame %u)", s->p2p.rank, (double)g_peer_timeout_ns * 1e-9, s->p2p.seq);
+  }
+  if (ov[1] || (perr & 2u)) {
+    if (perr) CU(cudaMemset(&s->p2p.d_mail->pc.err, 0, 4));
+    return fail(GVTB200_ERR_CAPACITY, "%llu rays found a ray queue full during the frame (the image is incomplete)", ov[1]);
+  }
+  if (ov[0]) return fail(GVTB200_ERR_CAPACITY, "the traversal stack overflowed (GVT_BLAS_STACK = %d entries is too small for this BVH)", GVT_BLAS_STACK);
+  return GVTB200_OK;
+}
 int gvtb200_scene_sync(gvtb200_scene s) {
   NEED_INIT();
   if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
-  CU(cudaStreamSynchronize(s->stream));
-  CU(cudaGetLastError());
-  if (s->p2p.d_mail) {
-    unsigned err = 0;
-    CU(cudaMemcpy(&err, &s->p2p.d_mail->err, 4, cudaMemcpyDeviceToHost));
-    if (err) {
-      CU(cudaMemset(&s->p2p.d_mail->err, 0, 4));
-      return fail(GVTB200_ERR_CUDA, "NVLink peer path: rank %d waited more than 4 s for a peer's flag (frame %u)", s->p2p.rank, s->p2p.seq);
-    }
-  }
-  return GVTB200_OK;
+  CU(cudaSetDevice(s->device));
+  return check_frame_errors(s);
 }
 int gvtb200_scene_counters(gvtb200_scene s, gvtb200_counters *out) {
   static_assert(sizeof(gvtb200_counters) == sizeof(DevCounters), "counter layouts must match");
@@ -1392,14 +1513,12 @@ int gvtb200_render_frame(gvtb200_scene s, int row0, int row1, float *rgba_out, g
   if (rc) return rc;
   if (rgba_out) CU(cudaMemcpyAsync(rgba_out, s->d_fb, s->fb_pix * 16, cudaMemcpyDeviceToHost, s->stream));
   if (counters) CU(cudaMemcpyAsync(counters, s->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s->stream));
-  CU(cudaStreamSynchronize(s->stream));
-  CU(cudaGetLastError());
-  return GVTB200_OK;
+  return check_frame_errors(s);
 }
 int gvtb200_scene_profile_launches(gvtb200_scene s, int enable) {
   NEED_INIT();
   if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(s->device));
   if (enable && !s->d_snap) CU(dalloc(&s->d_snap, (size_t)gvtb200_scene_s::MAX_LAUNCH_REC));
   s->launch_prof = enable != 0;
   s->n_launch_rec = 0;
@@ -1408,7 +1527,7 @@ int gvtb200_scene_profile_launches(gvtb200_scene s, int enable) {
 int gvtb200_scene_launch_records(gvtb200_scene s, int cap, int *n, int32_t *kind, float *ms, gvtb200_counters *after) {
   NEED_INIT();
   if (!s || !n) return fail(GVTB200_ERR_INVALID, "NULL argument");
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(s->device));
   CU(cudaStreamSynchronize(s->stream));
   int k = std::min(cap, s->n_launch_rec);
   for (int i = 0; i < k; ++i) {
@@ -1427,7 +1546,7 @@ int gvtb200_scene_profile_counters(gvtb200_scene s, int enable) {
 int gvtb200_scene_device_framebuffer(gvtb200_scene s, void **d_rgba, void **cuda_stream) {
   NEED_INIT();
   if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
-  CU(cudaSetDevice(g_device));
+  CU(cudaSetDevice(s->device));
   if (int rc = scene_fb(s)) return rc;
   if (d_rgba) *d_rgba = s->d_fb;
   if (cuda_stream) *cuda_stream = (void *)s->stream;
@@ -1477,7 +1596,7 @@ int gvtb200_domain_begin_frame(gvtb200_scene s) {
   // every rank generates all camera rays and keeps those whose first instance it owns (DomainTracer.h:148-181)
   RowTiles tiles;
   tiles.row0 = 0, tiles.row1 = s->H, tiles.tile_rows = 1, tiles.index = 0, tiles.stride = 1;
-  k_camera_route<<<g_sms * 8, 256, 0, st>>>(fp, scene_dev(*s), tiles, count, s->q_a.q);
+  k_camera_route<<<g_dev[s->device].sms * 8, 256, 0, st>>>(fp, scene_dev(*s), tiles, count, s->q_a.q);
   LAUNCHED(1);
   CU(cudaGetLastError());
   s->timing_valid = false;
@@ -1503,7 +1622,7 @@ int gvtb200_domain_export(gvtb200_scene s, uint32_t *counts, void **d_export, si
   if (n_ex > s->q_ex.q.cap) return fail(GVTB200_ERR_CAPACITY, "export queue overflow (%u > %u)", n_ex, s->q_ex.q.cap);
   std::vector<unsigned> c(P, 0), off(P, 0);
   if (n_ex) {
-    k_export_count<<<g_sms * 4, 256, 0, st>>>(s->q_ex.q, s->d_inst, s->d_peer);
+    k_export_count<<<g_dev[s->device].sms * 4, 256, 0, st>>>(s->q_ex.q, s->d_inst, s->d_peer);
     CU(cudaMemcpyAsync(c.data(), s->d_peer, 4 * (size_t)P, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     for (int p = 1; p < P; ++p) off[p] = off[p - 1] + c[p - 1];
@@ -1513,7 +1632,7 @@ int gvtb200_domain_export(gvtb200_scene s, uint32_t *counts, void **d_export, si
       s->export_cap = n_ex;
     }
     CU(cudaMemcpyAsync(s->d_peer, off.data(), 4 * (size_t)P, cudaMemcpyHostToDevice, st));
-    k_export_pack<<<g_sms * 4, 256, 0, st>>>(s->q_ex.q, s->d_inst, s->d_peer, s->d_export);
+    k_export_pack<<<g_dev[s->device].sms * 4, 256, 0, st>>>(s->q_ex.q, s->d_inst, s->d_peer, s->d_export);
     CU(cudaMemsetAsync(s->q_ex.q.count, 0, 4, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
@@ -1560,7 +1679,7 @@ int gvtb200_domain_pending(gvtb200_scene s, uint64_t *n) {
 // =============================================================================================================
 // NVLink peer path
 // =============================================================================================================
-static RayQueue queue_at(void *slab, size_t cap) { // the layout QueueMem::ensure gives a slab (no hit column)
+static RayQueue queue_at(void *slab, size_t cap) { // the layout QueueMem::ensure gives an inbound slab (no hit column, ready column)
   RayQueue q;
   char *p = (char *)slab;
   q.count = (unsigned *)p, p += 256;
@@ -1568,38 +1687,40 @@ static RayQueue queue_at(void *slab, size_t cap) { // the layout QueueMem::ensur
   q.c1 = (float4 *)p, p += cap * 16;
   q.c2 = (float4 *)p, p += cap * 16;
   q.c3 = (int4 *)p, p += cap * 16;
-  q.inst = (int *)p;
+  q.inst = (int *)p, p += cap * 4;
+  q.ready = (unsigned *)p;
   q.cap = (unsigned)cap;
   return q;
 }
-// asynchronous DomainScheduler: region r of an inbound area (two slabs of `cap` rays each): regions alternate between the
-// slabs, (world + 1) / 2 per slab, each laid out like a queue of its own
-static unsigned async_region_cap(size_t cap, int world) {
-  const size_t per_slab = ((size_t)world + 1) / 2, bytes = (cap * 68 / per_slab) / 256 * 256;
-  if (bytes < 256 + 68 * 32) return 0;
-  return (unsigned)((bytes - 256) / 68 / 32 * 32);
+// capacity of an inbound queue: what one exchange round can bring (every camera ray with its shadow rays and its bounce),
+// and, for the persistent scheduler, everything a rank is handed in a whole frame
+static size_t inbox_capacity(const gvtb200_scene_s *s) {
+  const size_t nl = std::max<size_t>(1, s->lights.size());
+  const size_t frame = (size_t)s->W * s->H * s->samples * s->samples;
+  const size_t cap = std::min<size_t>(frame * (nl + 1) * (size_t)std::max(1, std::min(s->depth, 4)), (size_t)1 << 27);
+  return s->queue_limit ? std::max<size_t>(64, std::min(cap, s->queue_limit)) : cap;
 }
-static RayQueue async_region(void *slab0, void *slab1, size_t cap, int world, int r) {
-  const size_t per_slab = ((size_t)world + 1) / 2, bytes = (cap * 68 / per_slab) / 256 * 256;
-  char *base = (char *)((r & 1) ? slab1 : slab0) + 256 + (size_t)(r >> 1) * bytes;
-  return queue_at(base, async_region_cap(cap, world));
+static int p2p_own_objects(gvtb200_scene s, bool both_inboxes) {
+  if (int rc = scene_fb(s)) return rc;
+  const size_t cap = inbox_capacity(s);
+  if (cap > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "frame has too many rays for one queue");
+  for (int k = 0; k < 2; ++k) {
+    if (s->p2p.inbox[k].slab && s->p2p.inbox[k].q.cap != cap) s->p2p.inbox[k].release();
+    const bool used = s->world > 1 ? (k == 0 || both_inboxes) : (k == 0 && !both_inboxes); // only the DomainScheduler exchanges rays
+    CU(s->p2p.inbox[k].ensure(used ? cap : 32, false, true));
+  }
+  if (!s->p2p.d_mail) CU(dalloc(&s->p2p.d_mail, 1));
+  CU(cudaMemset(s->p2p.d_mail, 0, sizeof(Mailbox)));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
 }
 int gvtb200_p2p_export(gvtb200_scene s, int world, gvtb200_peer_desc *out) {
   NEED_SCENE();
   if (!out) return fail(GVTB200_ERR_INVALID, "out is NULL");
   if (world < 1 || world > GVT_P2P_MAX) return fail(GVTB200_ERR_INVALID, "world size %d outside 1..%d", world, GVT_P2P_MAX);
   if (s->p2p.attached) return fail(GVTB200_ERR_INVALID, "already attached: gvtb200_p2p_detach first");
-  if (int rc = scene_fb(s)) return rc;
-  const size_t nl = std::max<size_t>(1, s->lights.size());
-  const size_t cap = (size_t)s->W * s->H * s->samples * s->samples * nl;
-  if (cap > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "frame has too many rays for one queue");
-  for (int k = 0; k < 2; ++k) {
-    if (s->p2p.inbox[k].slab && s->p2p.inbox[k].q.cap != cap) s->p2p.inbox[k].release();
-    CU(s->p2p.inbox[k].ensure(s->world > 1 ? cap : 32)); // only the DomainScheduler exchanges rays
-  }
-  if (!s->p2p.d_mail) CU(dalloc(&s->p2p.d_mail, 1));
-  CU(cudaMemset(s->p2p.d_mail, 0, sizeof(Mailbox)));
-  CU(cudaStreamSynchronize(s->stream));
+  if (s->p2p.private_box) gvtb200_p2p_detach(s);
+  if (int rc = p2p_own_objects(s, true)) return rc;
   memset(out, 0, sizeof(*out));
   void *ptrs[4] = { s->d_fb, s->p2p.inbox[0].slab, s->p2p.inbox[1].slab, s->p2p.d_mail };
   uint8_t *handles[4] = { out->fb_handle, out->inbox_handle[0], out->inbox_handle[1], out->mail_handle };
@@ -1610,9 +1731,20 @@ int gvtb200_p2p_export(gvtb200_scene s, int world, gvtb200_peer_desc *out) {
     memcpy(handles[k], &h, 64);
     out->raw[k] = (uint64_t)(uintptr_t)ptrs[k];
   }
-  out->inbox_cap = s->p2p.inbox[0].q.cap, out->fb_pix = s->fb_pix, out->pid = (int32_t)getpid(), out->device = g_device;
+  out->inbox_cap = s->p2p.inbox[0].q.cap, out->inbox_cap1 = s->p2p.inbox[1].q.cap, out->fb_pix = s->fb_pix, out->pid = (int32_t)getpid(), out->device = s->device;
   s->p2p.exported = true;
   return GVTB200_OK;
+}
+// another device of this process: direct peer access (one host thread per GPU, no IPC)
+static int enable_peer(int self, int other) {
+  if (self == other) return 0;
+  int can = 0;
+  CU(cudaDeviceCanAccessPeer(&can, self, other));
+  if (!can) return fail(GVTB200_ERR_INVALID, "device %d cannot access device %d (no NVLink / PCIe peer path)", self, other);
+  cudaError_t e = cudaDeviceEnablePeerAccess(other, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(GVTB200_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", other, cudaGetErrorString(e));
+  (void)cudaGetLastError();
+  return 0;
 }
 int gvtb200_p2p_attach(gvtb200_scene s, int rank, int world, const gvtb200_peer_desc *all) {
   NEED_SCENE();
@@ -1621,9 +1753,7 @@ int gvtb200_p2p_attach(gvtb200_scene s, int rank, int world, const gvtb200_peer_
   if (world < 1 || world > GVT_P2P_MAX || rank < 0 || rank >= world) return fail(GVTB200_ERR_INVALID, "bad rank/world %d/%d", rank, world);
   if (s->world > 1 && (s->world != world || s->rank != rank)) return fail(GVTB200_ERR_INVALID, "rank/world differ from gvtb200_domain_set_owner (%d/%d)", s->rank, s->world);
   if (s->p2p.attached) return fail(GVTB200_ERR_INVALID, "already attached");
-  std::vector<RayQueue> table(2 * (size_t)world), async_peer((size_t)world), async_mine((size_t)world + 1);
-  if (!s->p2p.d_out_count) CU(dalloc(&s->p2p.d_out_count, GVT_P2P_MAX));
-  CU(cudaMemset(s->p2p.d_out_count, 0, GVT_P2P_MAX * sizeof(unsigned)));
+  std::vector<RayQueue> table(2 * (size_t)world);
   for (int r = 0; r < world; ++r) {
     const gvtb200_peer_desc &d = all[r];
     if (d.fb_pix != s->fb_pix) return fail(GVTB200_ERR_INVALID, "rank %d renders a different film (%llu vs %zu pixels)", r, (unsigned long long)d.fb_pix, s->fb_pix);
@@ -1631,9 +1761,9 @@ int gvtb200_p2p_attach(gvtb200_scene s, int rank, int world, const gvtb200_peer_
     if (r == rank) {
       ptrs[0] = s->d_fb, ptrs[1] = s->p2p.inbox[0].slab, ptrs[2] = s->p2p.inbox[1].slab, ptrs[3] = s->p2p.d_mail;
     } else if (d.pid == (int32_t)getpid()) {
-      // another scene of this process: same address space.  (A different device of the same process would need
-      // cudaDeviceEnablePeerAccess; one process per GPU is the supported layout.)
-      if (d.device != g_device) return fail(GVTB200_ERR_INVALID, "rank %d lives on device %d of this process: use one process per GPU", r, d.device);
+      // another scene of this process: same address space.  The same device (several simulated ranks on one GPU: the
+      // single-process tests) needs nothing; another device (one host thread per GPU) needs peer access.
+      if (int rc = enable_peer(s->device, d.device)) return rc;
       for (int k = 0; k < 4; ++k) ptrs[k] = (void *)(uintptr_t)d.raw[k];
     } else {
       const uint8_t *handles[4] = { d.fb_handle, d.inbox_handle[0], d.inbox_handle[1], d.mail_handle };
@@ -1649,37 +1779,28 @@ int gvtb200_p2p_attach(gvtb200_scene s, int rank, int world, const gvtb200_peer_
       }
     }
     s->p2p.peer_fb[r] = (float *)ptrs[0];
-    table[r] = queue_at(ptrs[1], d.inbox_cap), table[(size_t)world + r] = queue_at(ptrs[2], d.inbox_cap);
-    async_peer[r] = async_region(ptrs[1], ptrs[2], d.inbox_cap, world, rank); // where this rank writes at rank r
-    async_peer[r].count = s->p2p.d_out_count + r;                                // reserved with a local atomic
-    async_mine[r] = async_region(s->p2p.inbox[0].slab, s->p2p.inbox[1].slab, s->p2p.inbox[0].q.cap, world, r);
+    table[r] = queue_at(ptrs[1], d.inbox_cap), table[(size_t)world + r] = queue_at(ptrs[2], d.inbox_cap1);
     s->p2p.mail.m[r] = (Mailbox *)ptrs[3];
   }
   dfree(s->p2p.d_peer_inbox);
   CU(dalloc(&s->p2p.d_peer_inbox, table.size()));
   CU(cudaMemcpy(s->p2p.d_peer_inbox, table.data(), table.size() * sizeof(RayQueue), cudaMemcpyHostToDevice));
-  dfree(s->p2p.d_async_peer), dfree(s->p2p.d_async_mine);
-  CU(dalloc(&s->p2p.d_async_peer, (size_t)world));
-  CU(dalloc(&s->p2p.d_async_mine, (size_t)world + 1)); // entry `world`: q_local, set every frame
-  memset(&async_mine[(size_t)world], 0, sizeof(RayQueue));
-  CU(cudaMemcpy(s->p2p.d_async_peer, async_peer.data(), (size_t)world * sizeof(RayQueue), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(s->p2p.d_async_mine, async_mine.data(), ((size_t)world + 1) * sizeof(RayQueue), cudaMemcpyHostToDevice));
-  if (const char *e = getenv("GVTB200_ASYNC_CHUNK")) s->p2p.async_chunk = (unsigned)std::max(1024, atoi(e));
-  s->p2p.async_region_cap = async_region_cap(s->p2p.inbox[0].q.cap, world);
   s->p2p.rank = rank, s->p2p.world = world, s->p2p.seq = 0, s->p2p.attached = true;
   return GVTB200_OK;
 }
 int gvtb200_p2p_detach(gvtb200_scene s) {
   if (!s) return GVTB200_OK;
+  cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   for (auto &r : s->p2p.opened)
     for (auto &p : r) {
       if (p) cudaIpcCloseMemHandle(p);
       p = nullptr;
     }
-  dfree(s->p2p.d_peer_inbox), dfree(s->p2p.d_mail), dfree(s->p2p.d_out_count), dfree(s->p2p.d_async_peer), dfree(s->p2p.d_async_mine);
-  s->p2p.inbox[0].release(), s->p2p.inbox[1].release(), s->p2p.q_local.release();
-  s->p2p.exported = s->p2p.attached = false;
+  dfree(s->p2p.d_peer_inbox), dfree(s->p2p.d_mail), dfree(s->p2p.d_scr2), dfree(s->p2p.d_scr3), dfree(s->p2p.d_inst_load);
+  s->p2p.scr_cap = 0;
+  s->p2p.inbox[0].release(), s->p2p.inbox[1].release();
+  s->p2p.exported = s->p2p.attached = s->p2p.private_box = false;
   return GVTB200_OK;
 }
 int gvtb200_image_frame_p2p(gvtb200_scene s, int row0, int row1, int tile_rows, int root, int phases) {
@@ -1709,85 +1830,231 @@ int gvtb200_domain_round_p2p(gvtb200_scene s, int round, void **d_exported_total
   if (d_exported_total) *d_exported_total = (void *)&s->d_ctr->rays_exported;
   return GVTB200_OK;
 }
-int gvtb200_domain_async_reset(gvtb200_scene s) {
-  NEED_SCENE();
-  if (!s->p2p.attached || s->world < 2) return fail(GVTB200_ERR_INVALID, "needs gvtb200_domain_set_owner with world > 1 and gvtb200_p2p_attach");
-  if (!s->p2p.async_region_cap) return fail(GVTB200_ERR_CAPACITY, "film too small for %d inbound regions", s->p2p.world);
-  cudaStream_t st = s->stream;
-  CU(cudaMemsetAsync(s->p2p.d_out_count, 0, GVT_P2P_MAX * sizeof(unsigned), st));
-  CU(cudaMemsetAsync(s->p2p.d_mail->tail, 0, GVT_P2P_MAX * sizeof(unsigned), st));
-  memset(s->p2p.async_head, 0, sizeof(s->p2p.async_head));
-  s->p2p.async_first = true;
-  // both local queues take whatever can arrive in one step
-  const size_t cap = (size_t)s->p2p.async_region_cap * s->p2p.world, nl = std::max<size_t>(1, s->lights.size());
-  if (cap * nl > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "frame has too many rays for one queue");
-  const size_t frame = (size_t)s->W * s->H * s->samples * s->samples;
-  CU(s->q_a.ensure(std::max(cap, frame) + s->p2p.async_chunk));
-  CU(s->p2p.q_local.ensure(std::max(cap, frame) + s->p2p.async_chunk));
-  CU(s->q_b.ensure(std::max(cap, frame) + s->p2p.async_chunk)); // run_waves swaps q_a and q_b after every wave
-  CU(s->q_sh.ensure((std::max(cap, frame) + s->p2p.async_chunk) * nl));
-  CU(s->q_hit.ensure(std::max(cap, frame) + s->p2p.async_chunk, true));
-  CU(cudaStreamSynchronize(st)); // the peers may publish into this rank's tails once every rank has returned from here
-  return GVTB200_OK;
-}
-int gvtb200_domain_async_step(gvtb200_scene s, int *busy, uint64_t *sent, uint64_t *received) {
-  NEED_SCENE();
-  if (!busy || !sent || !received) return fail(GVTB200_ERR_INVALID, "NULL argument");
-  if (!s->p2p.attached || s->world < 2) return fail(GVTB200_ERR_INVALID, "needs gvtb200_domain_set_owner with world > 1 and gvtb200_p2p_attach");
-  cudaStream_t st = s->stream;
-  const int P = s->p2p.world, me = s->p2p.rank;
-  *busy = 1, *sent = 0, *received = 0;
-  FrameParams fp;
-  build_frame_params(*s, fp);
-  if (s->p2p.async_first) { // the camera rays gvtb200_domain_begin_frame kept: set them aside, they are consumed in slices
-    s->p2p.async_first = false;
-    std::swap(s->q_a, s->p2p.q_local);
-    unsigned n_local = 0;
-    CU(cudaMemcpyAsync(&n_local, s->p2p.q_local.q.count, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(s->p2p.d_async_mine + P, &s->p2p.q_local.q, sizeof(RayQueue), cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
-    s->p2p.local_total = std::min(n_local, s->p2p.q_local.q.cap), s->p2p.local_done = 0;
-  } else {
-    cudaError_t q = cudaStreamQuery(st);
-    if (q == cudaErrorNotReady) return GVTB200_OK; // the previous step is still running
-    CU(q);
-  }
-  unsigned tails[GVT_P2P_MAX], outc[GVT_P2P_MAX];
-  CU(cudaMemcpyAsync(tails, s->p2p.d_mail->tail, sizeof(tails), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(outc, s->p2p.d_out_count, sizeof(outc), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  AsyncGather g;
-  memset(&g, 0, sizeof(g));
-  const unsigned cap = s->p2p.async_region_cap;
-  unsigned total = 0;
-  bool work = false;
-  for (int p = 0; p < P; ++p) { // rays beyond a region's capacity were counted by the producer but not stored
-    const unsigned h = std::min(s->p2p.async_head[p], cap), t = p == me ? h : std::min(tails[p], cap);
-    g.head[p] = h, g.prefix[p] = total;
-    total += t - h;
-    if (p != me && tails[p] != s->p2p.async_head[p]) work = true, s->p2p.async_head[p] = tails[p];
-  }
-  const unsigned slice = std::min(s->p2p.async_chunk, s->p2p.local_total - s->p2p.local_done);
-  g.head[P] = s->p2p.local_done, g.prefix[P] = total;
-  total += slice, s->p2p.local_done += slice;
-  g.prefix[P + 1] = total;
-  if (slice) work = true;
-  if (work) {
-    CU(cudaMemcpyAsync(s->q_a.q.count, &total, 4, cudaMemcpyHostToDevice, st)); // pageable source: staged before the call returns
-    if (total) {
-      k_async_gather<<<std::min<unsigned>(g_sms * 8, blocks_for(total, 256)), 256, 0, st>>>(s->p2p.d_async_mine, g, P + 1, s->q_a.q);
-      LAUNCHED(1);
-      if (int rc = run_waves(s, fp, std::max(1, s->depth), false, nullptr, nullptr, s->p2p.d_async_peer)) return rc;
-      k_async_publish<<<1, GVT_P2P_MAX, 0, st>>>(s->p2p.mail, s->p2p.d_out_count, P, me);
-      LAUNCHED(1);
-    }
-    CU(cudaGetLastError());
+// ---- persistent DomainScheduler -----------------------------------------------------------------------------------------
+int gvtb200_domain_set_servers(gvtb200_scene s, const int32_t *ranks, const float *weights, int n) {
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  if (!ranks) { // back to "the owner serves its instances"
+    s->p2p.servers.clear();
     return GVTB200_OK;
   }
-  *busy = 0;
-  for (int p = 0; p < P; ++p) *sent += outc[p], *received += s->p2p.async_head[p];
+  if (n != (int)s->inst.size()) return fail(GVTB200_ERR_INVALID, "server table has %d entries, scene has %zu instances", n, s->inst.size());
+  std::vector<uint4> tab((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    unsigned packed = 0, cnt = 0;
+    double w[4] = { 0, 0, 0, 0 }, sum = 0;
+    for (int j = 0; j < 4; ++j) {
+      const int r = ranks[4 * i + j];
+      if (r < 0) continue;
+      if (r >= std::max(1, s->world) || r > 255) return fail(GVTB200_ERR_INVALID, "instance %d: server rank %d outside 0..%d", i, r, s->world - 1);
+      const double wj = weights ? (double)weights[4 * i + j] : 1.0;
+      if (!(wj > 0.0)) continue;
+      if (r == s->rank && !s->inst[i].mesh) return fail(GVTB200_ERR_INVALID, "instance %d: this rank is listed as a server but holds no BLAS for it", i);
+      packed |= (unsigned)r << (8 * cnt), w[cnt] = wj, sum += wj, ++cnt;
+    }
+    if (!cnt) return fail(GVTB200_ERR_INVALID, "instance %d has no server", i);
+    unsigned thr[3] = { 65536u, 65536u, 65536u };
+    double acc = 0;
+    for (unsigned j = 0; j + 1 < cnt; ++j) acc += w[j] / sum, thr[j] = (unsigned)std::min(65535.0, std::max(0.0, acc * 65536.0 + 0.5));
+    // the 16-bit hash h picks server #(thresholds <= h): unused thresholds are above every h
+    tab[i] = make_uint4(packed, std::min(thr[0], 65535u) | (std::min(thr[1], 65535u) << 16), thr[2], cnt);
+    if (cnt < 2) tab[i].y = 0xFFFFFFFFu;
+    else if (cnt < 3) tab[i].y |= 0xFFFF0000u;
+  }
+  s->p2p.servers = tab;
   return GVTB200_OK;
 }
+int gvtb200_scene_set_instance_mesh(gvtb200_scene s, int instance, gvtb200_mesh mesh) {
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  if (instance < 0 || instance >= (int)s->inst.size()) return fail(GVTB200_ERR_INVALID, "instance %d outside 0..%zu", instance, s->inst.size());
+  if (mesh && mesh->device != s->device) return fail(GVTB200_ERR_INVALID, "the mesh lives on device %d, the scene on device %d", mesh->device, s->device);
+  s->inst[instance].mesh = mesh;
+  s->committed = false;
+  return GVTB200_OK;
+}
+int gvtb200_domain_persist_config(gvtb200_scene s, int grid_ctas, int shade_at) {
+  if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
+  if (grid_ctas < 0 || shade_at < 1 || shade_at > 32) return fail(GVTB200_ERR_INVALID, "grid_ctas %d (>= 0), shade_at %d (1..32)", grid_ctas, shade_at);
+  s->p2p.grid_limit = grid_ctas, s->p2p.shade_at = shade_at;
+  return GVTB200_OK;
+}
+int gvtb200_domain_frame_persist(gvtb200_scene s, int root, int tile_rows) {
+  NEED_SCENE();
+  const int world = std::max(1, s->world);
+  if (world > 1 && !s->p2p.attached) return fail(GVTB200_ERR_INVALID, "needs gvtb200_p2p_attach (world > 1)");
+  if (world == 1 && !s->p2p.attached) { // a private mailbox + inbox: one rank serves everything
+    if (!s->p2p.private_box || s->p2p.inbox[0].q.cap != inbox_capacity(s)) {
+      gvtb200_p2p_detach(s);
+      if (int rc = p2p_own_objects(s, false)) return rc;
+      RayQueue self = s->p2p.inbox[0].q;
+      CU(dalloc(&s->p2p.d_peer_inbox, 1));
+      CU(cudaMemcpy(s->p2p.d_peer_inbox, &self, sizeof(RayQueue), cudaMemcpyHostToDevice));
+      memset(&s->p2p.mail, 0, sizeof(s->p2p.mail));
+      s->p2p.mail.m[0] = s->p2p.d_mail, s->p2p.peer_fb[0] = s->d_fb;
+      s->p2p.rank = 0, s->p2p.world = 1, s->p2p.seq = 0, s->p2p.private_box = true;
+    }
+    root = 0;
+  }
+  if (s->p2p.world != world) return fail(GVTB200_ERR_INVALID, "attached to %d ranks, the scene is partitioned over %d", s->p2p.world, world);
+  if (root < 0 || root >= world) return fail(GVTB200_ERR_INVALID, "root %d outside 0..%d", root, world - 1);
+  if (tile_rows < 1) return fail(GVTB200_ERR_INVALID, "tile_rows %d", tile_rows);
+  if (!s->p2p.inbox[0].q.ready || s->p2p.inbox[0].q.cap < 64) return fail(GVTB200_ERR_INVALID, "no inbound queue (ImageScheduler attachment?)");
+  const int me = s->p2p.rank;
+  cudaStream_t st = s->stream;
+  const bool count = s->profile;
+  int grid = persist_grid(s->device, count);
+  if (s->p2p.grid_limit > 0) grid = std::min(grid, s->p2p.grid_limit);
+  grid = std::max(grid, 2);
+  const size_t threads = (size_t)grid * TRACE_THREADS;
+  if (s->p2p.scr_cap < threads) {
+    dfree(s->p2p.d_scr2), dfree(s->p2p.d_scr3);
+    CU(dalloc(&s->p2p.d_scr2, threads));
+    CU(dalloc(&s->p2p.d_scr3, threads));
+    s->p2p.scr_cap = threads;
+  }
+  const size_t n_inst = std::max<size_t>(1, s->inst.size());
+  if (!s->p2p.d_inst_load) CU(dalloc(&s->p2p.d_inst_load, n_inst));
+  if (count) CU(cudaMemsetAsync(s->p2p.d_inst_load, 0, n_inst * 8, st));
+  if (!s->p2p.servers.empty()) {
+    if (s->p2p.servers.size() != s->inst.size()) return fail(GVTB200_ERR_INVALID, "server table is stale (instances changed)");
+    dfree(s->p2p.d_servers);
+    CU(dalloc(&s->p2p.d_servers, s->p2p.servers.size()));
+    CU(cudaMemcpyAsync(s->p2p.d_servers, s->p2p.servers.data(), s->p2p.servers.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+  } else
+    dfree(s->p2p.d_servers);
+  FrameParams fp;
+  build_frame_params(*s, fp);
+  PersistParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.inbox = s->p2p.inbox[0].q;
+  pp.peer_inbox = s->p2p.d_peer_inbox; // entries [0, world): the round-0 inbound queues
+  pp.mail = s->p2p.mail;
+  pp.root_fb = s->p2p.peer_fb[root];
+  pp.scr2 = s->p2p.d_scr2, pp.scr3 = s->p2p.d_scr3;
+  pp.servers = s->p2p.d_servers;
+  pp.inst_load = s->p2p.d_inst_load;
+  pp.timeout_ns = g_peer_timeout_ns;
+  pp.tiles.row0 = 0, pp.tiles.row1 = s->H, pp.tiles.tile_rows = tile_rows, pp.tiles.index = me, pp.tiles.stride = world;
+  const size_t cam = tiles_local_rows(pp.tiles) * (size_t)s->W * s->samples * s->samples;
+  if (cam > 0x7FFFFFFFu) return fail(GVTB200_ERR_INVALID, "frame has too many camera rays");
+  pp.cam_count = (unsigned)cam;
+  pp.seq = ++s->p2p.seq;
+  pp.rank = me, pp.world = world, pp.root = root;
+  pp.shade_at = s->p2p.shade_at, pp.clamp = 1, pp.timeline = 1;
+  pp.fb_pix = s->fb_pix;
+  CU(cudaEventRecord(s->ev[0], st));
+  CU(cudaMemsetAsync(&s->p2p.d_mail->pc, 0, GVT_PERSIST_RESET_BYTES, st));
+  CU(cudaMemsetAsync(s->d_ctr, 0, sizeof(DevCounters), st));
+  if (me == root) CU(cudaMemsetAsync(s->d_fb, 0, s->fb_pix * 16, st)); // clearBuffer (TracerBase.h:310); the peers add into it
+  s->n_launch_rec = 0;
+  LAUNCHED(1);
+  if (count)
+    k_persist<true><<<grid, TRACE_THREADS, 0, st>>>(fp, scene_dev(*s), pp, g_tune);
+  else
+    k_persist<false><<<grid, TRACE_THREADS, 0, st>>>(fp, scene_dev(*s), pp, g_tune);
+  CU(cudaEventRecord(s->ev[1], st));
+  for (int k = 2; k < 5; ++k) CU(cudaEventRecord(s->ev[k], st));
+  CU(cudaGetLastError());
+  s->timing_valid = true;
+  return GVTB200_OK;
+}
+int gvtb200_domain_persist_stats(gvtb200_scene s, double *busy_ms, uint64_t *inbox_rays, uint64_t *instance_load, int n_instances) {
+  NEED_SCENE();
+  if (!s->p2p.d_mail) return fail(GVTB200_ERR_INVALID, "no persistent frame has run");
+  CU(cudaStreamSynchronize(s->stream));
+  PersistCtl pc;
+  CU(cudaMemcpy(&pc, &s->p2p.d_mail->pc, sizeof(pc), cudaMemcpyDeviceToHost));
+  if (busy_ms) *busy_ms = pc.t_last > pc.t_go ? (double)(pc.t_last - pc.t_go) * 1e-6 : 0.0;
+  if (inbox_rays) *inbox_rays = pc.tail;
+  if (instance_load) {
+    if (n_instances != (int)s->inst.size() || !s->p2p.d_inst_load) return fail(GVTB200_ERR_INVALID, "instance_load needs %zu entries", s->inst.size());
+    CU(cudaMemcpy(instance_load, s->p2p.d_inst_load, (size_t)n_instances * 8, cudaMemcpyDeviceToHost));
+  }
+  return GVTB200_OK;
+}
+
+// ---- BLAS sharing between ranks: a replica in spare HBM, or the owner's arrays mapped over NVLink ------------------------
+int gvtb200_mesh_export(gvtb200_mesh m, gvtb200_mesh_desc *out) {
+  NEED_INIT();
+  if (!m || !out) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  if (m->imported) return fail(GVTB200_ERR_INVALID, "an imported mesh cannot be exported again: export the owner's");
+  CU(cudaSetDevice(m->device));
+  memset(out, 0, sizeof(*out));
+  const void *ptrs[6] = { m->d_nodes, m->d_tris, m->d_faces, m->d_normals, m->d_vcolors, m->d_mats };
+  const size_t bytes[6] = { GVT_NODE_WORDS * sizeof(float4) * std::max<size_t>(1, m->stats[0]), 3 * sizeof(float4) * std::max<size_t>(1, m->tri_slots),
+                            sizeof(int4) * std::max<size_t>(1, m->nf), sizeof(float4) * std::max<size_t>(1, m->nv), sizeof(float4) * std::max<size_t>(1, m->nv),
+                            2 * sizeof(float4) * (size_t)m->n_mats };
+  for (int k = 0; k < 6; ++k) {
+    if (!ptrs[k]) continue;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, (void *)ptrs[k]));
+    memcpy(out->handle[k], &h, 64);
+    out->raw[k] = (uint64_t)(uintptr_t)ptrs[k], out->bytes[k] = bytes[k];
+  }
+  memcpy(out->mat, &m->blas.mat0, 32);
+  out->n_tris = m->nf, out->n_nodes = (uint32_t)m->stats[0], out->n_vertices = m->nv, out->n_mats = m->n_mats;
+  out->tri_slots = m->tri_slots;
+  out->pid = (int32_t)getpid(), out->device = m->device;
+  return GVTB200_OK;
+}
+int gvtb200_mesh_import(const gvtb200_mesh_desc *d, int mode, gvtb200_mesh *out) {
+  NEED_INIT();
+  if (!d || !out) return fail(GVTB200_ERR_INVALID, "NULL argument");
+  if (mode != GVTB200_IMPORT_COPY && mode != GVTB200_IMPORT_MAP) return fail(GVTB200_ERR_INVALID, "mode %d", mode);
+  *out = nullptr;
+  const int dev = cur_device();
+  CU(cudaSetDevice(dev));
+  gvtb200_mesh m = new gvtb200_mesh_s();
+  memset(&m->blas, 0, sizeof(Blas));
+  m->device = dev, m->imported = true;
+  m->nv = d->n_vertices, m->nf = d->n_tris, m->n_mats = d->n_mats, m->tri_slots = d->tri_slots;
+  m->stats[0] = d->n_nodes, m->stats[1] = d->n_tris;
+  void *local[6] = {};
+  const bool same_process = d->pid == (int32_t)getpid();
+  int rc = GVTB200_OK;
+  for (int k = 0; k < 6 && rc == GVTB200_OK; ++k) {
+    if (!d->raw[k]) continue;
+    void *src = nullptr;
+    if (same_process) {
+      if ((rc = enable_peer(dev, d->device))) break;
+      src = (void *)(uintptr_t)d->raw[k];
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, d->handle[k], 64);
+      cudaError_t e = cudaIpcOpenMemHandle(&src, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        rc = fail(GVTB200_ERR_CUDA, "cudaIpcOpenMemHandle(mesh array %d): %s", k, cudaGetErrorString(e));
+        break;
+      }
+    }
+    if (mode == GVTB200_IMPORT_COPY) {
+      cudaError_t e = cudaMalloc(&local[k], std::max<size_t>(16, d->bytes[k]));
+      if (e == cudaSuccess) e = cudaMemcpy(local[k], src, d->bytes[k], cudaMemcpyDefault);
+      if (!same_process) cudaIpcCloseMemHandle(src);
+      if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? GVTB200_ERR_OOM : GVTB200_ERR_CUDA, "replica of mesh array %d: %s", k, cudaGetErrorString(e));
+    } else {
+      local[k] = src;
+      if (same_process) m->borrowed[k] = true; else m->ipc_opened[k] = src;
+    }
+  }
+  m->d_nodes = (float4 *)local[0], m->d_tris = (float4 *)local[1], m->d_faces = (int4 *)local[2], m->d_normals = (float4 *)local[3];
+  m->d_vcolors = (float4 *)local[4], m->d_mats = (float4 *)local[5];
+  if (rc != GVTB200_OK) {
+    gvtb200_mesh_destroy(m);
+    return rc;
+  }
+  memcpy(&m->blas.mat0, d->mat, 32);
+  m->blas.nodes = m->d_nodes, m->blas.tris = m->d_tris, m->blas.faces = m->d_faces, m->blas.normals = m->d_normals;
+  m->blas.vcolors = m->d_vcolors, m->blas.mats = m->d_mats;
+  m->blas.n_tris = d->n_tris, m->blas.n_nodes = d->n_nodes;
+  cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    gvtb200_mesh_destroy(m);
+    return fail(GVTB200_ERR_CUDA, "stream: %s", cudaGetErrorString(e));
+  }
+  *out = m;
+  return GVTB200_OK;
+}
+
 int gvtb200_domain_composite_p2p(gvtb200_scene s, int root) {
   NEED_SCENE();
   if (!s->p2p.attached) return fail(GVTB200_ERR_INVALID, "scene is not attached to its peers (gvtb200_p2p_attach)");
@@ -1796,10 +2063,10 @@ int gvtb200_domain_composite_p2p(gvtb200_scene s, int root) {
   const unsigned seq = ++s->p2p.seq;
   Mailbox *mine = s->p2p.d_mail;
   if (s->p2p.rank == root) {
-    k_p2p_wait<<<1, GVT_P2P_MAX, 0, st>>>(mine->done, s->p2p.world, root, seq, &mine->err);
+    k_p2p_wait<<<1, GVT_P2P_MAX, 0, st>>>(mine->done, s->p2p.world, root, seq, &mine->err, g_peer_timeout_ns);
     k_fb_clamp<<<blocks_for(s->fb_pix, 256), 256, 0, st>>>(s->d_fb, s->fb_pix);
   } else {
-    k_fb_accumulate_root<<<g_sms * 8, 256, 0, st>>>((const float4 *)s->d_fb, s->p2p.peer_fb[root], s->fb_pix, mine, s->p2p.mail.m[root], s->p2p.rank, seq);
+    k_fb_accumulate_root<<<g_dev[s->device].sms * 8, 256, 0, st>>>((const float4 *)s->d_fb, s->p2p.peer_fb[root], s->fb_pix, mine, s->p2p.mail.m[root], s->p2p.rank, seq);
   }
   LAUNCHED(s->p2p.rank == root ? 2 : 1);
   CU(cudaGetLastError());

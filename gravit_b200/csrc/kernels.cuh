@@ -514,7 +514,7 @@ __host__ __device__ inline size_t tiles_local_rows(const RowTiles &t) { // rows 
 // camera rays of this shard's rows -> initial routing (FilterRaysLocally: TracerBase.h:319 / DomainTracer.h:148-181)
 __global__ void k_camera_route(FrameParams fp, SceneDev sd, RowTiles tiles, size_t count, RayQueue out) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  unsigned long long routed = 0;
+  unsigned long long routed = 0, qovf = 0;
   const size_t per_row = (size_t)fp.cam.W * fp.cam.samples * fp.cam.samples;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += stride) {
     size_t lr = i / per_row, within = i - lr * per_row;
@@ -529,9 +529,11 @@ __global__ void k_camera_route(FrameParams fp, SceneDev sd, RowTiles tiles, size
     r.o = xadd(r.o, xmul(r.d, xmul(t, 0.95f)));                   // TracerBase.h:394
     unsigned pos = queue_reserve(out.count);
     if (pos < out.cap) queue_store(out, pos, r, next);
+    else qovf++;
     routed++;
   }
   count_add(&sd.ctr->routed_initial, routed);
+  count_add(&sd.ctr->queue_overflows, qovf);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&sd.ctr->camera_rays, (unsigned long long)count);
 }
 
@@ -634,6 +636,57 @@ struct SmemStack {
     return sp < TRACE_SM_STACK ? s[sp * TRACE_THREADS] : l[sp - TRACE_SM_STACK];
   }
 };
+
+// The lock-step traversal loop of one warp (shared by k_trace and k_persist): every lane with `active` set advances its
+// traversal -- a burst of node visits, then triangle tests, postponed while too few lanes hold a triangle -- until the warp
+// should go back to its caller: all lanes are finished, or at least tune.exit_at lanes are not traversing and there is
+// something better to do for them (`resting` = lanes that had no ray on entry; a lane outside `resting` that stopped
+// traversing has a finished ray to hand over; more_input = the caller can refill).  Returns this lane's `done`.
+template <bool COUNT, class Stack>
+__device__ __forceinline__ bool warp_traverse(bool active, unsigned resting, bool more_input, const TraceTune &tune, const float4 *nodes,
+                                              const float4 *tris, const RayLocal &rl, float tfar, bool any, Trav &tv, Stack &stack,
+                                              TravCounters &tc, const unsigned char *s_lut) {
+  const unsigned FULL = 0xffffffffu;
+  bool done = false;
+  for (;;) {
+    const bool trav = active && !done;
+    const unsigned tm = __ballot_sync(FULL, trav);
+    if (tm == 0u) break;
+    const unsigned waiting = 32u - (unsigned)__popc(tm);
+    if (waiting >= (unsigned)tune.exit_at && ((~tm & ~resting) != 0u || more_input)) break;
+    if (trav) {
+#pragma unroll 1
+      for (int k = 0; k < tune.node_burst; ++k) {
+        if (!trav_has_nodes(tv)) {
+          if (k == 0 || trav_has_tris(tv)) break; // first trip: the group popped last time may be a triangle group
+          if (!trav_next(tv, stack)) {
+            done = true;
+            break;
+          }
+          if (!trav_has_nodes(tv)) break; // popped a postponed triangle group
+        }
+        node_step<COUNT, true>(nodes, rl, GVT_RAY_EPSILON, tv, stack, &tc, s_lut);
+        if (trav_has_tris(tv)) break;
+      }
+    }
+    for (;;) {
+      const bool ht = trav && !done && trav_has_tris(tv);
+      const unsigned tb = __ballot_sync(FULL, ht);
+      if (tb == 0u) break;
+      if (__popc(tb) * 8 < __popc(tm) * tune.postpone_num) {
+        // too few lanes have a triangle: lanes with node work postpone theirs, the others keep it pending
+        if (ht && trav_has_nodes(tv)) {
+          stack.push(tv.sp, tv.tg);
+          tv.tg.y &= 0xFF000000u;
+        }
+        break;
+      }
+      if (ht) done = tri_step<COUNT>(tris, rl, GVT_RAY_EPSILON, tfar, any, tv, &tc);
+    }
+    if (trav && !done) done = !trav_next(tv, stack);
+  }
+  return done;
+}
 
 template <bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(FrameParams fp, SceneDev sd, TraceQueues q, int mode, TraceTune tune) {
@@ -742,44 +795,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
       continue;
     }
     // ---- traverse in lock step ---------------------------------------------------------------------------
-    bool done = false;
-    for (;;) {
-      const bool trav = active && !done;
-      const unsigned tm = __ballot_sync(FULL, trav);
-      if (tm == 0u) break;
-      const unsigned waiting = 32u - (unsigned)__popc(tm);
-      if (waiting >= (unsigned)tune.exit_at && ((~tm & ~idle) != 0u || !exhausted)) break;
-      if (trav) {
-#pragma unroll 1
-        for (int k = 0; k < tune.node_burst; ++k) {
-          if (!trav_has_nodes(tv)) {
-            if (k == 0 || trav_has_tris(tv)) break; // first trip: the group popped last time may be a triangle group
-            if (!trav_next(tv, stack)) {
-              done = true;
-              break;
-            }
-            if (!trav_has_nodes(tv)) break; // popped a postponed triangle group
-          }
-          node_step<COUNT, true>(nodes, rl, GVT_RAY_EPSILON, tv, stack, &tc, s_lut);
-          if (trav_has_tris(tv)) break;
-        }
-      }
-      for (;;) {
-        const bool ht = trav && !done && trav_has_tris(tv);
-        const unsigned tb = __ballot_sync(FULL, ht);
-        if (tb == 0u) break;
-        if (__popc(tb) * 8 < __popc(tm) * tune.postpone_num) {
-          // too few lanes have a triangle: lanes with node work postpone theirs, the others keep it pending
-          if (ht && trav_has_nodes(tv)) {
-            stack.push(tv.sp, tv.tg);
-            tv.tg.y &= 0xFF000000u;
-          }
-          break;
-        }
-        if (ht) done = tri_step<COUNT>(tris, rl, GVT_RAY_EPSILON, tfar, any, tv, &tc);
-      }
-      if (trav && !done) done = !trav_next(tv, stack);
-    }
+    const bool done = warp_traverse<COUNT>(active, idle, !exhausted, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
     // ---- rays that finished their instance -------------------------------------------------------------------
     if (active && done) {
       if (tv.hit.prim >= 0) {
@@ -791,7 +807,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
           if (pos < q.hq.cap) {
             queue_store(q.hq, pos, r, mode == 1 ? q.in.inst[idx] : inst);
             q.hit[pos] = make_int4(tv.hit.prim, tv.hit.slot, (int)f2u(tv.hit.u), (int)f2u(tv.hit.v));
-          }
+          } else
+            c_qovf++; // the reference never drops a ray (TracerBase.h:403-409): reported as GVTB200_ERR_CAPACITY
         }
         active = false;
       } else {
@@ -803,6 +820,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
           const int slot = q.in.inst[idx];
           const unsigned pos = queue_reserve(q.mvq.count);
           if (pos < q.mvq.cap) queue_store(q.mvq, pos, r, slot);
+          else c_qovf++;
           if (type != RAY_SHADOW && slot >= 0) queue_store(q.fin, (unsigned)slot, r, slot);
           active = false;
         } else {
@@ -820,6 +838,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
             active = false;
           } else {
             o = xadd(o, xmul(d, xmul(t, 0.95f))); // TracerBase.h:394
+            if (to_light && type == RAY_SHADOW) t_max = xsub(t_max, xmul(t, 0.95f)); // the distance left to the light
             const int owner = fp.world > 1 ? sd.inst[next].owner : fp.rank;
             if (owner != fp.rank) {
               Ray r;
@@ -834,6 +853,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
               } else {
                 const unsigned pos = queue_reserve(q.exq.count);
                 if (pos < q.exq.cap) queue_store(q.exq, pos, r, next);
+                else c_qovf++;
               }
               c_exp++;
               active = false;
@@ -868,7 +888,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
 __global__ void __launch_bounds__(256) k_shade(FrameParams fp, SceneDev sd, ShadeQueues q, int mode) {
   const unsigned n = min(*q.hq.count, q.hq.cap);
   const bool to_light = (fp.flags & FLAG_SHADOW_TO_LIGHT) != 0;
-  unsigned long long c_hits = 0, c_shgen = 0, c_sec = 0;
+  unsigned long long c_hits = 0, c_shgen = 0, c_sec = 0, c_qovf = 0;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     Ray r;
     int inst;
@@ -895,11 +915,13 @@ __global__ void __launch_bounds__(256) k_shade(FrameParams fp, SceneDev sd, Shad
       c_shgen++;
       unsigned pos = queue_reserve(q.shq.count);
       if (pos < q.shq.cap) queue_store(q.shq, pos, sh, mode == 1 ? -1 : inst);
+      else c_qovf++;
     }
     if (make_bounce(r, normal, fp.seed)) {
       c_sec++;
       unsigned pos = queue_reserve(q.nxq.count);
       if (pos < q.nxq.cap) queue_store(q.nxq, pos, r, mode == 1 ? slot : inst);
+      else c_qovf++;
     } else if (mode == 1 && slot >= 0) {
       queue_store(q.fin, (unsigned)slot, r, slot);
     }
@@ -907,6 +929,7 @@ __global__ void __launch_bounds__(256) k_shade(FrameParams fp, SceneDev sd, Shad
   count_add(&sd.ctr->primary_hits, c_hits);
   count_add(&sd.ctr->shadow_generated, c_shgen);
   count_add(&sd.ctr->secondary_generated, c_sec);
+  count_add(&sd.ctr->queue_overflows, c_qovf);
 }
 
 // closest-hit / any-hit queries in mesh-local space (parity hooks)
@@ -961,6 +984,7 @@ __global__ void k_shuffle(FrameParams fp, SceneDev sd, RayQueue in, unsigned n, 
   int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, from, from == -1 && (fp.flags & FLAG_ENTER_INSIDE) != 0, t);
   if (next >= 0) {
     r.o = xadd(r.o, xmul(r.d, xmul(t, 0.95f)));
+    if ((fp.flags & FLAG_SHADOW_TO_LIGHT) && r.type == RAY_SHADOW) r.t_max = xsub(r.t_max, xmul(t, 0.95f));
     unsigned pos = queue_reserve(out.count);
     if (pos < out.cap) queue_store(out, pos, r, next);
   } else if (r.type == RAY_SHADOW && xlength(r.color) > 0.f) {
@@ -1006,12 +1030,29 @@ __global__ void k_import(const uint4 *packed, unsigned n, RayQueue q, unsigned o
 // Every rank owns one Mailbox that its peers can write: `go` is set by the root when its framebuffer may be overwritten,
 // done[r] by rank r when its contribution to this rank's framebuffer is complete.  Values are frame sequence numbers.
 #define GVT_P2P_MAX 16
+// Control block of the persistent DomainScheduler kernel (k_persist), one per rank, mapped into every peer.  The three hot
+// words sit on separate 128-byte lines (remote atomics on `tail` must not fight the local atomics on `head`).
+struct PersistCtl {
+  unsigned tail; // inbox slots reserved so far by producers on any rank (== rays ever put into this inbox this frame)
+  unsigned pad0[31];
+  unsigned head;     // inbox tickets handed to consumer lanes of this rank
+  unsigned cam_next; // cursor over this rank's shard of the camera rays
+  unsigned pad1[30];
+  unsigned consumed; // rays this rank has retired: items of its inbox plus its own camera rays
+  unsigned err;      // 1 = a wait timed out, 2 = an inbound queue overflowed (the frame is invalid either way)
+  unsigned pad2[30];
+  // ---- not reset between frames: values are frame sequence numbers ----
+  unsigned cam_total; // camera rays of this rank's film shard in the current frame
+  unsigned go, stop, done_seq;
+  unsigned long long t_go, t_last; // globaltimer at the start barrier / at the last retire flush (per-rank busy time)
+  unsigned arrive[GVT_P2P_MAX];    // start barrier: arrive[r] = frame number, written by rank r
+};
+#define GVT_PERSIST_RESET_BYTES 384 /* tail .. pad2 */
 struct Mailbox {
   unsigned go, err, cta_done, pad;
   unsigned done[GVT_P2P_MAX];
-  unsigned tail[GVT_P2P_MAX]; // asynchronous DomainScheduler: tail[p] = rays rank p has finished storing into its region of
-                              // this rank's inbound area (cumulative over the frame)
-  unsigned reserved[60 - 2 * GVT_P2P_MAX];
+  unsigned reserved[60 - GVT_P2P_MAX];
+  PersistCtl pc;
 };
 struct PeerMail {
   Mailbox *m[GVT_P2P_MAX];
@@ -1027,14 +1068,14 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// thread i < n (i != skip) waits until flags[i] has reached sequence number seq; gives up after ~4 s (err is set)
-__global__ void k_p2p_wait(const unsigned *flags, int n, int skip, unsigned seq, unsigned *err) {
+// thread i < n (i != skip) waits until flags[i] has reached sequence number seq; gives up after timeout_ns (err is set)
+__global__ void k_p2p_wait(const unsigned *flags, int n, int skip, unsigned seq, unsigned *err, unsigned long long timeout_ns) {
   const int i = (int)threadIdx.x;
   if (i >= n || i == skip) return;
   const unsigned long long t0 = global_ns();
   while ((int)(ld_acquire_sys(flags + i) - seq) < 0) {
     __nanosleep(128);
-    if (global_ns() - t0 > 4000000000ull) {
+    if (global_ns() - t0 > timeout_ns) {
       atomicExch(err, 1u);
       return;
     }
@@ -1058,36 +1099,6 @@ __device__ __forceinline__ void p2p_signal_done(Mailbox *mine, Mailbox *root_mai
     }
   }
 }
-// ---- asynchronous DomainScheduler (reference: tracer/Domain/DomainTracer.cpp:109-192) -------------------
-// Every rank owns one inbound REGION per producer, so a producer reserves slots with an atomic on its own memory and no
-// consumer ever sees a reserved-but-unwritten slot: after the kernels of one step the producer publishes how far it has
-// written (tail), and the consumer only touches rays below the published tail.  No kernel waits for another GPU.
-// thread c < world: tell rank c how many rays this rank has stored into its region there
-__global__ void k_async_publish(PeerMail pm, const unsigned *out_count, int world, int self) {
-  const int c = (int)threadIdx.x;
-  if (c >= world || c == self) return;
-  __threadfence_system(); // the rays were written by earlier kernels of this stream
-  st_release_sys(&pm.m[c]->tail[self], out_count[c]);
-}
-// copies rays [head[p], tail[p]) of every producer's region into `out` (this rank's local queue), region after region
-// source `world` is this rank's own queue of camera rays (handed out in slices, so that what they export reaches the peers
-// while the rest is still waiting)
-struct AsyncGather {
-  unsigned head[GVT_P2P_MAX + 1];
-  unsigned prefix[GVT_P2P_MAX + 2]; // prefix[p] = rays of sources < p
-};
-__global__ void k_async_gather(const RayQueue *regions, AsyncGather g, int n_src, RayQueue out) {
-  const unsigned total = g.prefix[n_src];
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int p = 0;
-    while (i >= g.prefix[p + 1]) ++p;
-    const RayQueue src = regions[p];
-    const unsigned k = g.head[p] + (i - g.prefix[p]);
-    out.c0[i] = src.c0[k], out.c1[i] = src.c1[k], out.c2[i] = src.c2[k], out.c3[i] = src.c3[k];
-    out.inst[i] = src.inst[k];
-  }
-}
-
 // ImageScheduler: clamp this shard's film rows and store them into dst (the root's framebuffer; dst == src on the root)
 __global__ void k_rows_to_root(const float4 *src, float4 *dst, RowTiles tiles, int W, Mailbox *mine, Mailbox *root_mail, int rank, unsigned seq) {
   const size_t n = tiles_local_rows(tiles) * (size_t)W;
@@ -1101,6 +1112,20 @@ __global__ void k_rows_to_root(const float4 *src, float4 *dst, RowTiles tiles, i
   }
   if (root_mail) p2p_signal_done(mine, root_mail, rank, seq);
 }
+// this shard's film rows of `src` (a framebuffer in this GPU's memory or a peer's, mapped over NVLink), clamped, packed row
+// tile after row tile into `dst`: the staging buffer of the parallel read-back (every rank brings its own rows to the host
+// over its own PCIe link; replaces the gather that follows icetCompositeImage, composite/IceTComposite.cpp:96-101)
+__global__ void k_rows_pack(const float4 *src, float4 *dst, RowTiles tiles, int W) {
+  const size_t n = tiles_local_rows(tiles) * (size_t)W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t lr = i / W, x = i - lr * W;
+    const size_t b = lr / tiles.tile_rows, k = lr - b * tiles.tile_rows;
+    const size_t pix = ((size_t)tiles.row0 + (b * tiles.stride + tiles.index) * tiles.tile_rows + k) * W + x;
+    float4 v = __ldcg(src + pix);
+    v.x = fminf(v.x, 1.f), v.y = fminf(v.y, 1.f), v.z = fminf(v.z, 1.f);
+    dst[i] = v;
+  }
+}
 // DomainScheduler: add the pixels this rank touched (alpha counts contributions) to the root's framebuffer
 __global__ void k_fb_accumulate_root(const float4 *src, float *dst, size_t npix, Mailbox *mine, Mailbox *root_mail, int rank, unsigned seq) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
@@ -1111,6 +1136,470 @@ __global__ void k_fb_accumulate_root(const float4 *src, float *dst, size_t npix,
     }
   }
   p2p_signal_done(mine, root_mail, rank, seq);
+}
+
+
+// =========================================================================================================
+// The persistent DomainScheduler kernel.  Tracer<DomainScheduler>::operator() (algorithm/DomainTracer.h:185-368) + SendRays
+// (:370-496) + the termination test (:339-349) + the composite (composite/IceTComposite.cpp:84-117) as ONE kernel launch per
+// rank and frame; the reference's asynchronous loop (tracer/Domain/DomainTracer.cpp:109-192, scheduler::AsyncDomain) is the
+// closest relative: there are no exchange rounds.
+//
+//   rays in      every rank generates 1/world of the camera rays (row tiles dealt round-robin) in registers, routes them
+//                through the instance BVH and hands each one to a rank that serves its first instance; everything else
+//                arrives through the rank's INBOX, a slot array in its own HBM that every peer has mapped (CUDA IPC / peer
+//                access over NVLink).  A producer on any GPU reserves a slot with one atomic on `tail`, stores the SoA ray and
+//                then publishes it by writing the frame number into the slot's `ready` word (release); consumer lanes draw
+//                tickets from `head` and wait for their slot's `ready` word (acquire).  No kernel launch, host round trip
+//                or collective sits between a ray leaving one GPU and being traced on the next.
+//   ray life     trace in the instance (closest hit / any hit); miss -> next instance through the TLAS: traced here if this
+//                rank serves it, else stored into a serving rank's inbox; closest hit -> shaded by the same lane (in batches
+//                of >= shade_at lanes per warp): the first shadow ray (or the bounce) continues in the lane, further rays go
+//                into the rank's own inbox; a finished shadow ray adds its colour to the ROOT's framebuffer (remote atomics).
+//   termination  every rank counts what it retires (`consumed`); `tail` + the camera shard is what it was given.  One control
+//                warp on the root reads all `consumed` words, then all `tail` words: equal sums mean that at the instant
+//                between the two passes nothing was queued or in flight anywhere (both counts only grow, and a ray is counted
+//                as given before its parent is counted as retired).  The root then releases every rank, clamps the image.
+//   servers      an instance may be served by several ranks (its owner plus ranks that hold a replica of its BLAS or have
+//                the owner's BLAS mapped over NVLink); a ray picks one by a hash of its direction bits against the
+//                cumulative weights of the table (gvtb200_domain_set_servers) -- the load balance the reference's hybrid
+//                schedulers looked for by loading hot domains on idle ranks.
+// Every wait gives up after timeout_ns and flags the frame as failed.
+// =========================================================================================================
+#ifndef PERSIST_MIN_BLOCKS
+#define PERSIST_MIN_BLOCKS 5
+#endif
+struct PersistParams {
+  RayQueue inbox;             // this rank's inbound slots (count unused: PersistCtl::tail / head)
+  const RayQueue *peer_inbox; // [world]: every rank's inbox as mapped into this GPU (entry `rank` == inbox)
+  PeerMail mail;              // every rank's mailbox (PersistCtl inside)
+  float *root_fb;             // the root's RGBA framebuffer as mapped here
+  float4 *scr2;               // per-thread backing store of the ray columns that are not kept in registers (colour, t)
+  int4 *scr3;                 //   (id, depth, w, type): rays made in the lane (shadow rays, bounces) have no queue slot
+  const uint4 *servers;       // per instance {ranks (4 x 8 bit), thresholds 0/1 (2 x 16 bit), threshold 2, count} or null
+  unsigned long long *inst_load; // COUNT only: wide nodes visited per instance (input of the replica planner)
+  unsigned long long timeout_ns;
+  RowTiles tiles;    // this rank's shard of the film rows
+  unsigned cam_count; // camera rays of the shard
+  unsigned seq;       // frame number (>= 1, the same on every rank)
+  int rank, world, root;
+  int shade_at;       // shade when at least this many lanes of a warp hold a closest hit
+  int clamp;          // the root clamps the image when the frame is over
+  int timeline;       // record when this rank last retired a ray (per-rank busy time)
+  size_t fb_pix;
+};
+
+// Polling loads and publishing stores of the worker warps.  ld.acquire / __threadfence() compile to LDG.STRONG + CCTL.IVALL:
+// they would wipe the SM's L1 (the BVH nodes every other warp is traversing) at every poll.  A worker therefore polls with
+// ld.volatile (LDG.STRONG.SYS, no invalidation), reads what the flag guards with ld.cg (L2, the coherence point for local
+// and peer writers alike; issued after the flag value has come back, the SM does not speculate loads), and publishes with
+// st.release / red.release (MEMBAR.ALL + the store: orders the lane's earlier writes, no invalidation).
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_release_sys_add(unsigned *p, unsigned v) { asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int pick_server(const uint4 *servers, int inst, int owner, V3 d) {
+  if (!servers) return owner;
+  const uint4 e = __ldg(servers + inst);
+  if (e.w <= 1u) return (int)(e.x & 0xFFu);
+  const unsigned h = pcg(f2u(d.x) + 0x9e3779b9u * f2u(d.y) + 0x85ebca6bu * f2u(d.z)) >> 16;
+  const unsigned j = (h >= (e.y & 0xFFFFu) ? 1u : 0u) + (h >= (e.y >> 16) ? 1u : 0u) + (h >= e.z ? 1u : 0u);
+  return (int)((e.x >> (8u * min(j, e.w - 1u))) & 0xFFu);
+}
+
+// the control warp (block 0, warp 0): start barrier, termination, release
+__device__ __noinline__ void persist_control(const PersistParams &pp, PersistCtl *ctl) {
+  const unsigned FULL = 0xffffffffu;
+  const int r = (int)threadIdx.x;
+  const bool peer = r < pp.world;
+  const unsigned seq = pp.seq;
+  const unsigned long long t0 = global_ns();
+  PersistCtl *theirs = peer ? &pp.mail.m[r]->pc : ctl;
+  if (r == 0) st_release_sys(&ctl->cam_total, pp.cam_count);
+  __syncwarp();
+  // start barrier: every rank has reset its counters (and the root has cleared the image) before anybody produces
+  bool bad = false;
+  if (peer) {
+    st_release_sys(&theirs->arrive[pp.rank], seq);
+    while ((int)(ld_volatile_u32(&ctl->arrive[r]) - seq) < 0) {
+      __nanosleep(64);
+      if (global_ns() - t0 > pp.timeout_ns) {
+        bad = true;
+        break;
+      }
+    }
+  }
+  bad = __any_sync(FULL, bad);
+  if (r == 0) {
+    ctl->t_go = global_ns();
+    if (bad) atomicOr(&ctl->err, 1u), st_release_sys(&ctl->stop, seq);
+    st_release_sys(&ctl->go, seq);
+  }
+  if (bad) return;
+  if (pp.rank == pp.root) {
+    for (;;) {
+      // pass 1: what every rank has retired; pass 2 (issued after every pass-1 value has come back: the reduction below
+      // consumes them): what every rank was given.  Volatile loads read the owner's L2, where its atomics are performed.
+      const unsigned c = peer ? ld_volatile_u32(&theirs->consumed) : 0u;
+      const unsigned e = peer ? ld_volatile_u32(&theirs->err) : 0u;
+      const unsigned cs = __reduce_add_sync(FULL, c), es = __reduce_or_sync(FULL, e);
+      const unsigned t = (peer && cs != 0xFFFFFFFFu) ? ld_volatile_u32(&theirs->tail) + ld_volatile_u32(&theirs->cam_total) : 0u;
+      const unsigned ts = __reduce_add_sync(FULL, t);
+      const bool late = global_ns() - t0 > pp.timeout_ns;
+      if (cs == ts || es || late) {
+        if ((es || late) && r == 0) atomicOr(&ctl->err, es ? es : 1u);
+        break;
+      }
+      __nanosleep(400);
+    }
+    if (peer) st_release_sys(&theirs->done_seq, seq);
+  }
+  if (r == 0) {
+    while ((int)(ld_volatile_u32(&ctl->done_seq) - seq) < 0) {
+      __nanosleep(100);
+      if (global_ns() - t0 > pp.timeout_ns) {
+        atomicOr(&ctl->err, 1u);
+        break;
+      }
+    }
+    st_release_sys(&ctl->stop, seq);
+  }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(FrameParams fp, SceneDev sd, PersistParams pp, TraceTune tune) {
+  __shared__ uint2 s_stack[TRACE_SM_STACK * TRACE_THREADS];
+  __shared__ unsigned char s_lut[8 * 256];
+  for (unsigned k = threadIdx.x; k < 8u * 256u; k += TRACE_THREADS) s_lut[k] = (unsigned char)best_slot(k & 255u, k >> 8);
+  __syncthreads(); // the only block-wide barrier: the control warp leaves the block's flow after it
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31, ltmask = (1u << lane) - 1u;
+  const unsigned gtid = blockIdx.x * TRACE_THREADS + threadIdx.x;
+  PersistCtl *ctl = &pp.mail.m[pp.rank]->pc;
+  const unsigned seq = pp.seq;
+  const int me = pp.rank;
+  const bool multi = pp.world > 1;
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    persist_control(pp, ctl);
+    return;
+  }
+  { // wait until every rank is ready
+    const unsigned long long t0 = global_ns();
+    if (lane == 0)
+      while (ld_volatile_u32(&ctl->go) != seq) {
+        __nanosleep(64);
+        if (global_ns() - t0 > 2 * pp.timeout_ns) break;
+      }
+    __syncwarp();
+  }
+  const bool to_light = (fp.flags & FLAG_SHADOW_TO_LIGHT) != 0;
+  const bool enter_inside = (fp.flags & FLAG_ENTER_INSIDE) != 0;
+  const unsigned per_row = (unsigned)(fp.cam.W * fp.cam.samples * fp.cam.samples);
+  auto camera_index = [&](unsigned i) -> size_t {
+    unsigned lr = i / per_row, within = i - lr * per_row;
+    unsigned b = lr / (unsigned)pp.tiles.tile_rows, k = lr - b * (unsigned)pp.tiles.tile_rows;
+    size_t row = (size_t)pp.tiles.row0 + ((size_t)b * pp.tiles.stride + pp.tiles.index) * pp.tiles.tile_rows + k;
+    return row * per_row + within;
+  };
+  unsigned long long c_visits = 0, c_shok = 0, c_fb = 0, c_exp = 0, c_ovf = 0, c_qovf = 0, c_routed = 0, c_hits = 0, c_shgen = 0, c_sec = 0;
+  TravCounters tc;
+  tc.nodes = 0, tc.tris = 0;
+  unsigned nodes0 = 0;
+  SmemStack stack;
+  stack.s = s_stack + threadIdx.x;
+  stack.overflow = false;
+
+  enum { L_IDLE = 0, L_WAIT = 1, L_ACTIVE = 2, L_SHADE = 3 };
+  int st = L_IDLE;
+  int src = 0;      // the columns not kept in registers: 0 = camera ray `idx` (regenerated), 1 = inbox slot `idx`, 2 = this thread's scratch
+  unsigned idx = 0; // camera ray of the shard / inbox ticket
+  bool first = true, any = false, dirty = false, cam_done = pp.cam_count == 0;
+  unsigned c_cons = 0; // retired since the last flush
+  int inst = 0, type = 0;
+  V3 o = v3(0.f, 0.f, 0.f), d = o;
+  float t_min = 0.f, t_max = 0.f, tfar = FLT_MAX;
+  const float4 *nodes = nullptr, *tris = nullptr;
+  RayLocal rl;
+  Trav tv;
+  ray_local(rl, o, o);
+  trav_begin(tv, 0u, 0.f);
+
+  auto begin_instance = [&]() {
+    const Instance in = sd.inst[inst];
+    const Blas &bl = sd.blas[in.mesh];
+    V3 lo, ld;
+    to_local(in, o, d, lo, ld);
+    ray_local(rl, lo, ld);
+    nodes = bl.nodes, tris = bl.tris;
+    tfar = (any && to_light) ? t_max : FLT_MAX; // prepGVT_EMBREE_PACKET_TYPE (EmbreeMeshAdapter.cpp:269-286)
+    trav_begin(tv, bl.n_tris, tfar);
+    c_visits++;
+    if (COUNT) nodes0 = tc.nodes;
+  };
+  auto reload = [&](Ray &r) {
+    if (src == 0) {
+      camera_ray(fp.cam, camera_index(idx), r);
+    } else {
+      const float4 c2 = src == 1 ? __ldcg(pp.inbox.c2 + idx) : pp.scr2[gtid];
+      const int4 c3 = src == 1 ? __ldcg(pp.inbox.c3 + idx) : pp.scr3[gtid];
+      r.color = v3(c2.x, c2.y, c2.z), r.t = c2.w;
+      r.id = c3.x, r.depth = c3.y, r.w = u2f((uint32_t)c3.z), r.type = c3.w;
+    }
+    r.o = o, r.t_min = t_min, r.d = d, r.t_max = t_max;
+  };
+  // a ray made in this lane becomes the lane's ray
+  auto continue_as = [&](const Ray &r) {
+    o = r.o, t_min = r.t_min, d = r.d, t_max = r.t_max, type = r.type;
+    pp.scr2[gtid] = make_float4(r.color.x, r.color.y, r.color.z, r.t);
+    pp.scr3[gtid] = make_int4(r.id, r.depth, (int)f2u(r.w), r.type);
+    src = 2;
+    any = (type == RAY_SHADOW), first = true, st = L_ACTIVE;
+    begin_instance();
+  };
+  // SendRays: into the inbox of `dest` (this rank's own inbox for rays it makes faster than it has lanes)
+  auto send = [&](const Ray &r, int target, int dest) {
+    const RayQueue q = dest == me ? pp.inbox : pp.peer_inbox[dest];
+    PersistCtl *pc = &pp.mail.m[dest]->pc;
+    unsigned pos;
+    if (dest == me) {
+      pos = queue_reserve(&pc->tail);
+    } else {
+      pos = queue_reserve_peer(&pc->tail, dest);
+      dirty = true;
+    }
+    if (pos < q.cap) {
+      queue_store(q, pos, r, target);
+      if (dest == me) st_release_gpu(q.ready + pos, seq); else st_release_sys(q.ready + pos, seq);
+    } else { // never silently: the frame fails with GVTB200_ERR_CAPACITY; the count stays balanced so that it still ends
+      c_qovf++;
+      atomicOr(&ctl->err, 2u);
+      if (dest == me) atomicAdd(&pc->consumed, 1u); else atomicAdd_system(&pc->consumed, 1u);
+    }
+  };
+  // retired rays -> `consumed`; everything this warp wrote anywhere (peer inboxes, the root's image) is ordered before it
+  // (each lane releases its own count: a lane's count covers exactly the rays whose stores that lane issued)
+  auto flush = [&]() {
+    if (c_cons != 0u) {
+      if (dirty) red_release_sys_add(&ctl->consumed, c_cons); else red_release_gpu_add(&ctl->consumed, c_cons);
+      c_cons = 0u, dirty = false;
+      if (pp.timeline) atomicMax(&ctl->t_last, global_ns());
+    }
+    __syncwarp();
+  };
+
+  unsigned iter = 0;
+  unsigned long long t_idle0 = 0;
+  for (;;) {
+    ++iter;
+    // ---- refill idle lanes: camera rays of the shard first, then inbox tickets ---------------------------------------
+    unsigned idle = __ballot_sync(FULL, st == L_IDLE);
+    const unsigned busy = __ballot_sync(FULL, st >= L_ACTIVE);
+    if (idle != 0u && (busy == 0u || __popc(idle) >= tune.refill_at)) {
+      const unsigned cnt = (unsigned)__popc(idle);
+      if (!cam_done) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->cam_next, cnt);
+        base = __shfl_sync(FULL, base, 0);
+        if (base + cnt >= pp.cam_count) cam_done = true;
+        if (st == L_IDLE) {
+          const unsigned my = base + (unsigned)__popc(idle & ltmask);
+          if (my < pp.cam_count) { // gvtPerspectiveCamera::generateRays + FilterRaysLocally (first routing hop), in registers
+            idx = my, src = 0;
+            Ray r;
+            camera_ray(fp.cam, camera_index(idx), r);
+            float t;
+            const int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, -1, enter_inside, t);
+            if (next < 0) {
+              c_cons++; // background
+            } else {
+              c_routed++;
+              r.o = xadd(r.o, xmul(r.d, xmul(t, 0.95f))); // TracerBase.h:394
+              const int dest = multi ? pick_server(pp.servers, next, sd.inst[next].owner, r.d) : me;
+              if (dest == me) {
+                o = r.o, t_min = r.t_min, d = r.d, t_max = r.t_max, type = r.type, inst = next;
+                any = false, first = true, st = L_ACTIVE;
+                begin_instance();
+              } else {
+                send(r, next, dest);
+                c_exp++, c_cons++;
+              }
+            }
+          }
+        }
+      } else {
+        unsigned take = 0, base = 0;
+        if (lane == 0) {
+          const unsigned t = ld_volatile_u32(&ctl->tail), h = ld_volatile_u32(&ctl->head);
+          take = t > h ? min(t - h, cnt) : 0u;
+          if (take) base = atomicAdd(&ctl->head, take);
+        }
+        take = __shfl_sync(FULL, take, 0), base = __shfl_sync(FULL, base, 0);
+        if (st == L_IDLE) {
+          const unsigned k = (unsigned)__popc(idle & ltmask);
+          if (k < take) idx = base + k, st = L_WAIT;
+        }
+      }
+    }
+    // ---- lanes that hold a ticket: has the ray landed? ------------------------------------------------------------
+    if (st == L_WAIT) {
+      if (idx >= pp.inbox.cap) {
+        st = L_IDLE; // the producer found the inbox full (it has flagged the frame and balanced the count)
+      } else if (ld_volatile_u32(pp.inbox.ready + idx) == seq) {
+        const float4 c0 = __ldcg(pp.inbox.c0 + idx), c1 = __ldcg(pp.inbox.c1 + idx);
+        type = __ldcg(&pp.inbox.c3[idx].w);
+        inst = __ldcg(pp.inbox.inst + idx);
+        o = v3(c0.x, c0.y, c0.z), t_min = c0.w, d = v3(c1.x, c1.y, c1.z), t_max = c1.w;
+        src = 1;
+        any = (type == RAY_SHADOW), first = true, st = L_ACTIVE;
+        begin_instance();
+      }
+    }
+    // ---- nothing to trace or shade in this warp --------------------------------------------------------------------
+    if (__ballot_sync(FULL, st >= L_ACTIVE) == 0u) {
+      flush();
+      unsigned stop = 0;
+      if (lane == 0) stop = ld_volatile_u32(&ctl->stop) == seq ? 1u : 0u;
+      if (__shfl_sync(FULL, stop, 0)) break;
+      if (cam_done) {
+        __nanosleep(__any_sync(FULL, st == L_WAIT) ? 32 : 128);
+        if ((iter & 255u) == 0u) { // a peer died, or a bug: never spin for ever
+          const unsigned long long now = global_ns();
+          if (t_idle0 == 0) t_idle0 = now;
+          if (now - t_idle0 > 2 * pp.timeout_ns) {
+            if (lane == 0) atomicOr(&ctl->err, 1u);
+            break;
+          }
+        }
+      }
+      continue;
+    }
+    t_idle0 = 0;
+    // ---- traverse in lock step ----------------------------------------------------------------------------------------
+    const unsigned resting = __ballot_sync(FULL, st != L_ACTIVE);
+    const bool done = warp_traverse<COUNT>(st == L_ACTIVE, resting, true, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
+    // ---- rays that finished their instance -------------------------------------------------------------------------
+    if (st == L_ACTIVE && done) {
+      if (COUNT && pp.inst_load) atomicAdd(pp.inst_load + inst, (unsigned long long)(tc.nodes - nodes0));
+      if (tv.hit.prim >= 0) {
+        if (type != RAY_SHADOW) {
+          st = L_SHADE; // closest hit: shaded below, together with the warp's other hits
+        } else {
+          st = L_IDLE, c_cons++; // occluded (EmbreeMeshAdapter.cpp:487-489)
+        }
+      } else {
+        if (any && first) c_shok++;
+        first = false;
+        float t;
+        const int next = tlas_route(sd.tlas, o, d, t_max, inst, false, t);
+        if (next < 0) {
+          if (type == RAY_SHADOW) { // TracerBase.h:396-399, straight into the root's image
+            Ray r;
+            reload(r);
+            if (xlength(r.color) > 0.f) {
+              const V3 c = xmul(r.color, r.w);
+              if (me == pp.root) {
+                fb_add(pp.root_fb, r.id, c);
+              } else {
+                float *px = pp.root_fb + 4 * (size_t)r.id;
+                atomicAdd_system(px, c.x), atomicAdd_system(px + 1, c.y), atomicAdd_system(px + 2, c.z), atomicAdd_system(px + 3, 1.0f);
+                dirty = true;
+              }
+              c_fb++;
+            }
+          }
+          st = L_IDLE, c_cons++;
+        } else {
+          o = xadd(o, xmul(d, xmul(t, 0.95f))); // TracerBase.h:394
+          if (to_light && type == RAY_SHADOW) t_max = xsub(t_max, xmul(t, 0.95f));
+          const int dest = multi ? pick_server(pp.servers, next, sd.inst[next].owner, d) : me;
+          if (dest == me) {
+            inst = next;
+            begin_instance();
+          } else {
+            Ray r;
+            reload(r);
+            send(r, next, dest);
+            c_exp++, c_cons++;
+            st = L_IDLE;
+          }
+        }
+      }
+    }
+    // ---- shade the warp's closest hits (EmbreeMeshAdapter.cpp:491-601) ------------------------------------------------------
+    {
+      const unsigned sm = __ballot_sync(FULL, st == L_SHADE);
+      if (sm != 0u && (__popc(sm) >= pp.shade_at || __ballot_sync(FULL, st == L_ACTIVE) == 0u) && st == L_SHADE) {
+        Ray r;
+        reload(r);
+        r.t = tv.hit.t;
+        const Instance in = sd.inst[inst];
+        const Blas &bl = sd.blas[in.mesh];
+        c_hits++;
+        V3 normal;
+        Mat mat;
+        surface_at(bl, in, tv.hit, r, fp.flags, normal, mat);
+        if (r.type == RAY_SECONDARY) { // :572-575
+          const float tt = (r.t > 1.f) ? xdiv(1.f, r.t) : r.t;
+          r.w = xmul(r.w, tt);
+        }
+        bool have = false;
+        Ray keep; // the first shadow ray stays in the lane unless the ray bounces
+        for (int li = 0; li < fp.n_lights; ++li) {
+          const Light &L = fp.lights[li];
+          Ray sh;
+          if (!make_shadow_ray(r, normal, mat, L, light_position(L, fp.seed, r.id, r.depth, li), to_light, sh)) continue;
+          c_shgen++;
+          if (!have)
+            keep = sh, have = true;
+          else
+            send(sh, inst, me);
+        }
+        if (make_bounce(r, normal, fp.seed)) {
+          c_sec++;
+          if (have) send(keep, inst, me);
+          continue_as(r);
+        } else if (have) {
+          continue_as(keep);
+        } else {
+          st = L_IDLE, c_cons++;
+        }
+      }
+    }
+    if ((iter & 63u) == 0u) flush();
+  }
+  flush();
+  if (stack.overflow) c_ovf = 1;
+  count_add(&sd.ctr->instance_visits, c_visits);
+  count_add(&sd.ctr->shadow_unoccluded, c_shok);
+  count_add(&sd.ctr->fb_adds, c_fb);
+  count_add(&sd.ctr->rays_exported, c_exp);
+  count_add(&sd.ctr->stack_overflows, c_ovf);
+  count_add(&sd.ctr->queue_overflows, c_qovf);
+  count_add(&sd.ctr->routed_initial, c_routed);
+  count_add(&sd.ctr->primary_hits, c_hits);
+  count_add(&sd.ctr->shadow_generated, c_shgen);
+  count_add(&sd.ctr->secondary_generated, c_sec);
+  if (blockIdx.x == 0 && threadIdx.x == 32) atomicAdd(&sd.ctr->camera_rays, (unsigned long long)pp.cam_count);
+  if (COUNT) {
+    count_add(&sd.ctr->nodes_visited, tc.nodes);
+    count_add(&sd.ctr->tris_tested, tc.tris);
+  }
+  // ---- the image is complete in the root's memory: every contribution was ordered before the `consumed` count the
+  // root's control warp saw.  IceTComposite::localAdd's running clamp, applied once (min(1, sum), non-negative terms).
+  if (pp.clamp && me == pp.root) {
+    float4 *fb4 = reinterpret_cast<float4 *>(pp.root_fb);
+    for (size_t i = gtid; i < pp.fb_pix; i += (size_t)gridDim.x * TRACE_THREADS) {
+      float4 v = __ldcg(fb4 + i);
+      if (v.w != 0.f) {
+        v.x = fminf(v.x, 1.f), v.y = fminf(v.y, 1.f), v.z = fminf(v.z, 1.f);
+        fb4[i] = v;
+      }
+    }
+  }
 }
 
 } // namespace gvt

@@ -11,7 +11,9 @@
 Both schedulers also have an NVLink peer path (`p2p_connect`, then `p2p=True` / `render_domain_schedule_p2p`): the ranks map
 each other's framebuffer and inbound ray queues with CUDA IPC; the trace kernel stores migrating rays straight into the
 owner's queue and the film rows / touched pixels go straight into the root's framebuffer, so the only collective left on
-the data path is the 8-byte termination all-reduce of the DomainScheduler.
+the data path is the 8-byte termination all-reduce of the round-synchronous DomainScheduler.  `render_domain_persist` removes
+that one too: one persistent kernel per rank and frame, termination found on the device (gvtb200_domain_frame_persist), and
+`plan_servers` / `apply_server_plan` let several ranks serve a hot domain (replicas or NVLink-mapped BLAS).
 
 The host logic (row shards, split sizes, termination) is backend-agnostic and is covered on CPU with gloo, world_size 2.
 """
@@ -129,150 +131,125 @@ def render_domain_schedule_p2p(engine, dist, rank, world, max_rounds=10000, root
     return log
 
 
-class AsyncTermination:
-    """Termination rule of the asynchronous DomainScheduler (Mattern's four-counter method; stands in for the two-phase
-    vote of core/comm/vote/vote.cpp).  Feed it the all-reduced (busy, sent, received) of every poll, in order; a poll's
-    values must have been read after the previous poll's all-reduce ended.  The frame is over when two consecutive polls
-    find no rank busy and the same totals with sent == received: nothing was in flight during the second poll."""
-
-    def __init__(self):
-        self.prev = None
-
-    def update(self, busy, sent, received):
-        quiet = busy == 0 and sent == received
-        done = quiet and self.prev == (sent, received)
-        self.prev = (sent, received) if quiet else None
-        return done
+def render_domain_persist(engine, root=0, tile_rows=8):
+    """One DomainScheduler frame as ONE persistent kernel per rank (after p2p_connect; world 1 needs no peers): camera rays
+    are sharded 1/world per rank, migrating rays go into the serving rank's inbound queue over NVLink and are picked up by
+    waiting lanes, termination and the composite happen on the device.  No collective, no host round trip inside the frame
+    (the reference's nearest relative is scheduler::AsyncDomain, tracer/Domain/DomainTracer.cpp:109-192).  Asynchronous on
+    the engine's stream; engine.sync() reports time-outs and full queues."""
+    engine.domain_frame_persist(root, tile_rows)
 
 
-class AsyncBoard:
-    """Control plane of the asynchronous DomainScheduler on one box: a few words per rank in POSIX shared memory (a file under
-    /dev/shm mapped by every rank).  It carries no rays -- those go over NVLink -- only what the reference's vote messages
-    carry (core/comm/vote/vote.cpp): who is idle and how many rays each rank has sent and received.  A collective cannot do
-    this job: an NCCL kernel queues behind a rank's persistent trace kernel (every SM is taken), so one busy rank would stall
-    the polls of all the others.  Words are int64; each rank writes only its own entry (seqlock: the sequence word is odd while
-    the entry is being written), rank 0 alone writes the header."""
+def plan_servers(load, owner, world, max_replicas=1, max_servers=4, slack=1.02):
+    """Which ranks serve which instance, and with what share, so that the ranks' loads even out.
 
-    HDR = 8                 # header words: [0] wave (coordinator), [1] frame whose rendering is over (coordinator)
-    ENT = 8                 # entry words: seq, wave_seen, busy, sent, received, frame, ready_frame, -
+    load[k]   measured cost of instance k in the last frame (wide BVH nodes visited, all ranks summed)
+    owner[k]  the rank that owns instance k (mpiInstanceMap, DomainTracer.h:115-144)
+    Every rank may hold up to `max_replicas` BLAS copies of instances it does not own (GraviT's hybrid schedulers load hot
+    domains on idle ranks; here the copy comes from the owner over NVLink).  Greedy: the least loaded rank with room takes a
+    copy of the most loaded rank's heaviest instance; after every step the shares of all multi-served instances are
+    re-balanced by water-filling.  Returns (ranks, weights): (n, 4) int32 (-1 = unused) and (n, 4) float32."""
+    load = np.asarray(load, np.float64)
+    n = len(load)
+    servers = [[int(owner[k])] for k in range(n)]
+    share = [{int(owner[k]): 1.0} for k in range(n)]
+    held = [0] * world
 
-    def __init__(self, path, rank, world, create):
-        self.path, self.rank, self.world = path, rank, world
-        n = self.HDR + self.ENT * world
-        if create:
-            np.zeros(n, np.int64).tofile(path)
-        self.a = np.memmap(path, dtype=np.int64, mode="r+", shape=(n,))
-        self.wave = 0       # coordinator only: the wave being collected
-        self.term = AsyncTermination()
+    def rank_load():
+        rl = np.zeros(world)
+        for k in range(n):
+            for r, x in share[k].items():
+                rl[r] += load[k] * x
+        return rl
 
-    @classmethod
-    def connect(cls, dist, rank, world):
-        """Rank 0 creates the board, the others map it (the path travels through torch.distributed)."""
-        import os
-        import tempfile
+    def rebalance(sweeps=30):
+        for _ in range(sweeps):
+            rl = rank_load()
+            for k in range(n):
+                if len(servers[k]) < 2 or load[k] <= 0:
+                    continue
+                others = {r: rl[r] - load[k] * share[k][r] for r in servers[k]}
+                # water level L: sum(max(0, L - others)) == load[k]
+                lv = sorted(others.values())
+                level = None
+                for m in range(len(lv), 0, -1):
+                    cand = (load[k] + sum(lv[:m])) / m
+                    if cand >= lv[m - 1]:
+                        level = cand
+                        break
+                for r in servers[k]:
+                    new = max(0.0, level - others[r]) / load[k]
+                    rl[r] += load[k] * (new - share[k][r])
+                    share[k][r] = new
 
-        box = [None]
-        if rank == 0:
-            root = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
-            fd, box[0] = tempfile.mkstemp(prefix="gvtb200_board_", dir=root)
-            os.close(fd)
-            board = cls(box[0], rank, world, True)
-        if world > 1:
-            dist.broadcast_object_list(box, src=0)
-        if rank != 0:
-            board = cls(box[0], rank, world, False)
-        if world > 1:
-            dist.barrier()
-        return board
-
-    def close(self):
-        import os
-
-        del self.a
-        if self.rank == 0:
-            try:
-                os.unlink(self.path)
-            except OSError:
-                pass
-
-    def _e(self, r):
-        return self.HDR + self.ENT * r
-
-    def publish(self, wave_seen, busy, sent, received, frame):
-        a, e = self.a, self._e(self.rank)
-        a[e] += 1  # odd: being written
-        a[e + 1], a[e + 2], a[e + 3], a[e + 4], a[e + 5] = wave_seen, int(busy), sent, received, frame
-        a[e] += 1
-
-    def read(self, r):
-        a, e = self.a, self._e(r)
-        while True:
-            s1 = int(a[e])
-            v = [int(x) for x in a[e + 1:e + 6]]
-            if not (s1 & 1) and int(a[e]) == s1:
-                return v
-
-    def frame_barrier(self, frame, spin=None):
-        """Every rank has finished gvtb200_domain_async_reset for `frame` (nobody publishes tails into a rank that has not
-        cleared them yet)."""
-        self.a[self._e(self.rank) + 6] = frame
-        while any(int(self.a[self._e(r) + 6]) < frame for r in range(self.world)):
-            if spin:
-                spin()
-
-    def current_wave(self):
-        return int(self.a[0])
-
-    def finished(self, frame):
-        return int(self.a[1]) >= frame
-
-    def coordinate(self, frame):
-        """Rank 0, once per poll: when every rank has published a snapshot taken after the current wave started, apply the
-        four-counter rule to the wave and start the next one."""
-        ents = [self.read(r) for r in range(self.world)]
-        if any(e[4] != frame or e[0] != self.wave for e in ents):
-            return
-        if self.term.update(sum(e[1] for e in ents), sum(e[2] for e in ents), sum(e[3] for e in ents)):
-            self.a[1] = frame
-            self.term = AsyncTermination()
-        self.wave += 1
-        self.a[0] = self.wave
+    total = load.sum()
+    if total > 0:
+        for _ in range(world * max_replicas):
+            rl = rank_load()
+            r_max = int(np.argmax(rl))
+            if rl[r_max] <= slack * total / world:
+                break
+            room = [r for r in range(world) if held[r] < max_replicas and r != r_max]
+            if not room:
+                break
+            r_min = min(room, key=lambda r: rl[r])
+            cands = sorted((k for k in range(n) if r_max in servers[k] and r_min not in servers[k] and len(servers[k]) < max_servers),
+                           key=lambda k: -load[k] * share[k][r_max])
+            if not cands or rl[r_min] >= rl[r_max]:
+                break
+            servers[cands[0]].append(r_min)
+            share[cands[0]][r_min] = 0.0
+            held[r_min] += 1
+            rebalance()
+    ranks = np.full((n, 4), -1, np.int32)
+    weights = np.zeros((n, 4), np.float32)
+    for k in range(n):
+        live = [r for r in servers[k] if share[k][r] > 1e-4 or r == owner[k]]
+        for j, r in enumerate(live):
+            ranks[k, j], weights[k, j] = r, max(share[k][r], 1e-4 if r == owner[k] else 0.0)
+    return ranks, weights
 
 
-def render_domain_schedule_async(engine, board, rank, world, frame, root=0, timeout_s=120.0):
-    """One DomainScheduler frame without exchange rounds (scheduler::AsyncDomain, tracer/Domain/DomainTracer.cpp:109-192)
-    over the NVLink peer path (after p2p_connect).  Every rank free-runs: each poll it asks its engine to trace whatever its
-    peers have published (non-blocking: nothing happens while its previous kernels are still running) and posts (busy, sent,
-    received) on the shared-memory board; rank 0 also plays the coordinator of the termination waves.  `frame` is a counter
-    that is the same on every rank and grows by one per call (starting at 1).  Returns the number of polls.  A rank that
-    waits longer than timeout_s for the others (one of them died) raises instead of spinning for ever."""
-    import time
+def planned_rank_load(load, ranks, weights, world):
+    """Per-rank load a server plan predicts (the planner's objective; reported beside the measured busy times)."""
+    rl = np.zeros(world)
+    for k in range(len(load)):
+        w = weights[k] / max(weights[k].sum(), 1e-30)
+        for j in range(4):
+            if ranks[k, j] >= 0:
+                rl[ranks[k, j]] += load[k] * w[j]
+    return rl
 
-    t0 = time.monotonic()
 
-    def check_time():
-        if time.monotonic() - t0 > timeout_s:
-            raise RuntimeError(f"asynchronous DomainScheduler: rank {rank} gave up after {timeout_s:.0f} s (frame {frame})")
+def exchange_mesh_descs(dist, scene_meshes, instances, owner, rank, world, device="cpu"):
+    """Every rank exports the meshes of the instances it owns; returns desc[k] (bytes) for every instance k."""
+    import gravit_b200 as g
 
-    engine.domain_async_reset()
-    board.frame_barrier(frame, spin=check_time)
-    engine.domain_begin_frame()
-    if rank == 0:
-        board.wave += 1  # a wave that starts inside this frame: snapshots of the previous frame cannot satisfy it
-        board.a[0] = board.wave
-    poll = 0
-    while True:
-        poll += 1
-        if (poll & 1023) == 0:
-            check_time()
-        wave = board.current_wave()  # read BEFORE the snapshot: a snapshot tagged w was taken after wave w started
-        busy, sent, received = engine.domain_async_step()
-        board.publish(wave, busy, sent, received, frame)
-        if rank == 0:
-            board.coordinate(frame)
-        if board.finished(frame):
-            engine.domain_composite_p2p(root)
-            return poll
+    blank = bytes(g.MESH_DESC_BYTES)
+    mine = b"".join((scene_meshes[mi].export() if (owner[k] == rank and scene_meshes[mi] is not None) else blank) for k, (mi, *_rest) in enumerate(instances))
+    if world == 1:
+        allb = mine
+    else:
+        allb = gather_descriptors(dist, mine, world, device)
+    n, sz = len(instances), g.MESH_DESC_BYTES
+    return [allb[(int(owner[k]) * n + k) * sz:(int(owner[k]) * n + k + 1) * sz] for k in range(n)]
+
+
+def apply_server_plan(engine, ranks, weights, descs, rank, mode=0):
+    """Import (replica: mode 0, NVLink mapping: mode 1) the BLAS of every instance this rank serves without owning it, attach
+    it to the instance, re-commit, and install the server table.  Returns the imported meshes (keep them alive)."""
+    import gravit_b200 as g
+
+    imported = {}
+    for k in range(len(ranks)):
+        if rank in [int(r) for r in ranks[k] if r >= 0][1:]:  # entry 0 is the owner
+            m = g.Mesh.from_desc(descs[k], mode)
+            engine.set_instance_mesh(k, m)
+            imported[k] = m
+    if imported:
+        engine.commit()
+    engine.domain_set_servers(ranks, weights)
+    return imported
 
 
 def render_domain_schedule(engine, dist, rank, world, device, fb_tensor, max_rounds=10000):

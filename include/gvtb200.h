@@ -95,6 +95,9 @@ GVTB200_API int gvtb200_device_info(int *sm_count, size_t *hbm_bytes, int *cc_ma
  * postpone_num/8 of the traversing lanes hold a triangle, let a lane visit up to node_burst nodes between two warp votes.
  * Replaces the TBB grain size of EmbreeMeshAdapter.cpp:648. */
 GVTB200_API int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num, int node_burst);
+/* how long a kernel of the NVLink peer path waits for another GPU before it gives up and flags the frame (default 4000 ms;
+ * also GVTB200_PEER_TIMEOUT_MS).  The reference blocks in MPI_Wait for ever (DomainTracer.h:480-486). */
+GVTB200_API int gvtb200_set_peer_timeout_ms(int ms);
 
 /* ---- B1: the engine adapter (Adapter.h:44-88) --------------------------------------------------------- */
 /* replaces EmbreeMeshAdapter::EmbreeMeshAdapter (adapter/embree/EmbreeMeshAdapter.cpp:125-162): takes the
@@ -147,6 +150,10 @@ GVTB200_API int gvtb200_scene_set_camera(gvtb200_scene scene, const float eye[3]
 /* api::addFilm (api/api.cpp:457-468) */
 GVTB200_API int gvtb200_scene_set_film(gvtb200_scene scene, int width, int height);
 GVTB200_API int gvtb200_scene_set_flags(gvtb200_scene scene, uint32_t flags, uint32_t seed);
+/* memory budget of the frame's ray queues, in rays per queue (0 = sized for the whole frame, the default).  The reference
+ * grows its std::vector queues without bound (TracerBase.h:403-409); here a frame that needs more than the budget fails with
+ * GVTB200_ERR_CAPACITY -- no ray is ever dropped silently. */
+GVTB200_API int gvtb200_scene_set_queue_limit(gvtb200_scene scene, size_t max_rays);
 /* AbstractTrace::Initialize (algorithm/TracerBase.h:247-308): builds the top-level instance BVH exactly as
  * data/accel/BVH.cpp:44-216 does (same split search, same std::partition) and uploads it. */
 GVTB200_API int gvtb200_scene_commit(gvtb200_scene scene);
@@ -182,8 +189,9 @@ typedef struct gvtb200_counters {
   uint64_t nodes_visited;   /* only when profiling counters are enabled */
   uint64_t tris_tested;
   uint64_t rays_exported; /* domain scheduler: rays handed to other ranks */
-  uint64_t stack_overflows; /* rays whose traversal stack overflowed (must be 0; deeper BVHs need GVT_BLAS_STACK raised) */
-  uint64_t queue_overflows; /* NVLink peer path: rays dropped because a peer's inbound queue was full (must be 0) */
+  uint64_t stack_overflows; /* rays whose traversal stack overflowed; non-zero => GVTB200_ERR_CAPACITY */
+  uint64_t queue_overflows; /* rays that found a ray queue (local, or a peer's inbound queue) full; non-zero => the frame calls
+                               return GVTB200_ERR_CAPACITY */
 } gvtb200_counters;
 GVTB200_API int gvtb200_render_frame(gvtb200_scene scene, int row0, int row1, float *rgba_out, gvtb200_counters *counters);
 /* same, asynchronous on the scene's stream, nothing copied back (bench / multi-GPU drivers) */
@@ -207,6 +215,13 @@ GVTB200_API int gvtb200_scene_launch_records(gvtb200_scene scene, int cap, int *
 /* device pointer of the RGBA float framebuffer (W*H*4) and the CUDA stream the scene launches on, so that
  * the multi-GPU drivers can hand them to NCCL (replaces icetCompositeImage, composite/IceTComposite.cpp:96) */
 GVTB200_API int gvtb200_scene_device_framebuffer(gvtb200_scene scene, void **d_rgba, void **cuda_stream);
+/* Parallel read-back of a multi-GPU frame (replaces the gather behind icetCompositeImage, composite/IceTComposite.cpp:96-101,
+ * and colorbf(), IceTComposite.h:106): this rank's row tiles (rows (b*tile_stride + tile_index)*tile_rows + k) of the final
+ * image -- taken from its own framebuffer (src_rank < 0: ImageScheduler, the rows it rendered) or from attached rank
+ * src_rank's framebuffer over NVLink (DomainScheduler: the root holds the composited image) -- are clamped and copied to the
+ * SAME rows of rgba_image, a full-size W*H*4 float host image (e.g. a pinned mapping shared by the ranks), over this rank's
+ * own PCIe link.  Asynchronous on the scene's stream. */
+GVTB200_API int gvtb200_framebuffer_read_rows(gvtb200_scene scene, float *rgba_image, int tile_rows, int tile_index, int tile_stride, int src_rank);
 /* final clamp after a cross-GPU sum (localAdd's clamp, composite/IceTComposite.cpp:113-114) */
 GVTB200_API int gvtb200_framebuffer_clamp(gvtb200_scene scene);
 /* elapsed GPU time (ms) of the last render_frame[_async] on this scene, measured with CUDA events on the
@@ -250,6 +265,7 @@ typedef struct gvtb200_peer_desc {
   uint8_t mail_handle[64];     /* flags: go, done[world], error */
   uint64_t raw[4];             /* the same four device pointers, valid inside the creating process */
   uint64_t inbox_cap;          /* rays per inbound queue */
+  uint64_t inbox_cap1;         /* the second queue's (only the round-synchronous DomainScheduler uses it) */
   uint64_t fb_pix;
   int32_t pid, device;
 } gvtb200_peer_desc;
@@ -259,7 +275,7 @@ GVTB200_API int gvtb200_p2p_detach(gvtb200_scene scene);
 /* Tracer<ImageScheduler> on `world_size` GPUs: this rank's row tiles (as gvtb200_render_frame_tiles, index = rank, stride =
  * world_size), then the clamped rows go straight into rank `root`'s framebuffer over NVLink.  The root tells the peers when
  * its framebuffer may be overwritten (after its own clear) and waits for their rows before the call's work completes on
- * its stream; a peer that waits longer than ~4 s gives up and the next gvtb200_scene_sync reports it. */
+ * its stream; a peer that waits longer than the peer time-out gives up and the next gvtb200_scene_sync reports it. */
 enum { GVTB200_P2P_CLEAR = 1, GVTB200_P2P_TRACE = 2, GVTB200_P2P_WAIT = 4, GVTB200_P2P_ALL = 7 };
 /* phases: GVTB200_P2P_ALL for a frame.  Several scenes of ONE process on ONE GPU (the single-process tests) split the
  * root's call -- CLEAR before the peers' frames, TRACE|WAIT after them -- so that no spinning kernel waits for a launch
@@ -271,22 +287,48 @@ GVTB200_API int gvtb200_image_frame_p2p(gvtb200_scene scene, int row0, int row1,
  * (may be NULL) receives the DEVICE address of the frame's cumulative exported-ray counter (uint64) for the termination
  * all-reduce: the frame is over when the sum over ranks did not grow during a round. */
 GVTB200_API int gvtb200_domain_round_p2p(gvtb200_scene scene, int round, void **d_exported_total);
-/* Asynchronous DomainScheduler (scheduler::AsyncDomain, Types.h:53-54; the loop of tracer/Domain/DomainTracer.cpp:109-192
- * with SendRayList messages replaced by stores over NVLink and the two-phase vote of core/comm/vote/vote.cpp replaced by
- * sent/received counters).  No round barrier: a rank traces whatever has arrived whenever its stream is idle.
- *   gvtb200_domain_async_reset   once per frame, BEFORE a host barrier across the ranks: clears this rank's counters
- *                                and the tails its peers publish into.
- *   gvtb200_domain_begin_frame   (as for the round-synchronous schedule) camera rays, first routing.
- *   gvtb200_domain_async_step    non-blocking.  If the previous step's kernels are still running: *busy = 1.  Else, if
- *                                peers have published rays this rank has not consumed: gathers them, traces them (rays for
- *                                other ranks go straight into this rank's region of the owner's inbound area), publishes
- *                                its own tails; *busy = 1.  Else *busy = 0 and *sent / *received are this rank's cumulative
- *                                ray counts.  The frame is over when two consecutive polls of ALL ranks (the second one
- *                                started after the first one ended) find every rank idle with equal, unchanged totals
- *                                sum(sent) == sum(received) (Mattern's four-counter rule).
- *   gvtb200_domain_composite_p2p as for the round-synchronous schedule. */
-GVTB200_API int gvtb200_domain_async_reset(gvtb200_scene scene);
-GVTB200_API int gvtb200_domain_async_step(gvtb200_scene scene, int *busy, uint64_t *sent, uint64_t *received);
+/* Persistent DomainScheduler: Tracer<DomainScheduler>::operator() (algorithm/DomainTracer.h:185-368), SendRays (:370-496), the
+ * termination test (:339-349) and the composite (composite/IceTComposite.cpp:84-117) as ONE kernel launch per rank and frame;
+ * like the reference's asynchronous tracer (scheduler::AsyncDomain, Types.h:53-54; tracer/Domain/DomainTracer.cpp:109-192,
+ * votes core/comm/vote/vote.cpp) it has no exchange rounds.  Every rank generates 1/world_size of the camera rays (row tiles of
+ * tile_rows rows dealt round-robin), a ray bound for an instance another rank serves is stored into that rank's inbound
+ * queue over NVLink by the trace kernel and picked up there by a waiting lane without any launch or host round trip, shading
+ * happens in the same kernel, finished shadow rays are added straight into the root's framebuffer, termination is found on
+ * the device (sum of rays retired == sum of rays handed out, read in that order) and the root clamps the image before its
+ * kernel ends.  world_size 1 (no peers needed) runs the same kernel on one GPU.  The call is asynchronous on the scene's
+ * stream; gvtb200_scene_sync reports time-outs and full queues.  The image is complete in the root's framebuffer. */
+GVTB200_API int gvtb200_domain_frame_persist(gvtb200_scene scene, int root, int tile_rows);
+/* grid_ctas: CTAs of the persistent kernel (0 = fill the GPU; tests that run several simulated ranks on one GPU bound it so
+ * that all of them are resident together); shade_at: a warp shades its closest hits once this many lanes hold one (1..32) */
+GVTB200_API int gvtb200_domain_persist_config(gvtb200_scene scene, int grid_ctas, int shade_at);
+/* after a persistent frame: how long this rank was busy (start barrier to its last retired ray, ms), how many rays its
+ * inbound queue received and -- for a frame rendered with gvtb200_scene_profile_counters on -- the wide BVH nodes visited per
+ * instance on this rank (n_instances entries; input of a replica plan).  Any pointer may be NULL. */
+GVTB200_API int gvtb200_domain_persist_stats(gvtb200_scene scene, double *busy_ms, uint64_t *inbox_rays, uint64_t *instance_load, int n_instances);
+/* Which ranks serve an instance (persistent scheduler only; default: its owner).  ranks[4*i+j], j < 4, are the ranks that
+ * hold a BLAS for instance i (-1 = unused), weights[4*i+j] their shares (NULL = equal); a ray bound for the instance picks
+ * one by a hash of its direction bits, so the choice is reproducible.  This is how the work of a hot domain is spread:
+ * GraviT's hybrid schedulers load a copy of a busy domain on idle ranks (the `Locations` list of a mesh,
+ * DomainTracer.h:115-144); here a rank gets its copy from the owner over NVLink (gvtb200_mesh_import). */
+GVTB200_API int gvtb200_domain_set_servers(gvtb200_scene scene, const int32_t *ranks, const float *weights, int n_instances);
+/* swap the mesh of an instance (NULL = not resident); gvtb200_scene_commit afterwards */
+GVTB200_API int gvtb200_scene_set_instance_mesh(gvtb200_scene scene, int instance, gvtb200_mesh mesh);
+
+/* BLAS sharing between ranks: the owner describes its mesh, another rank (process, or device of the same process) imports
+ * it without rebuilding anything: GVTB200_IMPORT_COPY = a replica in the importer's HBM, fetched over NVLink;
+ * GVTB200_IMPORT_MAP = no copy, the importer traverses the owner's arrays through peer-mapped pointers. */
+typedef struct gvtb200_mesh_desc {
+  uint8_t handle[6][64]; /* cudaIpcMemHandle_t of: nodes, triangle records, faces, vertex normals, vertex colours, materials */
+  uint64_t raw[6];       /* the same device pointers (valid inside the owner's process), 0 = absent */
+  uint64_t bytes[6];
+  uint64_t tri_slots;
+  float mat[8];          /* the mesh material */
+  uint32_t n_tris, n_nodes, n_vertices, n_mats;
+  int32_t pid, device;
+} gvtb200_mesh_desc;
+enum { GVTB200_IMPORT_COPY = 0, GVTB200_IMPORT_MAP = 1 };
+GVTB200_API int gvtb200_mesh_export(gvtb200_mesh mesh, gvtb200_mesh_desc *out);
+GVTB200_API int gvtb200_mesh_import(const gvtb200_mesh_desc *desc, int mode, gvtb200_mesh *out);
 /* end of a DomainScheduler frame: every rank adds the pixels it touched to the root's framebuffer; the root waits for all
  * of them, then clamps (IceTComposite::localAdd's clamp, composite/IceTComposite.cpp:113-114). */
 GVTB200_API int gvtb200_domain_composite_p2p(gvtb200_scene scene, int root);

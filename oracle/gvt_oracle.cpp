@@ -935,6 +935,9 @@ void shuffleRays(const Scene &s, std::vector<Ray80> &rays, int domID, std::map<i
     Ray80 &r = rays[i];
     if (next[i] != -1) {
       r.o = r.o + r.d * (tt[i] * 0.95f); // TracerBase.h:394
+      // FLAG_SHADOW_TO_LIGHT (documented deviation): t_max is the distance left to the light, so it shrinks with the origin
+      // advance; otherwise occluders behind the light in a later instance would shadow the pixel
+      if ((s.flags & FLAG_SHADOW_TO_LIGHT) && r.type == RAY_SHADOW) r.t_max = r.t_max - tt[i] * 0.95f;
       if (drop_mode && s.owner[next[i]] != rank) continue;
       queue[next[i]].push_back(r);
     } else if (!drop_mode && r.type == RAY_SHADOW && length(r.color) > 0) { // :396-399

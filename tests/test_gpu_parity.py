@@ -485,57 +485,131 @@ def test_domain_scheduler_peer_exchange(gpu, world):
         e.close()
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("world,scene", [(2, "simple"), (3, "simple"), (4, "gyroid")])
-def test_domain_scheduler_async_peer(gpu, world, scene):
-    """scheduler::AsyncDomain (SURVEY 8(f) N3; tracer/Domain/DomainTracer.cpp:109-192): no exchange rounds -- every rank
-    traces whatever its peers have published whenever it is idle, termination by sent/received counters.  The rays that
-    change rank are the same rays as in the round-synchronous schedule (same total as the oracle's routing log), the
-    composited image equals the single-process image."""
-    from gravit_b200 import schedulers
+def _persist_frame(ranks, root=0, tile_rows=4, grid=24):
+    """One persistent DomainScheduler frame on simulated ranks: every rank's kernel must be resident at the same time on the
+    one GPU they share (they wait for each other at the start barrier and exchange rays while running), so the grids are
+    bounded; each scene launches on its own stream."""
+    for e in ranks:
+        e.domain_persist_config(grid_ctas=grid, shade_at=4)
+    for e in ranks:
+        e.domain_frame_persist(root, tile_rows)
+    for e in ranks:
+        e.sync()
 
-    d = library.simple_scene(256, 256) if scene == "simple" else library.gyroid_scene(48, 2, 320, 240)
-    flags = 1 if scene == "simple" else d.flags
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,scene", [(1, "simple"), (2, "simple"), (3, "simple"), (4, "gyroid"), (1, "bunny_obj")])
+def test_domain_scheduler_persistent(gpu, world, scene):
+    """The persistent DomainScheduler (gvtb200_domain_frame_persist; the reference's nearest relative is scheduler::AsyncDomain,
+    tracer/Domain/DomainTracer.cpp:109-192): one kernel per rank and frame, sharded camera rays, rays stored into the serving
+    rank's inbound queue and picked up by waiting lanes, shading in the same kernel, termination and composite on the device.
+    The image in the root's framebuffer equals the single-process oracle image; hits, shadow rays and framebuffer adds equal
+    the oracle's counts."""
+    g = gpu
+    g.check(g.lib().gvtb200_set_peer_timeout_ms(3000))
+    d = {"simple": lambda: library.simple_scene(256, 256), "gyroid": lambda: library.gyroid_scene(48, 2, 320, 240),
+         "bunny_obj": lambda: library.bunny_obj_scene(200, 160)}[scene]()
+    flags = 1 if scene != "gyroid" else d.flags
     o = oracle_scene(d, flags)
-    o.set_owner(np.arange(len(d.instances)) % world)
-    ref, st = o.render(schedule=1, world_size=world, threads=8)
-    exchanged_o = int(sum(m.sum() for m in o.route_log(world)))
-    ref1, _ = o.render(schedule=0, world_size=1, threads=8)
-    ranks, owner = _standalone_ranks(gpu, d, flags, world)
-    _connect(ranks)
-    for frame in range(2):  # twice: regions, tails and counters must be reusable
-        for e in ranks:
-            e.domain_async_reset()
-        for e in ranks:
-            e.domain_begin_frame()
-        term = schedulers.AsyncTermination()
-        polls = 0
-        while True:
-            res = [e.domain_async_step() for e in ranks]
-            polls += 1
-            assert polls < 200000
-            if term.update(sum(int(r[0]) for r in res), sum(r[1] for r in res), sum(r[2] for r in res)):
-                break
-        assert sum(r[1] for r in res) == exchanged_o and exchanged_o > 0
-        assert sum(e.counters()["rays_exported"] for e in ranks) == exchanged_o
-        assert all(e.counters()["queue_overflows"] == 0 for e in ranks)
-        for e in ranks[1:] + ranks[:1]:  # peers add their pixels, the root waits and clamps
-            e.domain_composite_p2p(0)
-        for e in ranks:
-            e.sync()
-        fb = ranks[0].fb_read(d.width, d.height)
-        assert np.allclose(fb, ref, atol=1e-6) and np.allclose(fb, ref1, atol=1e-6)
-        assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref1)) >= 50.0
+    ref1, st = o.render(schedule=0, world_size=1, threads=8)
+    ranks, owner = _standalone_ranks(g, d, flags, world)
+    if world > 1:
+        _connect(ranks)
+    for frame, root in enumerate([0, 0, world - 1]):  # three frames: counters, flags and queues are reusable; any root works
+        _persist_frame(ranks, root)
+        fb = ranks[root].fb_read(d.width, d.height)
+        assert np.allclose(fb, ref1, atol=1e-6), (frame, float(np.abs(fb - ref1).max()))
+        assert po.image_diff(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref1)) == 0
+        c = [e.counters() for e in ranks]
+        for k in ("primary_hits", "shadow_generated", "fb_adds", "routed_initial", "camera_rays"):
+            assert sum(x[k] for x in c) == st[k], (k, [x[k] for x in c], st[k])
+        assert all(x["queue_overflows"] == 0 and x["stack_overflows"] == 0 for x in c)
+        if world > 1:
+            assert sum(x["rays_exported"] for x in c) > 0
     for e in ranks:
         e.close()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("schedule", ["rounds", "async"])
-def test_domain_scheduler_with_bounces(gpu, schedule):
-    """Both DomainScheduler schedules with rayMaxDepth 2 on 3 simulated ranks: secondary rays migrate as well (their random
-    numbers are a function of ray id and depth, not of who traces them), so the number of rays that change rank equals the
-    oracle's and the image matches the single-process image to fp32 reassociation."""
+@pytest.mark.parametrize("mode", ["replica", "mapped"])
+def test_domain_scheduler_persistent_shared_blas(gpu, mode):
+    """Several ranks serve one domain: the owner exports its BLAS, two other ranks import it -- one a replica in its own
+    memory, or both a mapping of the owner's arrays -- and the server table splits the domain's rays between them by a hash of
+    the ray.  Same image, same hit counts; the importing ranks really trace in the shared domain."""
+    from gravit_b200 import schedulers
+
+    g = gpu
+    g.check(g.lib().gvtb200_set_peer_timeout_ms(3000))
+    world = 3
+    d = library.gyroid_scene(48, 2, 320, 240)
+    o = oracle_scene(d, d.flags)
+    ref1, st = o.render(schedule=0, world_size=1, threads=8)
+    ranks, owner = _standalone_ranks(g, d, d.flags, world)
+    _connect(ranks)
+    # a counted frame measures the load per instance (summed over the ranks), the planner spreads the hot ones
+    for e in ranks:
+        e.profile_counters(True)
+    _persist_frame(ranks)
+    load = sum(e.domain_persist_stats(len(d.instances))[2].astype(np.float64) for e in ranks)
+    for e in ranks:
+        e.profile_counters(False)
+    assert load.sum() > 0
+    tab_r, tab_w = schedulers.plan_servers(load, owner, world, max_replicas=2)
+    assert (tab_r[:, 1] >= 0).any()
+    before = schedulers.planned_rank_load(load, np.stack([owner, -np.ones(8), -np.ones(8), -np.ones(8)], 1).astype(np.int32), np.eye(4, dtype=np.float32)[[0] * 8], world)
+    after = schedulers.planned_rank_load(load, tab_r, tab_w, world)
+    assert after.max() < before.max()
+    descs = [ranks[owner[k]]._keep[d.instances[k][0]].export() for k in range(len(d.instances))]
+    keep = [schedulers.apply_server_plan(e, tab_r, tab_w, descs, r, mode=g.IMPORT_COPY if mode == "replica" else g.IMPORT_MAP) for r, e in enumerate(ranks)]
+    assert any(keep)
+    for frame in range(2):
+        _persist_frame(ranks)
+        fb = ranks[0].fb_read(d.width, d.height)
+        assert np.allclose(fb, ref1, atol=1e-6)
+        c = [e.counters() for e in ranks]
+        for k in ("primary_hits", "shadow_generated", "fb_adds"):
+            assert sum(x[k] for x in c) == st[k]
+    # busy time and inbound-ray statistics exist for every rank
+    for e in ranks:
+        busy, rays, _ = e.domain_persist_stats()
+        assert busy >= 0.0 and rays >= 0
+    for e in ranks:
+        e.close()
+    del keep
+
+
+@pytest.mark.gpu
+def test_domain_scheduler_persistent_with_bounces_and_lights(gpu):
+    """rayMaxDepth 3, two lights, 3 simulated ranks: bounces continue in the lane, extra shadow rays go through the rank's own
+    inbound queue, secondary rays migrate.  Random numbers are a function of (ray id, depth), not of who traces the ray, so the
+    counters equal the oracle's and the image matches to fp32 reassociation."""
+    g = gpu
+    g.check(g.lib().gvtb200_set_peer_timeout_ms(3000))
+    world = 3
+    d = library.simple_scene(192, 192)
+    d.depth = 3
+    d.lights = d.lights + [((2.0, 2.0, 1.0), (0.6, 0.5, 0.4))]
+    flags = 1
+    o = oracle_scene(d, flags)
+    ref1, st = o.render(schedule=0, world_size=1, threads=8)
+    ranks, owner = _standalone_ranks(g, d, flags, world)
+    _connect(ranks)
+    _persist_frame(ranks)
+    c = [e.counters() for e in ranks]
+    for k in ("primary_hits", "shadow_generated", "secondary_generated", "fb_adds"):
+        assert abs(sum(x[k] for x in c) - st[k]) <= max(2, st[k] // 1000), (k, sum(x[k] for x in c), st[k])
+    assert st["secondary_generated"] > 0
+    fb = ranks[0].fb_read(d.width, d.height)
+    assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref1)) >= 50.0
+    for e in ranks:
+        e.close()
+
+
+@pytest.mark.gpu
+def test_domain_scheduler_with_bounces(gpu):
+    """The round-synchronous DomainScheduler with rayMaxDepth 2 on 3 simulated ranks: secondary rays migrate as well (their
+    random numbers are a function of ray id and depth, not of who traces them), so the number of rays that change rank equals
+    the oracle's and the image matches the single-process image to fp32 reassociation."""
     from gravit_b200 import schedulers
 
     world = 3
@@ -549,29 +623,17 @@ def test_domain_scheduler_with_bounces(gpu, schedule):
     ref1, _ = o.render(schedule=0, world_size=1, threads=8)
     ranks, owner = _standalone_ranks(gpu, d, flags, world)
     _connect(ranks)
-    if schedule == "async":
-        for e in ranks:
-            e.domain_async_reset()
     for e in ranks:
         e.domain_begin_frame()
-    if schedule == "async":
-        term = schedulers.AsyncTermination()
-        for polls in range(200000):
-            res = [e.domain_async_step() for e in ranks]
-            if term.update(sum(int(r[0]) for r in res), sum(r[1] for r in res), sum(r[2] for r in res)):
-                break
-        else:
-            raise AssertionError("no termination")
-    else:
-        log = []
-        for rnd in range(100):
-            for e in ranks:
-                e.domain_round_p2p(rnd)
-            for e in ranks:
-                e.sync()
-            log.append(sum(e.counters()["rays_exported"] for e in ranks))
-            if schedulers.domain_terminated(log):
-                break
+    log = []
+    for rnd in range(100):
+        for e in ranks:
+            e.domain_round_p2p(rnd)
+        for e in ranks:
+            e.sync()
+        log.append(sum(e.counters()["rays_exported"] for e in ranks))
+        if schedulers.domain_terminated(log):
+            break
     assert sum(e.counters()["rays_exported"] for e in ranks) == exchanged_o and exchanged_o > 0
     assert sum(e.counters()["secondary_generated"] for e in ranks) == st["secondary_generated"] > 0
     assert all(e.counters()["queue_overflows"] == 0 for e in ranks)
@@ -584,6 +646,41 @@ def test_domain_scheduler_with_bounces(gpu, schedule):
     assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref)) >= 50.0
     for e in ranks:
         e.close()
+
+
+@pytest.mark.gpu
+def test_queue_overflow_is_an_error(gpu):
+    """The reference never drops a ray (its queues are std::vectors, TracerBase.h:403-409).  With a queue budget too small
+    for the frame (gvtb200_scene_set_queue_limit) the frame calls fail with GVTB200_ERR_CAPACITY -- from the wave path
+    (hit / shadow queues) and from the persistent path (inbound queue) -- instead of returning an incomplete image, and the
+    same scene renders correctly again once the budget is lifted."""
+    g = gpu
+    d = library.simple_scene(192, 192)
+    d.depth = 2
+    d.lights = d.lights + [((2.0, 2.0, 1.0), (0.6, 0.5, 0.4))]
+    o = oracle_scene(d, 1)
+    ref1, st = o.render(schedule=0, world_size=1, threads=8)
+    ranks, _ = _standalone_ranks(g, d, 1, 1)
+    e = ranks[0]
+    fb, c = e.render(d.width, d.height)
+    assert c["queue_overflows"] == 0 and po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref1)) >= 50.0
+    e.set_queue_limit(1000)
+    with pytest.raises(g.EngineError, match="-4"):
+        e.render(d.width, d.height)
+    assert e.counters()["queue_overflows"] > 0
+    e.render_async(d.height)
+    with pytest.raises(g.EngineError, match="-4"):
+        e.sync()
+    with pytest.raises(g.EngineError, match="-4"):  # two lights + bounces: the extra rays go through the inbound queue
+        e.domain_frame_persist(0, 4)
+        e.sync()
+    e.set_queue_limit(0)
+    fb, c = e.render(d.width, d.height)
+    assert c["queue_overflows"] == 0 and po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref1)) >= 50.0
+    e.domain_frame_persist(0, 4)
+    e.sync()
+    assert po.psnr(po.fb_to_ppm_bytes(e.fb_read(d.width, d.height)), po.fb_to_ppm_bytes(ref1)) >= 50.0
+    e.close()
 
 
 @pytest.mark.gpu
