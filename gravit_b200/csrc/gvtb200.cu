@@ -1835,6 +1835,8 @@ int gvtb200_domain_set_servers(gvtb200_scene s, const int32_t *ranks, const floa
   if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
   if (!ranks) { // back to "the owner serves its instances"
     s->p2p.servers.clear();
+    cudaSetDevice(s->device);
+    dfree(s->p2p.d_servers);
     return GVTB200_OK;
   }
   if (n != (int)s->inst.size()) return fail(GVTB200_ERR_INVALID, "server table has %d entries, scene has %zu instances", n, s->inst.size());
@@ -1861,6 +1863,10 @@ int gvtb200_domain_set_servers(gvtb200_scene s, const int32_t *ranks, const floa
     else if (cnt < 3) tab[i].y |= 0xFFFF0000u;
   }
   s->p2p.servers = tab;
+  CU(cudaSetDevice(s->device));
+  dfree(s->p2p.d_servers);
+  CU(dalloc(&s->p2p.d_servers, tab.size()));
+  CU(cudaMemcpy(s->p2p.d_servers, tab.data(), tab.size() * sizeof(uint4), cudaMemcpyHostToDevice));
   return GVTB200_OK;
 }
 int gvtb200_scene_set_instance_mesh(gvtb200_scene s, int instance, gvtb200_mesh mesh) {
@@ -1871,11 +1877,26 @@ int gvtb200_scene_set_instance_mesh(gvtb200_scene s, int instance, gvtb200_mesh 
   s->committed = false;
   return GVTB200_OK;
 }
+static int persist_prepare(gvtb200_scene s);
 int gvtb200_domain_persist_config(gvtb200_scene s, int grid_ctas, int shade_at) {
   if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
   if (grid_ctas < 0 || shade_at < 1 || shade_at > 32) return fail(GVTB200_ERR_INVALID, "grid_ctas %d (>= 0), shade_at %d (1..32)", grid_ctas, shade_at);
   s->p2p.grid_limit = grid_ctas, s->p2p.shade_at = shade_at;
-  return GVTB200_OK;
+  NEED_INIT();
+  CU(cudaSetDevice(s->device));
+  return persist_prepare(s);
+}
+static int persist_prepare(gvtb200_scene s) {
+  const int grid = std::max(persist_grid(s->device, false), persist_grid(s->device, true));
+  const size_t threads = (size_t)std::max(grid, 2) * TRACE_THREADS;
+  if (s->p2p.scr_cap < threads) {
+    dfree(s->p2p.d_scr2), dfree(s->p2p.d_scr3);
+    CU(dalloc(&s->p2p.d_scr2, threads));
+    CU(dalloc(&s->p2p.d_scr3, threads));
+    s->p2p.scr_cap = threads;
+  }
+  if (!s->p2p.d_inst_load) CU(dalloc(&s->p2p.d_inst_load, std::max<size_t>(1, s->inst.size())));
+  return 0;
 }
 int gvtb200_domain_frame_persist(gvtb200_scene s, int root, int tile_rows) {
   NEED_SCENE();
@@ -1901,26 +1922,15 @@ int gvtb200_domain_frame_persist(gvtb200_scene s, int root, int tile_rows) {
   const int me = s->p2p.rank;
   cudaStream_t st = s->stream;
   const bool count = s->profile;
+  // (allocations happen here only the first time: cudaMalloc / cudaFree may wait for running kernels, and another rank's
+  // persistent kernel on the same device -- the single-process tests -- would be waiting for this rank's launch)
+  if (int rc = persist_prepare(s)) return rc;
   int grid = persist_grid(s->device, count);
   if (s->p2p.grid_limit > 0) grid = std::min(grid, s->p2p.grid_limit);
   grid = std::max(grid, 2);
-  const size_t threads = (size_t)grid * TRACE_THREADS;
-  if (s->p2p.scr_cap < threads) {
-    dfree(s->p2p.d_scr2), dfree(s->p2p.d_scr3);
-    CU(dalloc(&s->p2p.d_scr2, threads));
-    CU(dalloc(&s->p2p.d_scr3, threads));
-    s->p2p.scr_cap = threads;
-  }
-  const size_t n_inst = std::max<size_t>(1, s->inst.size());
-  if (!s->p2p.d_inst_load) CU(dalloc(&s->p2p.d_inst_load, n_inst));
-  if (count) CU(cudaMemsetAsync(s->p2p.d_inst_load, 0, n_inst * 8, st));
-  if (!s->p2p.servers.empty()) {
-    if (s->p2p.servers.size() != s->inst.size()) return fail(GVTB200_ERR_INVALID, "server table is stale (instances changed)");
-    dfree(s->p2p.d_servers);
-    CU(dalloc(&s->p2p.d_servers, s->p2p.servers.size()));
-    CU(cudaMemcpyAsync(s->p2p.d_servers, s->p2p.servers.data(), s->p2p.servers.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
-  } else
-    dfree(s->p2p.d_servers);
+  if ((size_t)grid * TRACE_THREADS > s->p2p.scr_cap) return fail(GVTB200_ERR_INVALID, "persistent grid grew after gvtb200_domain_persist_config");
+  if (count) CU(cudaMemsetAsync(s->p2p.d_inst_load, 0, std::max<size_t>(1, s->inst.size()) * 8, st));
+  if (!s->p2p.servers.empty() && s->p2p.servers.size() != s->inst.size()) return fail(GVTB200_ERR_INVALID, "server table is stale (instances changed)");
   FrameParams fp;
   build_frame_params(*s, fp);
   PersistParams pp;

@@ -642,18 +642,22 @@ struct SmemStack {
 // should go back to its caller: all lanes are finished, or at least tune.exit_at lanes are not traversing and there is
 // something better to do for them (`resting` = lanes that had no ray on entry; a lane outside `resting` that stopped
 // traversing has a finished ray to hand over; more_input = the caller can refill).  Returns this lane's `done`.
-template <bool COUNT, class Stack>
+// BUDGET > 0: return after that many iterations at the latest (the persistent kernel must look at its inbox now and then).
+template <bool COUNT, int BUDGET, class Stack>
 __device__ __forceinline__ bool warp_traverse(bool active, unsigned resting, bool more_input, const TraceTune &tune, const float4 *nodes,
                                               const float4 *tris, const RayLocal &rl, float tfar, bool any, Trav &tv, Stack &stack,
                                               TravCounters &tc, const unsigned char *s_lut) {
   const unsigned FULL = 0xffffffffu;
   bool done = false;
+  int trips = 0;
   for (;;) {
     const bool trav = active && !done;
     const unsigned tm = __ballot_sync(FULL, trav);
     if (tm == 0u) break;
     const unsigned waiting = 32u - (unsigned)__popc(tm);
-    if (waiting >= (unsigned)tune.exit_at && ((~tm & ~resting) != 0u || more_input)) break;
+    // (the persistent kernel always advances one step per call: its callers' lanes can rest in states a refill cannot end)
+    if ((BUDGET == 0 || trips > 0) && waiting >= (unsigned)tune.exit_at && ((~tm & ~resting) != 0u || more_input)) break;
+    if (BUDGET > 0 && ++trips > BUDGET) break;
     if (trav) {
 #pragma unroll 1
       for (int k = 0; k < tune.node_burst; ++k) {
@@ -795,7 +799,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
       continue;
     }
     // ---- traverse in lock step ---------------------------------------------------------------------------
-    const bool done = warp_traverse<COUNT>(active, idle, !exhausted, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
+    const bool done = warp_traverse<COUNT, 0>(active, idle, !exhausted, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
     // ---- rays that finished their instance -------------------------------------------------------------------
     if (active && done) {
       if (tv.hit.prim >= 0) {
@@ -1169,6 +1173,9 @@ __global__ void k_fb_accumulate_root(const float4 *src, float *dst, size_t npix,
 #ifndef PERSIST_MIN_BLOCKS
 #define PERSIST_MIN_BLOCKS 5
 #endif
+#ifndef PERSIST_TRIPS
+#define PERSIST_TRIPS 16
+#endif
 struct PersistParams {
   RayQueue inbox;             // this rank's inbound slots (count unused: PersistCtl::tail / head)
   const RayQueue *peer_inbox; // [world]: every rank's inbox as mapped into this GPU (entry `rank` == inbox)
@@ -1393,12 +1400,22 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
 
   unsigned iter = 0;
   unsigned long long t_idle0 = 0;
+  const unsigned long long t_start = global_ns();
   for (;;) {
     ++iter;
+    if ((iter & 4095u) == 0u) { // watchdog: a frame never runs this long (decided by lane 0: the warp leaves together)
+      const unsigned late = __shfl_sync(FULL, global_ns() - t_start > 4 * pp.timeout_ns ? 1u : 0u, 0);
+      if (late) {
+        if (lane == 0) atomicOr(&ctl->err, 1u);
+        break;
+      }
+    }
     // ---- refill idle lanes: camera rays of the shard first, then inbox tickets ---------------------------------------
     unsigned idle = __ballot_sync(FULL, st == L_IDLE);
     const unsigned busy = __ballot_sync(FULL, st >= L_ACTIVE);
-    if (idle != 0u && (busy == 0u || __popc(idle) >= tune.refill_at)) {
+    const unsigned tracing = __ballot_sync(FULL, st == L_ACTIVE);
+    const bool starved = 32 - __popc(tracing) >= tune.exit_at; // the traversal loop would come straight back
+    if (idle != 0u && (busy == 0u || starved || __popc(idle) >= tune.refill_at)) {
       const unsigned cnt = (unsigned)__popc(idle);
       if (!cam_done) {
         unsigned base = 0;
@@ -1467,7 +1484,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       if (cam_done) {
         __nanosleep(__any_sync(FULL, st == L_WAIT) ? 32 : 128);
         if ((iter & 255u) == 0u) { // a peer died, or a bug: never spin for ever
-          const unsigned long long now = global_ns();
+          const unsigned long long now = __shfl_sync(FULL, global_ns(), 0);
           if (t_idle0 == 0) t_idle0 = now;
           if (now - t_idle0 > 2 * pp.timeout_ns) {
             if (lane == 0) atomicOr(&ctl->err, 1u);
@@ -1479,8 +1496,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
     }
     t_idle0 = 0;
     // ---- traverse in lock step ----------------------------------------------------------------------------------------
+    // (leaves early for a refill only while camera rays are left -- whether the inbox has rays is not known without asking
+    // -- and after PERSIST_TRIPS iterations at the latest, so that tickets get polled and new arrivals get lanes)
     const unsigned resting = __ballot_sync(FULL, st != L_ACTIVE);
-    const bool done = warp_traverse<COUNT>(st == L_ACTIVE, resting, true, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
+    const bool done = warp_traverse<COUNT, PERSIST_TRIPS>(st == L_ACTIVE, resting, !cam_done, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
     // ---- rays that finished their instance -------------------------------------------------------------------------
     if (st == L_ACTIVE && done) {
       if (COUNT && pp.inst_load) atomicAdd(pp.inst_load + inst, (unsigned long long)(tc.nodes - nodes0));
@@ -1532,7 +1551,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
     // ---- shade the warp's closest hits (EmbreeMeshAdapter.cpp:491-601) ------------------------------------------------------
     {
       const unsigned sm = __ballot_sync(FULL, st == L_SHADE);
-      if (sm != 0u && (__popc(sm) >= pp.shade_at || __ballot_sync(FULL, st == L_ACTIVE) == 0u) && st == L_SHADE) {
+      const unsigned am = __ballot_sync(FULL, st == L_ACTIVE);
+      if (sm != 0u && (__popc(sm) >= pp.shade_at || 32 - __popc(am) >= tune.exit_at) && st == L_SHADE) {
         Ray r;
         reload(r);
         r.t = tv.hit.t;
