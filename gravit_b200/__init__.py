@@ -71,6 +71,18 @@ class EngineError(RuntimeError):
     pass
 
 
+def source_hash():
+    """sha256 over the kernel sources (gravit_b200/csrc): ties a committed ncu capture to the code it was taken from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(HERE, "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def _fp(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -544,8 +556,8 @@ class EngineScene:
         """One whole DomainScheduler frame as one persistent kernel per rank (asynchronous; sync() reports errors)."""
         check(lib().gvtb200_domain_frame_persist(self.h, root, tile_rows))
 
-    def domain_persist_config(self, grid_ctas=0, shade_at=8):
-        check(lib().gvtb200_domain_persist_config(self.h, grid_ctas, shade_at))
+    def domain_persist_config(self, grid_ctas=0, shade_sms=0):
+        check(lib().gvtb200_domain_persist_config(self.h, grid_ctas, shade_sms))
 
     def domain_persist_stats(self, n_instances=0):
         """(busy ms of this rank, rays its inbox received, per-instance wide-node visits of a counted frame or None)."""

@@ -236,14 +236,12 @@ struct gvtb200_scene_s {
     RayQueue *d_peer_inbox = nullptr; // [2][world]
     bool private_box = false;         // mailbox + inbox made for a single-rank persistent frame (nothing exported)
     // persistent DomainScheduler (gvtb200_domain_frame_persist)
-    float4 *d_scr2 = nullptr;         // per-thread backing store of rays made inside the kernel
-    int4 *d_scr3 = nullptr;
-    size_t scr_cap = 0;
+    QueueMem hitq;                    // closest hits waiting for the shader SMs (ray + hit column + ready words)
     uint4 *d_servers = nullptr;       // per instance: serving ranks + cumulative weights (gvtb200_domain_set_servers)
     std::vector<uint4> servers;
     unsigned long long *d_inst_load = nullptr; // wide nodes visited per instance (counted frames)
     int grid_limit = 0;               // CTAs of the persistent kernel (0 = fill the GPU); the single-GPU tests run several ranks on one device
-    int shade_at = 8;
+    int shade_sms = 0;                // SMs that shade instead of tracing (0 = default share)
     float *peer_fb[GVT_P2P_MAX] = {};
     PeerMail mail;
     void *opened[GVT_P2P_MAX][4] = {}; // cudaIpcOpenMemHandle results (closed on detach)
@@ -1797,8 +1795,8 @@ int gvtb200_p2p_detach(gvtb200_scene s) {
       if (p) cudaIpcCloseMemHandle(p);
       p = nullptr;
     }
-  dfree(s->p2p.d_peer_inbox), dfree(s->p2p.d_mail), dfree(s->p2p.d_scr2), dfree(s->p2p.d_scr3), dfree(s->p2p.d_inst_load);
-  s->p2p.scr_cap = 0;
+  dfree(s->p2p.d_peer_inbox), dfree(s->p2p.d_mail), dfree(s->p2p.d_inst_load);
+  s->p2p.hitq.release();
   s->p2p.inbox[0].release(), s->p2p.inbox[1].release();
   s->p2p.exported = s->p2p.attached = s->p2p.private_box = false;
   return GVTB200_OK;
@@ -1878,23 +1876,17 @@ int gvtb200_scene_set_instance_mesh(gvtb200_scene s, int instance, gvtb200_mesh 
   return GVTB200_OK;
 }
 static int persist_prepare(gvtb200_scene s);
-int gvtb200_domain_persist_config(gvtb200_scene s, int grid_ctas, int shade_at) {
+int gvtb200_domain_persist_config(gvtb200_scene s, int grid_ctas, int shade_sms) {
   if (!s) return fail(GVTB200_ERR_INVALID, "scene is NULL");
-  if (grid_ctas < 0 || shade_at < 1 || shade_at > 32) return fail(GVTB200_ERR_INVALID, "grid_ctas %d (>= 0), shade_at %d (1..32)", grid_ctas, shade_at);
-  s->p2p.grid_limit = grid_ctas, s->p2p.shade_at = shade_at;
-  NEED_INIT();
-  CU(cudaSetDevice(s->device));
+  if (grid_ctas < 0 || shade_sms < 0) return fail(GVTB200_ERR_INVALID, "grid_ctas %d, shade_sms %d must be >= 0", grid_ctas, shade_sms);
+  s->p2p.grid_limit = grid_ctas, s->p2p.shade_sms = shade_sms;
+  NEED_SCENE();
   return persist_prepare(s);
 }
 static int persist_prepare(gvtb200_scene s) {
-  const int grid = std::max(persist_grid(s->device, false), persist_grid(s->device, true));
-  const size_t threads = (size_t)std::max(grid, 2) * TRACE_THREADS;
-  if (s->p2p.scr_cap < threads) {
-    dfree(s->p2p.d_scr2), dfree(s->p2p.d_scr3);
-    CU(dalloc(&s->p2p.d_scr2, threads));
-    CU(dalloc(&s->p2p.d_scr3, threads));
-    s->p2p.scr_cap = threads;
-  }
+  const size_t cap = inbox_capacity(s);
+  if (s->p2p.hitq.slab && s->p2p.hitq.q.cap != cap) s->p2p.hitq.release();
+  CU(s->p2p.hitq.ensure(cap, true, true));
   if (!s->p2p.d_inst_load) CU(dalloc(&s->p2p.d_inst_load, std::max<size_t>(1, s->inst.size())));
   return 0;
 }
@@ -1928,7 +1920,6 @@ int gvtb200_domain_frame_persist(gvtb200_scene s, int root, int tile_rows) {
   int grid = persist_grid(s->device, count);
   if (s->p2p.grid_limit > 0) grid = std::min(grid, s->p2p.grid_limit);
   grid = std::max(grid, 2);
-  if ((size_t)grid * TRACE_THREADS > s->p2p.scr_cap) return fail(GVTB200_ERR_INVALID, "persistent grid grew after gvtb200_domain_persist_config");
   if (count) CU(cudaMemsetAsync(s->p2p.d_inst_load, 0, std::max<size_t>(1, s->inst.size()) * 8, st));
   if (!s->p2p.servers.empty() && s->p2p.servers.size() != s->inst.size()) return fail(GVTB200_ERR_INVALID, "server table is stale (instances changed)");
   FrameParams fp;
@@ -1939,7 +1930,7 @@ int gvtb200_domain_frame_persist(gvtb200_scene s, int root, int tile_rows) {
   pp.peer_inbox = s->p2p.d_peer_inbox; // entries [0, world): the round-0 inbound queues
   pp.mail = s->p2p.mail;
   pp.root_fb = s->p2p.peer_fb[root];
-  pp.scr2 = s->p2p.d_scr2, pp.scr3 = s->p2p.d_scr3;
+  pp.hitq = s->p2p.hitq.q, pp.hit = s->p2p.hitq.hit;
   pp.servers = s->p2p.d_servers;
   pp.inst_load = s->p2p.d_inst_load;
   pp.timeout_ns = g_peer_timeout_ns;
@@ -1949,7 +1940,13 @@ int gvtb200_domain_frame_persist(gvtb200_scene s, int root, int tile_rows) {
   pp.cam_count = (unsigned)cam;
   pp.seq = ++s->p2p.seq;
   pp.rank = me, pp.world = world, pp.root = root;
-  pp.shade_at = s->p2p.shade_at, pp.clamp = 1, pp.timeline = 1;
+  // roles: with the GPU to itself the kernel splits by SM (one role's code per instruction cache); a bounded grid (several
+  // simulated ranks on one GPU) cannot count on where its CTAs land and splits by CTA index instead
+  const int full = persist_grid(s->device, count), sms = g_dev[s->device].sms;
+  const int want = s->p2p.shade_sms > 0 ? s->p2p.shade_sms : std::max(2, sms / 10);
+  pp.shade_sms = grid == full ? std::min(want, sms - 1) : 0;
+  pp.shade_mod = std::max(2, std::min(grid, sms / std::max(1, want)));
+  pp.clamp = 1, pp.timeline = 1;
   pp.fb_pix = s->fb_pix;
   CU(cudaEventRecord(s->ev[0], st));
   CU(cudaMemsetAsync(&s->p2p.d_mail->pc, 0, GVT_PERSIST_RESET_BYTES, st));

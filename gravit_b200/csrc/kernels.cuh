@@ -1040,18 +1040,22 @@ struct PersistCtl {
   unsigned tail; // inbox slots reserved so far by producers on any rank (== rays ever put into this inbox this frame)
   unsigned pad0[31];
   unsigned head;     // inbox tickets handed to consumer lanes of this rank
-  unsigned cam_next; // cursor over this rank's shard of the camera rays
-  unsigned pad1[30];
-  unsigned consumed; // rays this rank has retired: items of its inbox plus its own camera rays
-  unsigned err;      // 1 = a wait timed out, 2 = an inbound queue overflowed (the frame is invalid either way)
+  unsigned pad1[31];
+  unsigned consumed; // rays and hits this rank has retired
+  unsigned err;      // 1 = a wait timed out, 2 = a queue overflowed (the frame is invalid either way)
   unsigned pad2[30];
+  unsigned hit_tail; // closest hits queued for the shader SMs (reserved slots)
+  unsigned pad3[31];
+  unsigned hit_head; // hit-queue tickets handed out
+  unsigned cam_warps; // warps that have finished phase 1 (camera rays)
+  unsigned pad4[30];
   // ---- not reset between frames: values are frame sequence numbers ----
-  unsigned cam_total; // camera rays of this rank's film shard in the current frame
+  unsigned cam_done; // every camera ray of this rank's shard has been handed out
   unsigned go, stop, done_seq;
   unsigned long long t_go, t_last; // globaltimer at the start barrier / at the last retire flush (per-rank busy time)
   unsigned arrive[GVT_P2P_MAX];    // start barrier: arrive[r] = frame number, written by rank r
 };
-#define GVT_PERSIST_RESET_BYTES 384 /* tail .. pad2 */
+#define GVT_PERSIST_RESET_BYTES 640 /* tail .. pad4 */
 struct Mailbox {
   unsigned go, err, cta_done, pad;
   unsigned done[GVT_P2P_MAX];
@@ -1149,21 +1153,26 @@ __global__ void k_fb_accumulate_root(const float4 *src, float *dst, size_t npix,
 // rank and frame; the reference's asynchronous loop (tracer/Domain/DomainTracer.cpp:109-192, scheduler::AsyncDomain) is the
 // closest relative: there are no exchange rounds.
 //
-//   rays in      every rank generates 1/world of the camera rays (row tiles dealt round-robin) in registers, routes them
-//                through the instance BVH and hands each one to a rank that serves its first instance; everything else
-//                arrives through the rank's INBOX, a slot array in its own HBM that every peer has mapped (CUDA IPC / peer
-//                access over NVLink).  A producer on any GPU reserves a slot with one atomic on `tail`, stores the SoA ray and
-//                then publishes it by writing the frame number into the slot's `ready` word (release); consumer lanes draw
-//                tickets from `head` and wait for their slot's `ready` word (acquire).  No kernel launch, host round trip
-//                or collective sits between a ray leaving one GPU and being traced on the next.
-//   ray life     trace in the instance (closest hit / any hit); miss -> next instance through the TLAS: traced here if this
-//                rank serves it, else stored into a serving rank's inbox; closest hit -> shaded by the same lane (in batches
-//                of >= shade_at lanes per warp): the first shadow ray (or the bounce) continues in the lane, further rays go
-//                into the rank's own inbox; a finished shadow ray adds its colour to the ROOT's framebuffer (remote atomics).
-//   termination  every rank counts what it retires (`consumed`); `tail` + the camera shard is what it was given.  One control
-//                warp on the root reads all `consumed` words, then all `tail` words: equal sums mean that at the instant
-//                between the two passes nothing was queued or in flight anywhere (both counts only grow, and a ray is counted
-//                as given before its parent is counted as retired).  The root then releases every rank, clamps the image.
+//   phase 1      every CTA: this rank's 1/world of the camera rays (row tiles dealt round-robin) are generated, routed through
+//                the instance BVH and stored into the INBOX of a rank that serves their first instance.
+//   phase 2      SMs split into two roles (by %smid, so that an SM's instruction cache holds one role's code: the first
+//                version ran everything in every warp, 133 KB of SASS, and stalled on instruction fetch three times per issue):
+//     tracer SMs   lanes draw tickets from the rank's inbox and wait for their slot; trace in the instance (closest hit / any
+//                  hit); miss -> next instance through the TLAS: traced here if this rank serves it, else stored into a
+//                  serving rank's inbox; closest hit -> hit record into the rank's HIT QUEUE; a finished shadow ray adds its
+//                  colour to the ROOT's framebuffer (remote atomics over NVLink).
+//     shader SMs   lanes draw tickets from the hit queue: surface, Shade() per light, shadow rays and the bounce go into the
+//                  rank's own inbox (EmbreeMeshAdapter.cpp:491-601).
+//   queues       an inbox is a slot array in its owner's HBM that every peer has mapped (CUDA IPC / peer access).  A producer
+//                on any GPU reserves a slot with one atomic on `tail`, stores the SoA ray and publishes it by writing the frame
+//                number into the slot's `ready` word (release); consumers draw tickets from `head` and poll their slot's
+//                `ready` word.  No kernel launch, host round trip or collective sits between a ray leaving one GPU and being
+//                traced on the next.
+//   termination  every rank counts what it retires (`consumed`); `tail` + `hit_tail` is what it was given.  One control warp
+//                on the root reads all `consumed` words, then all `given` words: equal sums (once every rank has finished phase
+//                1) mean that at the instant between the two passes nothing was queued or in flight anywhere (both counts only
+//                grow, and a ray is counted as given before its parent is counted as retired).  The root then releases every
+//                rank and clamps the image.
 //   servers      an instance may be served by several ranks (its owner plus ranks that hold a replica of its BLAS or have
 //                the owner's BLAS mapped over NVLink); a ray picks one by a hash of its direction bits against the
 //                cumulative weights of the table (gvtb200_domain_set_servers) -- the load balance the reference's hybrid
@@ -1171,26 +1180,27 @@ __global__ void k_fb_accumulate_root(const float4 *src, float *dst, size_t npix,
 // Every wait gives up after timeout_ns and flags the frame as failed.
 // =========================================================================================================
 #ifndef PERSIST_MIN_BLOCKS
-#define PERSIST_MIN_BLOCKS 5
+#define PERSIST_MIN_BLOCKS 6
 #endif
 #ifndef PERSIST_TRIPS
 #define PERSIST_TRIPS 16
 #endif
 struct PersistParams {
   RayQueue inbox;             // this rank's inbound slots (count unused: PersistCtl::tail / head)
+  RayQueue hitq;              // this rank's closest hits: ray + hit column, ticketed like the inbox (hit_tail / hit_head)
+  int4 *hit;                  // hit column of hitq: prim, triangle slot, u bits, v bits
   const RayQueue *peer_inbox; // [world]: every rank's inbox as mapped into this GPU (entry `rank` == inbox)
   PeerMail mail;              // every rank's mailbox (PersistCtl inside)
   float *root_fb;             // the root's RGBA framebuffer as mapped here
-  float4 *scr2;               // per-thread backing store of the ray columns that are not kept in registers (colour, t)
-  int4 *scr3;                 //   (id, depth, w, type): rays made in the lane (shadow rays, bounces) have no queue slot
   const uint4 *servers;       // per instance {ranks (4 x 8 bit), thresholds 0/1 (2 x 16 bit), threshold 2, count} or null
   unsigned long long *inst_load; // COUNT only: wide nodes visited per instance (input of the replica planner)
   unsigned long long timeout_ns;
-  RowTiles tiles;    // this rank's shard of the film rows
+  RowTiles tiles;     // this rank's shard of the film rows
   unsigned cam_count; // camera rays of the shard
   unsigned seq;       // frame number (>= 1, the same on every rank)
   int rank, world, root;
-  int shade_at;       // shade when at least this many lanes of a warp hold a closest hit
+  int shade_sms;      // SMs with %smid below this shade, the others trace; 0: every shade_mod-th CTA shades (bounded test grids)
+  int shade_mod;
   int clamp;          // the root clamps the image when the frame is over
   int timeline;       // record when this rank last retired a ray (per-rank busy time)
   size_t fb_pix;
@@ -1209,6 +1219,11 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
 __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_release_sys_add(unsigned *p, unsigned v) { asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned sm_id() {
+  unsigned v;
+  asm("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
+}
 __device__ __forceinline__ int pick_server(const uint4 *servers, int inst, int owner, V3 d) {
   if (!servers) return owner;
   const uint4 e = __ldg(servers + inst);
@@ -1226,8 +1241,6 @@ __device__ __noinline__ void persist_control(const PersistParams &pp, PersistCtl
   const unsigned seq = pp.seq;
   const unsigned long long t0 = global_ns();
   PersistCtl *theirs = peer ? &pp.mail.m[r]->pc : ctl;
-  if (r == 0) st_release_sys(&ctl->cam_total, pp.cam_count);
-  __syncwarp();
   // start barrier: every rank has reset its counters (and the root has cleared the image) before anybody produces
   bool bad = false;
   if (peer) {
@@ -1249,15 +1262,17 @@ __device__ __noinline__ void persist_control(const PersistParams &pp, PersistCtl
   if (bad) return;
   if (pp.rank == pp.root) {
     for (;;) {
-      // pass 1: what every rank has retired; pass 2 (issued after every pass-1 value has come back: the reduction below
-      // consumes them): what every rank was given.  Volatile loads read the owner's L2, where its atomics are performed.
+      // pass 1: what every rank has retired (and whether its camera rays are all out); pass 2 (issued after every pass-1
+      // value has come back: the reduction below consumes them): what every rank was given.  Volatile loads read the
+      // owner's L2, where its atomics are performed.
       const unsigned c = peer ? ld_volatile_u32(&theirs->consumed) : 0u;
       const unsigned e = peer ? ld_volatile_u32(&theirs->err) : 0u;
-      const unsigned cs = __reduce_add_sync(FULL, c), es = __reduce_or_sync(FULL, e);
-      const unsigned t = (peer && cs != 0xFFFFFFFFu) ? ld_volatile_u32(&theirs->tail) + ld_volatile_u32(&theirs->cam_total) : 0u;
+      const unsigned started = peer ? (ld_volatile_u32(&theirs->cam_done) == seq ? 1u : 0u) : 1u;
+      const unsigned cs = __reduce_add_sync(FULL, c), es = __reduce_or_sync(FULL, e), all_started = __reduce_and_sync(FULL, started);
+      const unsigned t = (peer && cs != 0xFFFFFFFFu) ? ld_volatile_u32(&theirs->tail) + ld_volatile_u32(&theirs->hit_tail) : 0u;
       const unsigned ts = __reduce_add_sync(FULL, t);
       const bool late = global_ns() - t0 > pp.timeout_ns;
-      if (cs == ts || es || late) {
+      if ((all_started && cs == ts) || es || late) {
         if ((es || late) && r == 0) atomicOr(&ctl->err, es ? es : 1u);
         break;
       }
@@ -1285,7 +1300,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
   __syncthreads(); // the only block-wide barrier: the control warp leaves the block's flow after it
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31, ltmask = (1u << lane) - 1u;
-  const unsigned gtid = blockIdx.x * TRACE_THREADS + threadIdx.x;
   PersistCtl *ctl = &pp.mail.m[pp.rank]->pc;
   const unsigned seq = pp.seq;
   const int me = pp.rank;
@@ -1304,70 +1318,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
     __syncwarp();
   }
   const bool to_light = (fp.flags & FLAG_SHADOW_TO_LIGHT) != 0;
-  const bool enter_inside = (fp.flags & FLAG_ENTER_INSIDE) != 0;
-  const unsigned per_row = (unsigned)(fp.cam.W * fp.cam.samples * fp.cam.samples);
-  auto camera_index = [&](unsigned i) -> size_t {
-    unsigned lr = i / per_row, within = i - lr * per_row;
-    unsigned b = lr / (unsigned)pp.tiles.tile_rows, k = lr - b * (unsigned)pp.tiles.tile_rows;
-    size_t row = (size_t)pp.tiles.row0 + ((size_t)b * pp.tiles.stride + pp.tiles.index) * pp.tiles.tile_rows + k;
-    return row * per_row + within;
-  };
   unsigned long long c_visits = 0, c_shok = 0, c_fb = 0, c_exp = 0, c_ovf = 0, c_qovf = 0, c_routed = 0, c_hits = 0, c_shgen = 0, c_sec = 0;
-  TravCounters tc;
-  tc.nodes = 0, tc.tris = 0;
-  unsigned nodes0 = 0;
-  SmemStack stack;
-  stack.s = s_stack + threadIdx.x;
-  stack.overflow = false;
-
-  enum { L_IDLE = 0, L_WAIT = 1, L_ACTIVE = 2, L_SHADE = 3 };
-  int st = L_IDLE;
-  int src = 0;      // the columns not kept in registers: 0 = camera ray `idx` (regenerated), 1 = inbox slot `idx`, 2 = this thread's scratch
-  unsigned idx = 0; // camera ray of the shard / inbox ticket
-  bool first = true, any = false, dirty = false, cam_done = pp.cam_count == 0;
   unsigned c_cons = 0; // retired since the last flush
-  int inst = 0, type = 0;
-  V3 o = v3(0.f, 0.f, 0.f), d = o;
-  float t_min = 0.f, t_max = 0.f, tfar = FLT_MAX;
-  const float4 *nodes = nullptr, *tris = nullptr;
-  RayLocal rl;
-  Trav tv;
-  ray_local(rl, o, o);
-  trav_begin(tv, 0u, 0.f);
+  bool dirty = false;  // this lane has stored into another GPU's memory since the last flush
 
-  auto begin_instance = [&]() {
-    const Instance in = sd.inst[inst];
-    const Blas &bl = sd.blas[in.mesh];
-    V3 lo, ld;
-    to_local(in, o, d, lo, ld);
-    ray_local(rl, lo, ld);
-    nodes = bl.nodes, tris = bl.tris;
-    tfar = (any && to_light) ? t_max : FLT_MAX; // prepGVT_EMBREE_PACKET_TYPE (EmbreeMeshAdapter.cpp:269-286)
-    trav_begin(tv, bl.n_tris, tfar);
-    c_visits++;
-    if (COUNT) nodes0 = tc.nodes;
-  };
-  auto reload = [&](Ray &r) {
-    if (src == 0) {
-      camera_ray(fp.cam, camera_index(idx), r);
-    } else {
-      const float4 c2 = src == 1 ? __ldcg(pp.inbox.c2 + idx) : pp.scr2[gtid];
-      const int4 c3 = src == 1 ? __ldcg(pp.inbox.c3 + idx) : pp.scr3[gtid];
-      r.color = v3(c2.x, c2.y, c2.z), r.t = c2.w;
-      r.id = c3.x, r.depth = c3.y, r.w = u2f((uint32_t)c3.z), r.type = c3.w;
-    }
-    r.o = o, r.t_min = t_min, r.d = d, r.t_max = t_max;
-  };
-  // a ray made in this lane becomes the lane's ray
-  auto continue_as = [&](const Ray &r) {
-    o = r.o, t_min = r.t_min, d = r.d, t_max = r.t_max, type = r.type;
-    pp.scr2[gtid] = make_float4(r.color.x, r.color.y, r.color.z, r.t);
-    pp.scr3[gtid] = make_int4(r.id, r.depth, (int)f2u(r.w), r.type);
-    src = 2;
-    any = (type == RAY_SHADOW), first = true, st = L_ACTIVE;
-    begin_instance();
-  };
-  // SendRays: into the inbox of `dest` (this rank's own inbox for rays it makes faster than it has lanes)
+  // SendRays: into the inbox of `dest` (this rank's own inbox for the rays it makes)
   auto send = [&](const Ray &r, int target, int dest) {
     const RayQueue q = dest == me ? pp.inbox : pp.peer_inbox[dest];
     PersistCtl *pc = &pp.mail.m[dest]->pc;
@@ -1387,71 +1342,192 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       if (dest == me) atomicAdd(&pc->consumed, 1u); else atomicAdd_system(&pc->consumed, 1u);
     }
   };
-  // retired rays -> `consumed`; everything this warp wrote anywhere (peer inboxes, the root's image) is ordered before it
-  // (each lane releases its own count: a lane's count covers exactly the rays whose stores that lane issued)
+  // retired rays -> `consumed`; everything this warp wrote anywhere (peer inboxes, the root's image) is ordered before it.
+  // One release-reduction per warp (same-address atomics serialise in L2 at ~1 per clock: one per lane and retired ray cost
+  // more than the traversal of a mostly-empty frame).  The warp barrier orders the other lanes' writes before lane 0's
+  // release (causality order is cumulative in the PTX memory model).
   auto flush = [&]() {
-    if (c_cons != 0u) {
-      if (dirty) red_release_sys_add(&ctl->consumed, c_cons); else red_release_gpu_add(&ctl->consumed, c_cons);
-      c_cons = 0u, dirty = false;
+    const unsigned tot = __reduce_add_sync(FULL, c_cons);
+    const bool far = __any_sync(FULL, dirty);
+    c_cons = 0u, dirty = false;
+    if (tot != 0u && lane == 0) {
+      if (far) red_release_sys_add(&ctl->consumed, tot); else red_release_gpu_add(&ctl->consumed, tot);
       if (pp.timeline) atomicMax(&ctl->t_last, global_ns());
     }
-    __syncwarp();
   };
 
+  // ---- phase 1: gvtPerspectiveCamera::generateRays + FilterRaysLocally (first routing hop) for this rank's film shard ------
+  {
+    const bool enter_inside = (fp.flags & FLAG_ENTER_INSIDE) != 0;
+    const size_t per_row = (size_t)fp.cam.W * fp.cam.samples * fp.cam.samples;
+    const size_t stride = (size_t)gridDim.x * TRACE_THREADS - 32; // every thread but the control warp's
+    for (size_t i = blockIdx.x * (size_t)TRACE_THREADS + threadIdx.x - 32; i < pp.cam_count; i += stride) {
+      const size_t lr = i / per_row, within = i - lr * per_row;
+      const size_t b = lr / pp.tiles.tile_rows, k = lr - b * pp.tiles.tile_rows;
+      const size_t row = (size_t)pp.tiles.row0 + (b * pp.tiles.stride + pp.tiles.index) * pp.tiles.tile_rows + k;
+      Ray r;
+      camera_ray(fp.cam, row * per_row + within, r);
+      float t;
+      const int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, -1, enter_inside, t);
+      if (next < 0) continue; // background
+      c_routed++;
+      r.o = xadd(r.o, xmul(r.d, xmul(t, 0.95f))); // TracerBase.h:394
+      const int dest = multi ? pick_server(pp.servers, next, sd.inst[next].owner, r.d) : me;
+      if (dest != me) c_exp++;
+      send(r, next, dest);
+    }
+    __syncwarp();
+    // (a lane's remote stores are ordered by its release stores of the ready words; the warp count below only tells the
+    // root that no more camera rays will be handed out by this rank)
+    if (lane == 0) {
+      __threadfence();
+      const unsigned total = gridDim.x * (TRACE_THREADS / 32) - 1u; // every warp but the control warp
+      if (atomicAdd(&ctl->cam_warps, 1u) == total - 1u) st_release_sys(&ctl->cam_done, seq);
+    }
+    __syncwarp();
+  }
+
+  const bool shader = pp.shade_sms > 0 ? (int)sm_id() < pp.shade_sms : (blockIdx.x % (unsigned)pp.shade_mod) == 1u;
   unsigned iter = 0;
   unsigned long long t_idle0 = 0;
   const unsigned long long t_start = global_ns();
-  for (;;) {
-    ++iter;
-    if ((iter & 4095u) == 0u) { // watchdog: a frame never runs this long (decided by lane 0: the warp leaves together)
-      const unsigned late = __shfl_sync(FULL, global_ns() - t_start > 4 * pp.timeout_ns ? 1u : 0u, 0);
-      if (late) {
-        if (lane == 0) atomicOr(&ctl->err, 1u);
-        break;
-      }
-    }
-    // ---- refill idle lanes: camera rays of the shard first, then inbox tickets ---------------------------------------
-    unsigned idle = __ballot_sync(FULL, st == L_IDLE);
-    const unsigned busy = __ballot_sync(FULL, st >= L_ACTIVE);
-    const unsigned tracing = __ballot_sync(FULL, st == L_ACTIVE);
-    const bool starved = 32 - __popc(tracing) >= tune.exit_at; // the traversal loop would come straight back
-    if (idle != 0u && (busy == 0u || starved || __popc(idle) >= tune.refill_at)) {
-      const unsigned cnt = (unsigned)__popc(idle);
-      if (!cam_done) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&ctl->cam_next, cnt);
-        base = __shfl_sync(FULL, base, 0);
-        if (base + cnt >= pp.cam_count) cam_done = true;
+  enum { L_IDLE = 0, L_WAIT = 1, L_ACTIVE = 2 };
+  int st = L_IDLE;
+  unsigned idx = 0; // the lane's ticket: inbox slot (tracer) or hit-queue slot (shader)
+
+  if (shader) {
+    // ================= shader SMs: EmbreeMeshAdapter.cpp:491-601 for every closest hit of this rank ==========================
+    for (;;) {
+      ++iter;
+      const unsigned idle = __ballot_sync(FULL, st == L_IDLE);
+      if (idle != 0u) {
+        unsigned take = 0, base = 0;
+        if (lane == 0) {
+          const unsigned t = ld_volatile_u32(&ctl->hit_tail), h = ld_volatile_u32(&ctl->hit_head);
+          take = t > h ? min(t - h, (unsigned)__popc(idle)) : 0u;
+          if (take) base = atomicAdd(&ctl->hit_head, take);
+        }
+        take = __shfl_sync(FULL, take, 0), base = __shfl_sync(FULL, base, 0);
         if (st == L_IDLE) {
-          const unsigned my = base + (unsigned)__popc(idle & ltmask);
-          if (my < pp.cam_count) { // gvtPerspectiveCamera::generateRays + FilterRaysLocally (first routing hop), in registers
-            idx = my, src = 0;
-            Ray r;
-            camera_ray(fp.cam, camera_index(idx), r);
-            float t;
-            const int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, -1, enter_inside, t);
-            if (next < 0) {
-              c_cons++; // background
-            } else {
-              c_routed++;
-              r.o = xadd(r.o, xmul(r.d, xmul(t, 0.95f))); // TracerBase.h:394
-              const int dest = multi ? pick_server(pp.servers, next, sd.inst[next].owner, r.d) : me;
-              if (dest == me) {
-                o = r.o, t_min = r.t_min, d = r.d, t_max = r.t_max, type = r.type, inst = next;
-                any = false, first = true, st = L_ACTIVE;
-                begin_instance();
-              } else {
-                send(r, next, dest);
-                c_exp++, c_cons++;
-              }
-            }
+          const unsigned k = (unsigned)__popc(idle & ltmask);
+          if (k < take) idx = base + k, st = L_WAIT;
+        }
+      }
+      bool got = false;
+      if (st == L_WAIT) {
+        if (idx >= pp.hitq.cap) st = L_IDLE; // the producer found the queue full (it has flagged the frame)
+        else got = ld_volatile_u32(pp.hitq.ready + idx) == seq;
+      }
+      if (__ballot_sync(FULL, got) == 0u) {
+        flush();
+        unsigned stop = 0;
+        if (lane == 0) stop = ld_volatile_u32(&ctl->stop) == seq ? 1u : 0u;
+        if (__shfl_sync(FULL, stop, 0)) break;
+        __nanosleep(__any_sync(FULL, st == L_WAIT) ? 32 : 200);
+        if ((iter & 255u) == 0u) {
+          const unsigned long long now = __shfl_sync(FULL, global_ns(), 0);
+          if (t_idle0 == 0) t_idle0 = now;
+          if (now - t_idle0 > 2 * pp.timeout_ns) {
+            if (lane == 0) atomicOr(&ctl->err, 1u);
+            break;
           }
         }
-      } else {
+        continue;
+      }
+      t_idle0 = 0;
+      if (got) {
+        Ray r;
+        {
+          const float4 a = __ldcg(pp.hitq.c0 + idx), b = __ldcg(pp.hitq.c1 + idx), c = __ldcg(pp.hitq.c2 + idx);
+          const int4 e = __ldcg(pp.hitq.c3 + idx);
+          r.o = v3(a.x, a.y, a.z), r.t_min = a.w, r.d = v3(b.x, b.y, b.z), r.t_max = b.w;
+          r.color = v3(c.x, c.y, c.z), r.t = c.w;
+          r.id = e.x, r.depth = e.y, r.w = u2f((uint32_t)e.z), r.type = e.w;
+        }
+        const int inst = __ldcg(pp.hitq.inst + idx);
+        const int4 hc = __ldcg(pp.hit + idx);
+        Hit h;
+        h.prim = hc.x, h.slot = hc.y, h.t = r.t, h.u = u2f((uint32_t)hc.z), h.v = u2f((uint32_t)hc.w);
+        const Instance in = sd.inst[inst];
+        const Blas &bl = sd.blas[in.mesh];
+        c_hits++;
+        V3 normal;
+        Mat mat;
+        surface_at(bl, in, h, r, fp.flags, normal, mat);
+        if (r.type == RAY_SECONDARY) { // :572-575
+          const float tt = (h.t > 1.f) ? xdiv(1.f, h.t) : h.t;
+          r.w = xmul(r.w, tt);
+        }
+        for (int li = 0; li < fp.n_lights; ++li) {
+          const Light &L = fp.lights[li];
+          Ray sh;
+          if (!make_shadow_ray(r, normal, mat, L, light_position(L, fp.seed, r.id, r.depth, li), to_light, sh)) continue;
+          c_shgen++;
+          send(sh, inst, me); // the shadow ray starts in the instance that was hit
+        }
+        if (make_bounce(r, normal, fp.seed)) {
+          c_sec++;
+          send(r, inst, me);
+        }
+        c_cons++;
+        st = L_IDLE;
+      }
+      flush();
+    }
+  } else {
+    // ================= tracer SMs ========================================================================================
+    TravCounters tc;
+    tc.nodes = 0, tc.tris = 0;
+    unsigned nodes0 = 0;
+    SmemStack stack;
+    stack.s = s_stack + threadIdx.x;
+    stack.overflow = false;
+    bool first = true, any = false;
+    int inst = 0, type = 0;
+    V3 o = v3(0.f, 0.f, 0.f), d = o;
+    float t_min = 0.f, t_max = 0.f, tfar = FLT_MAX;
+    const float4 *nodes = nullptr, *tris = nullptr;
+    RayLocal rl;
+    Trav tv;
+    ray_local(rl, o, o);
+    trav_begin(tv, 0u, 0.f);
+    auto begin_instance = [&]() {
+      const Instance in = sd.inst[inst];
+      const Blas &bl = sd.blas[in.mesh];
+      V3 lo, ld;
+      to_local(in, o, d, lo, ld);
+      ray_local(rl, lo, ld);
+      nodes = bl.nodes, tris = bl.tris;
+      tfar = (any && to_light) ? t_max : FLT_MAX; // prepGVT_EMBREE_PACKET_TYPE (EmbreeMeshAdapter.cpp:269-286)
+      trav_begin(tv, bl.n_tris, tfar);
+      c_visits++;
+      if (COUNT) nodes0 = tc.nodes;
+    };
+    auto reload = [&](Ray &r) { // the columns that are not kept in registers stay in the lane's inbox slot
+      const float4 c2 = __ldcg(pp.inbox.c2 + idx);
+      const int4 c3 = __ldcg(pp.inbox.c3 + idx);
+      r.color = v3(c2.x, c2.y, c2.z), r.t = c2.w;
+      r.id = c3.x, r.depth = c3.y, r.w = u2f((uint32_t)c3.z), r.type = c3.w;
+      r.o = o, r.t_min = t_min, r.d = d, r.t_max = t_max;
+    };
+    for (;;) {
+      ++iter;
+      if ((iter & 4095u) == 0u) { // watchdog: a frame never runs this long (decided by lane 0: the warp leaves together)
+        const unsigned late = __shfl_sync(FULL, global_ns() - t_start > 4 * pp.timeout_ns ? 1u : 0u, 0);
+        if (late) {
+          if (lane == 0) atomicOr(&ctl->err, 1u);
+          break;
+        }
+      }
+      // ---- idle lanes draw inbox tickets ---------------------------------------------------------------------------
+      const unsigned idle = __ballot_sync(FULL, st == L_IDLE);
+      const unsigned tracing = __ballot_sync(FULL, st == L_ACTIVE);
+      const bool starved = 32 - __popc(tracing) >= tune.exit_at; // the traversal loop would come straight back
+      if (idle != 0u && (tracing == 0u || starved || __popc(idle) >= tune.refill_at)) {
         unsigned take = 0, base = 0;
         if (lane == 0) {
           const unsigned t = ld_volatile_u32(&ctl->tail), h = ld_volatile_u32(&ctl->head);
-          take = t > h ? min(t - h, cnt) : 0u;
+          take = t > h ? min(t - h, (unsigned)__popc(idle)) : 0u;
           if (take) base = atomicAdd(&ctl->head, take);
         }
         take = __shfl_sync(FULL, take, 0), base = __shfl_sync(FULL, base, 0);
@@ -1460,28 +1536,25 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
           if (k < take) idx = base + k, st = L_WAIT;
         }
       }
-    }
-    // ---- lanes that hold a ticket: has the ray landed? ------------------------------------------------------------
-    if (st == L_WAIT) {
-      if (idx >= pp.inbox.cap) {
-        st = L_IDLE; // the producer found the inbox full (it has flagged the frame and balanced the count)
-      } else if (ld_volatile_u32(pp.inbox.ready + idx) == seq) {
-        const float4 c0 = __ldcg(pp.inbox.c0 + idx), c1 = __ldcg(pp.inbox.c1 + idx);
-        type = __ldcg(&pp.inbox.c3[idx].w);
-        inst = __ldcg(pp.inbox.inst + idx);
-        o = v3(c0.x, c0.y, c0.z), t_min = c0.w, d = v3(c1.x, c1.y, c1.z), t_max = c1.w;
-        src = 1;
-        any = (type == RAY_SHADOW), first = true, st = L_ACTIVE;
-        begin_instance();
+      // ---- lanes that hold a ticket: has the ray landed? ------------------------------------------------------------
+      if (st == L_WAIT) {
+        if (idx >= pp.inbox.cap) {
+          st = L_IDLE; // the producer found the inbox full (it has flagged the frame and balanced the count)
+        } else if (ld_volatile_u32(pp.inbox.ready + idx) == seq) {
+          const float4 c0 = __ldcg(pp.inbox.c0 + idx), c1 = __ldcg(pp.inbox.c1 + idx);
+          type = __ldcg(&pp.inbox.c3[idx].w);
+          inst = __ldcg(pp.inbox.inst + idx);
+          o = v3(c0.x, c0.y, c0.z), t_min = c0.w, d = v3(c1.x, c1.y, c1.z), t_max = c1.w;
+          any = (type == RAY_SHADOW), first = true, st = L_ACTIVE;
+          begin_instance();
+        }
       }
-    }
-    // ---- nothing to trace or shade in this warp --------------------------------------------------------------------
-    if (__ballot_sync(FULL, st >= L_ACTIVE) == 0u) {
-      flush();
-      unsigned stop = 0;
-      if (lane == 0) stop = ld_volatile_u32(&ctl->stop) == seq ? 1u : 0u;
-      if (__shfl_sync(FULL, stop, 0)) break;
-      if (cam_done) {
+      // ---- nothing to trace in this warp ----------------------------------------------------------------------------------
+      if (__ballot_sync(FULL, st == L_ACTIVE) == 0u) {
+        flush();
+        unsigned stop = 0;
+        if (lane == 0) stop = ld_volatile_u32(&ctl->stop) == seq ? 1u : 0u;
+        if (__shfl_sync(FULL, stop, 0)) break;
         __nanosleep(__any_sync(FULL, st == L_WAIT) ? 32 : 128);
         if ((iter & 255u) == 0u) { // a peer died, or a bug: never spin for ever
           const unsigned long long now = __shfl_sync(FULL, global_ns(), 0);
@@ -1491,108 +1564,81 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
             break;
           }
         }
+        continue;
       }
-      continue;
-    }
-    t_idle0 = 0;
-    // ---- traverse in lock step ----------------------------------------------------------------------------------------
-    // (leaves early for a refill only while camera rays are left -- whether the inbox has rays is not known without asking
-    // -- and after PERSIST_TRIPS iterations at the latest, so that tickets get polled and new arrivals get lanes)
-    const unsigned resting = __ballot_sync(FULL, st != L_ACTIVE);
-    const bool done = warp_traverse<COUNT, PERSIST_TRIPS>(st == L_ACTIVE, resting, !cam_done, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
-    // ---- rays that finished their instance -------------------------------------------------------------------------
-    if (st == L_ACTIVE && done) {
-      if (COUNT && pp.inst_load) atomicAdd(pp.inst_load + inst, (unsigned long long)(tc.nodes - nodes0));
-      if (tv.hit.prim >= 0) {
-        if (type != RAY_SHADOW) {
-          st = L_SHADE; // closest hit: shaded below, together with the warp's other hits
-        } else {
-          st = L_IDLE, c_cons++; // occluded (EmbreeMeshAdapter.cpp:487-489)
-        }
-      } else {
-        if (any && first) c_shok++;
-        first = false;
-        float t;
-        const int next = tlas_route(sd.tlas, o, d, t_max, inst, false, t);
-        if (next < 0) {
-          if (type == RAY_SHADOW) { // TracerBase.h:396-399, straight into the root's image
+      t_idle0 = 0;
+      // ---- traverse in lock step (comes back after PERSIST_TRIPS iterations at the latest: tickets get polled and new
+      // arrivals get lanes; whether the inbox holds rays is not known without asking, so it never leaves early for a refill)
+      const unsigned resting = __ballot_sync(FULL, st != L_ACTIVE);
+      const bool done = warp_traverse<COUNT, PERSIST_TRIPS>(st == L_ACTIVE, resting, false, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
+      // ---- rays that finished their instance -------------------------------------------------------------------------
+      if (st == L_ACTIVE && done) {
+        if (COUNT && pp.inst_load) atomicAdd(pp.inst_load + inst, (unsigned long long)(tc.nodes - nodes0));
+        if (tv.hit.prim >= 0) {
+          if (type != RAY_SHADOW) { // closest hit -> the shader SMs; an occluded shadow ray is dropped (:487-489)
             Ray r;
             reload(r);
-            if (xlength(r.color) > 0.f) {
-              const V3 c = xmul(r.color, r.w);
-              if (me == pp.root) {
-                fb_add(pp.root_fb, r.id, c);
-              } else {
-                float *px = pp.root_fb + 4 * (size_t)r.id;
-                atomicAdd_system(px, c.x), atomicAdd_system(px + 1, c.y), atomicAdd_system(px + 2, c.z), atomicAdd_system(px + 3, 1.0f);
-                dirty = true;
-              }
-              c_fb++;
+            r.t = tv.hit.t;
+            const unsigned pos = queue_reserve(&ctl->hit_tail);
+            if (pos < pp.hitq.cap) {
+              queue_store(pp.hitq, pos, r, inst);
+              pp.hit[pos] = make_int4(tv.hit.prim, tv.hit.slot, (int)f2u(tv.hit.u), (int)f2u(tv.hit.v));
+              st_release_gpu(pp.hitq.ready + pos, seq);
+            } else {
+              c_qovf++;
+              atomicOr(&ctl->err, 2u);
+              atomicAdd(&ctl->consumed, 1u);
             }
           }
           st = L_IDLE, c_cons++;
         } else {
-          o = xadd(o, xmul(d, xmul(t, 0.95f))); // TracerBase.h:394
-          if (to_light && type == RAY_SHADOW) t_max = xsub(t_max, xmul(t, 0.95f));
-          const int dest = multi ? pick_server(pp.servers, next, sd.inst[next].owner, d) : me;
-          if (dest == me) {
-            inst = next;
-            begin_instance();
+          if (any && first) c_shok++;
+          first = false;
+          float t;
+          const int next = tlas_route(sd.tlas, o, d, t_max, inst, false, t);
+          if (next < 0) {
+            if (type == RAY_SHADOW) { // TracerBase.h:396-399, straight into the root's image
+              Ray r;
+              reload(r);
+              if (xlength(r.color) > 0.f) {
+                const V3 c = xmul(r.color, r.w);
+                if (me == pp.root) {
+                  fb_add(pp.root_fb, r.id, c);
+                } else {
+                  float *px = pp.root_fb + 4 * (size_t)r.id;
+                  atomicAdd_system(px, c.x), atomicAdd_system(px + 1, c.y), atomicAdd_system(px + 2, c.z), atomicAdd_system(px + 3, 1.0f);
+                  dirty = true;
+                }
+                c_fb++;
+              }
+            }
+            st = L_IDLE, c_cons++;
           } else {
-            Ray r;
-            reload(r);
-            send(r, next, dest);
-            c_exp++, c_cons++;
-            st = L_IDLE;
+            o = xadd(o, xmul(d, xmul(t, 0.95f))); // TracerBase.h:394
+            if (to_light && type == RAY_SHADOW) t_max = xsub(t_max, xmul(t, 0.95f));
+            const int dest = multi ? pick_server(pp.servers, next, sd.inst[next].owner, d) : me;
+            if (dest == me) {
+              inst = next;
+              begin_instance();
+            } else {
+              Ray r;
+              reload(r);
+              send(r, next, dest);
+              c_exp++, c_cons++;
+              st = L_IDLE;
+            }
           }
         }
       }
+      if ((iter & 63u) == 0u) flush();
     }
-    // ---- shade the warp's closest hits (EmbreeMeshAdapter.cpp:491-601) ------------------------------------------------------
-    {
-      const unsigned sm = __ballot_sync(FULL, st == L_SHADE);
-      const unsigned am = __ballot_sync(FULL, st == L_ACTIVE);
-      if (sm != 0u && (__popc(sm) >= pp.shade_at || 32 - __popc(am) >= tune.exit_at) && st == L_SHADE) {
-        Ray r;
-        reload(r);
-        r.t = tv.hit.t;
-        const Instance in = sd.inst[inst];
-        const Blas &bl = sd.blas[in.mesh];
-        c_hits++;
-        V3 normal;
-        Mat mat;
-        surface_at(bl, in, tv.hit, r, fp.flags, normal, mat);
-        if (r.type == RAY_SECONDARY) { // :572-575
-          const float tt = (r.t > 1.f) ? xdiv(1.f, r.t) : r.t;
-          r.w = xmul(r.w, tt);
-        }
-        bool have = false;
-        Ray keep; // the first shadow ray stays in the lane unless the ray bounces
-        for (int li = 0; li < fp.n_lights; ++li) {
-          const Light &L = fp.lights[li];
-          Ray sh;
-          if (!make_shadow_ray(r, normal, mat, L, light_position(L, fp.seed, r.id, r.depth, li), to_light, sh)) continue;
-          c_shgen++;
-          if (!have)
-            keep = sh, have = true;
-          else
-            send(sh, inst, me);
-        }
-        if (make_bounce(r, normal, fp.seed)) {
-          c_sec++;
-          if (have) send(keep, inst, me);
-          continue_as(r);
-        } else if (have) {
-          continue_as(keep);
-        } else {
-          st = L_IDLE, c_cons++;
-        }
-      }
+    flush();
+    if (stack.overflow) c_ovf = 1;
+    if (COUNT) {
+      count_add(&sd.ctr->nodes_visited, tc.nodes);
+      count_add(&sd.ctr->tris_tested, tc.tris);
     }
-    if ((iter & 63u) == 0u) flush();
   }
-  flush();
-  if (stack.overflow) c_ovf = 1;
   count_add(&sd.ctr->instance_visits, c_visits);
   count_add(&sd.ctr->shadow_unoccluded, c_shok);
   count_add(&sd.ctr->fb_adds, c_fb);
@@ -1604,14 +1650,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
   count_add(&sd.ctr->shadow_generated, c_shgen);
   count_add(&sd.ctr->secondary_generated, c_sec);
   if (blockIdx.x == 0 && threadIdx.x == 32) atomicAdd(&sd.ctr->camera_rays, (unsigned long long)pp.cam_count);
-  if (COUNT) {
-    count_add(&sd.ctr->nodes_visited, tc.nodes);
-    count_add(&sd.ctr->tris_tested, tc.tris);
-  }
   // ---- the image is complete in the root's memory: every contribution was ordered before the `consumed` count the
   // root's control warp saw.  IceTComposite::localAdd's running clamp, applied once (min(1, sum), non-negative terms).
   if (pp.clamp && me == pp.root) {
     float4 *fb4 = reinterpret_cast<float4 *>(pp.root_fb);
+    const size_t gtid = blockIdx.x * (size_t)TRACE_THREADS + threadIdx.x;
     for (size_t i = gtid; i < pp.fb_pix; i += (size_t)gridDim.x * TRACE_THREADS) {
       float4 v = __ldcg(fb4 + i);
       if (v.w != 0.f) {

@@ -293,14 +293,14 @@ GVTB200_API int gvtb200_domain_round_p2p(gvtb200_scene scene, int round, void **
  * votes core/comm/vote/vote.cpp) it has no exchange rounds.  Every rank generates 1/world_size of the camera rays (row tiles of
  * tile_rows rows dealt round-robin), a ray bound for an instance another rank serves is stored into that rank's inbound
  * queue over NVLink by the trace kernel and picked up there by a waiting lane without any launch or host round trip, shading
- * happens in the same kernel, finished shadow rays are added straight into the root's framebuffer, termination is found on
+ * happens in the same kernel (on SMs set aside for it), finished shadow rays are added straight into the root's framebuffer, termination is found on
  * the device (sum of rays retired == sum of rays handed out, read in that order) and the root clamps the image before its
  * kernel ends.  world_size 1 (no peers needed) runs the same kernel on one GPU.  The call is asynchronous on the scene's
  * stream; gvtb200_scene_sync reports time-outs and full queues.  The image is complete in the root's framebuffer. */
 GVTB200_API int gvtb200_domain_frame_persist(gvtb200_scene scene, int root, int tile_rows);
 /* grid_ctas: CTAs of the persistent kernel (0 = fill the GPU; tests that run several simulated ranks on one GPU bound it so
- * that all of them are resident together); shade_at: a warp shades its closest hits once this many lanes hold one (1..32) */
-GVTB200_API int gvtb200_domain_persist_config(gvtb200_scene scene, int grid_ctas, int shade_at);
+ * that all of them are resident together); shade_sms: how many SMs shade hits instead of tracing rays (0 = a tenth) */
+GVTB200_API int gvtb200_domain_persist_config(gvtb200_scene scene, int grid_ctas, int shade_sms);
 /* after a persistent frame: how long this rank was busy (start barrier to its last retired ray, ms), how many rays its
  * inbound queue received and -- for a frame rendered with gvtb200_scene_profile_counters on -- the wide BVH nodes visited per
  * instance on this rank (n_instances entries; input of a replica plan).  Any pointer may be NULL. */

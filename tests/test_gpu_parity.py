@@ -490,7 +490,7 @@ def _persist_frame(ranks, root=0, tile_rows=4, grid=24):
     one GPU they share (they wait for each other at the start barrier and exchange rays while running), so the grids are
     bounded; each scene launches on its own stream."""
     for e in ranks:
-        e.domain_persist_config(grid_ctas=grid, shade_at=4)
+        e.domain_persist_config(grid_ctas=grid)
     for e in ranks:
         e.domain_frame_persist(root, tile_rows)
     for e in ranks:

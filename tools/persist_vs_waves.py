@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""One GPU: the wave schedule (k_trace / k_shade launches per bounce level) against the persistent kernel (k_persist, one
+launch per frame) on the bench workloads.  python tools/persist_vs_waves.py [sibenik bunny grid gyroid[:res]] ...
+Prints one JSON line per workload: ms per frame of both, rays per frame, image agreement."""
+import json
+import os
+import statistics
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import gravit_b200 as g  # noqa: E402
+from gravit_b200 import schedulers  # noqa: E402
+from scenes import library  # noqa: E402
+
+names = sys.argv[1:] or ["sibenik", "bunny", "grid"]
+g.init(0)
+dev = torch.device("cuda", 0)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for name in names:
+    t0 = time.perf_counter()
+    if name.startswith("gyroid"):
+        res = int(name.split(":")[1]) if ":" in name else library.GYROID_RES_100M
+        d = library.gyroid_scene(res, 2, 3840, 2160, brick_fn=lambda *a: library.gyroid_brick_torch(*a, device=dev))
+        e, _ = schedulers.build_domain_rank(d, 0, 1)
+        for m in d.meshes:
+            m.verts = m.tris = None
+    else:
+        d = bench.WORKLOADS[name]["make"]()
+        s = library.apply(d, g.GvtScene(flags=d.flags))
+        e = s.engine()
+    build_s = time.perf_counter() - t0
+    out = {"workload": name, "film": [d.width, d.height], "build_s": round(build_s, 2)}
+    fbs = {}
+    for mode in ("waves", "persist"):
+        for shade_at in ((8,) if mode == "waves" else (8, 14, 24)):
+            if mode == "persist":
+                e.domain_persist_config(0, shade_at)
+            frame = (lambda: e.render_async(d.height)) if mode == "waves" else (lambda: e.domain_frame_persist(0, 8))
+            for _ in range(3):
+                frame()
+            e.sync()
+            c = e.counters()
+            ms = []
+            for i in range(10):
+                flush.fill_(i)
+                torch.cuda.synchronize()
+                frame()
+                e.sync()
+                ms.append(e.last_timing()[0])
+            key = mode if mode == "waves" else f"persist_shadesms{shade_at}"
+            out[key + "_ms"] = round(statistics.median(ms), 4)
+            out["rays"] = c["camera_rays"] + c["shadow_generated"] + c["secondary_generated"]
+            fbs[mode] = e.fb_read(d.width, d.height)
+    out["max_abs_diff"] = float(np.abs(fbs["waves"] - fbs["persist"]).max())
+    print(json.dumps(out), flush=True)
+    del e
