@@ -8,25 +8,30 @@ secondary rays -> framebuffer) on one synthetic scene.  rays = camera rays gener
 rays traced (device counters).  Prints ONE JSON line (rank 0).
 
   value      device-timed throughput, scene + BVH resident in HBM, CUDA events around each frame, L2 flushed between
-             frames (a buffer larger than L2 is rewritten)
-  e2e        the same metric through the public frame call (gvtb200_render_frame == api::render): camera/film/light
-             parameters go host->device and the RGBA float image comes back to pinned host memory inside the timed region
-  roofline   dominant kernel = the k_trace launch with the largest share of the frame (for configs[1]: the closest-hit wave
-             of the bounce): algorithmic bytes of THAT launch (ray stream + 128 B per wide node visited + 48 B per
-             triangle tested, from per-launch counter snapshots of a counted frame) / its CUDA-event duration averaged over
-             the timed frames, vs the measured HBM peak
+             frames (a buffer larger than L2 is rewritten), max over ranks
+  e2e        the same metric through the public frame calls with HOST buffers: N = 1 gvtb200_render_frame (== api::render:
+             camera/film/light parameters host->device, the RGBA float image back to pinned host memory); N > 1 every rank
+             renders its rows and brings them to ONE shared pinned host image over its own PCIe link
+             (gvtb200_framebuffer_read_rows), so the image is never funnelled through one GPU
+  roofline   SURVEY 8(d): dominant kernel = the launch with the largest share of the frame; bound = the larger of the issue
+             term (smsp__inst_executed of that launch / (SMs x 4 schedulers x SM clock x its duration)) and the HBM term
+             (dram bytes of that launch / its duration / measured HBM peak).  Instruction and DRAM counts come from an ncu
+             capture of the SAME kernel sources (profiles/r2_ncu_metrics_*.json carries the hash of gravit_b200/csrc; a
+             capture of other sources is refused), durations and the SM clock are measured live in this run
   cpu_baseline  the CPU oracle (a port of the reference semantics; Embree is absent) on the host cores, bounded sample
+  parity     N > 1: max |difference| between the N-GPU image and the same film rendered by rank 0 alone
+  other_workloads  at EVERY N: BASELINE configs[2] (1,024-instance grid, ImageScheduler, 4K, strong scaling) and configs[3]
+             (100 M-triangle gyroid, DomainScheduler, 4K, strong scaling: persistent scheduler with and without shared
+             BLAS, round-synchronous schedule, per-rank busy times); N = 1 also bunny 1080p and configs[4]
 
 --impl reference times that CPU port alone (rank 0 only).
 
-N > 1 (torchrun, one rank per GPU).  ImageScheduler workloads: the film rows of ONE frame are dealt to the ranks in 8-row
-tiles, geometry replicated, and the rows are gathered into rank 0's framebuffer over the NVLink peer path (no collective;
---no-p2p falls back to an NCCL reduce).  gyroid (BASELINE configs[3]): Tracer<DomainScheduler>, brick k of the 2x2x2 split
-lives on rank k mod N, the trace kernel stores migrating rays into the owner's queue over NVLink, one 8-byte all-reduce
-per exchange round (strong scaling of one frame: the 100 M-triangle mesh is the fixed job).  ImageScheduler workloads default to
-WEAK scaling (--scaling weak): the unit of work is a film tile, and with N ranks the film grows by sqrt(N) on each axis (same
-scene, camera and aspect: 1920x1080 -> 2715x1527 -> 3840x2160 -> 5431x3055), so every rank keeps the N = 1 ray count and the
-only cross-rank step is the row gather into rank 0.  --scaling strong deals the N = 1 film over the ranks instead.
+N > 1 (torchrun, one rank per GPU).  Headline: sibenik ImageScheduler, WEAK scaling (--scaling weak): the unit of work is a
+film tile, and with N ranks the film grows by sqrt(N) on each axis (same scene, camera and aspect: 1920x1080 -> 2715x1527 ->
+3840x2160 -> 5431x3055), so every rank keeps the N = 1 ray count; rows are dealt in 8-row tiles and gathered into rank 0's
+framebuffer over the NVLink peer path (no collective; --no-p2p falls back to an NCCL reduce).  --scaling strong deals the
+N = 1 film over the ranks instead.  gyroid (configs[3]): brick k of the 2x2x2 split is OWNED by rank k mod N
+(DomainTracer.h:140); the persistent scheduler lets idle ranks serve copies of the busiest bricks (a measured load plan).
 """
 import argparse
 import json
@@ -56,7 +61,8 @@ WORKLOADS = {
     # configs[3]: 100M-triangle gyroid isosurface in 8 bricks (built per rank in main(): geometry is generated on the GPU)
     "gyroid": dict(make=None, name="gyroid isosurface, 2x2x2 bricks, 3840x2160, primary+shadow (configs[3])"),
 }
-EXTRA_WORKLOADS = ("bunny", "grid", "incoherent")  # measured next to the default workload at N = 1
+EXTRA_N1 = ("bunny", "incoherent")  # measured next to the default workload at N = 1 only
+EXTRA_ALL_N = ("grid", "gyroid")   # BASELINE configs[2] and configs[3]: measured at every N (strong scaling)
 
 
 def peaks():
@@ -201,6 +207,51 @@ def cpu_reference(desc, threads, target_s=12.0):
     return rays / dt / 1e6, f"{frames} frame(s) of the {w}x{h} film of the same scene/camera, {rays} rays in {dt:.2f} s, {threads} threads", rays, dt
 
 
+def ncu_capture(workload, mode="waves"):
+    """The committed ncu counters of `workload`, or (None, why) when they were taken from other kernel sources."""
+    import gravit_b200 as g
+
+    path = os.path.join(ROOT, "profiles", f"r2_ncu_metrics_{workload}_{mode}.json")
+    if not os.path.exists(path):
+        return None, f"no capture ({os.path.relpath(path, ROOT)} is missing)"
+    j = json.load(open(path))
+    if j.get("source_hash") != g.source_hash():
+        return None, f"stale capture: taken from kernel sources {j.get('source_hash')}, this run uses {g.source_hash()}"
+    return j, os.path.relpath(path, ROOT)
+
+
+def shared_host_image(dist, rank, world, H, W):
+    """One RGBA float image in host memory that every rank can write: a file under /dev/shm mapped by all ranks and pinned
+    (cudaHostRegister) by each of them.  Returns (torch tensor view, numpy array, cleanup)."""
+    import torch
+
+    path = [None]
+    if rank == 0:
+        root = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        fd, path[0] = tempfile.mkstemp(prefix="gvtb200_img_", dir=root)
+        os.ftruncate(fd, H * W * 16)
+        os.close(fd)
+    if world > 1:
+        dist.broadcast_object_list(path, src=0)
+    arr = np.memmap(path[0], dtype=np.float32, mode="r+", shape=(H, W, 4))
+    t = torch.from_numpy(arr)
+    rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * 4, 0)
+    pinned = int(rc) == 0
+
+    def cleanup():
+        if pinned:
+            torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(path[0])
+            except OSError:
+                pass
+
+    return t, arr, cleanup, pinned
+
+
 def main():
     # the JSON line must be the only thing on stdout: libraries (NCCL's version banner) write to fd 1, so fd 1 is pointed at
     # stderr for the run and the line goes to the saved descriptor
@@ -221,12 +272,13 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--extra", default=None, help="comma-separated subset of the secondary workloads (bunny,incoherent,grid,gyroid)")
     ap.add_argument("--no-p2p", action="store_true", help="N > 1: NCCL reduce / all-to-all instead of the NVLink peer path")
     ap.add_argument("--owner", default="mod", choices=["mod", "balanced"], help="gyroid: brick k on rank k mod N (the reference's map) or the view-balanced placement")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1, ImageScheduler workloads: weak = the film grows by sqrt(N) per axis so every rank keeps the N = 1 "
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1, ImageScheduler headline: weak = the film grows by sqrt(N) per axis so every rank keeps the N = 1 "
                     "ray count (same scene, camera and aspect); strong = the N = 1 film split over the ranks")
-    ap.add_argument("--domain-schedule", default="rounds", choices=["async", "rounds"], help="gyroid, N > 1, peer path: free-running ranks with counter termination (scheduler::AsyncDomain) or "
-                    "exchange rounds ended by an all-reduce (Tracer<DomainScheduler>); the other one is timed as well and reported in config")
+    ap.add_argument("--replicas", type=int, default=1, help="gyroid, persistent scheduler: BLAS copies of other ranks' bricks a rank may hold (0 = the owner alone serves a brick)")
+    ap.add_argument("--shade-sms", type=int, default=0, help="persistent scheduler: SMs that shade instead of tracing (0 = default)")
     ap.add_argument("--gyroid-res", type=int, default=library.GYROID_RES_100M, help="grid cells per axis of the gyroid volume (946 = 100 M triangles)")
     a = ap.parse_args()
     a.warmup = max(3, a.warmup)
@@ -235,6 +287,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = WORKLOADS[a.workload]
     threads = os.cpu_count() or 1
+    vs_note = "CPU port of the reference path (oracle/), NOT Embree: Embree 2.15 / TBB / MPI / IceT are absent, the Embree adapter cannot be built here"
 
     if a.impl == "reference":
         if rank != 0:
@@ -260,7 +313,8 @@ def main():
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(dts) / len(dts), "higher_is_better": True,
             "scaling": "strong" if (a.gpus > 1 and (a.scaling == "strong" or a.workload == "gyroid")) else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "film": [d.width, d.height], "depth": d.depth, "note": "CPU port of the reference path (oracle/); Embree 2.15 is absent so the Embree adapter itself cannot be built"},
+            "config": {"workload": wl["name"], "film": [timer.w, timer.h], "film_of_the_workload": [d.width, d.height], "depth": d.depth,
+                       "note": vs_note + "; the bounded sample is the same scene and camera on the reduced film given in `film`"},
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
@@ -278,279 +332,427 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-
-    domain = a.workload == "gyroid"
     p2p = world > 1 and not a.no_p2p
-    # ImageScheduler at N > 1: the unit of work is a film tile.  weak = N times the tiles of the N = 1 film (each axis x sqrt(N),
-    # same scene / camera / aspect), every rank keeps the N = 1 ray count; strong = the N = 1 film dealt over the ranks.
-    weak = world > 1 and not domain and a.scaling == "weak"
-    build_s = [0.0]
-
-    def setup(name):
-        if name == "gyroid":
-            # every rank generates (on its GPU) and builds only the bricks it owns: brick k -> rank k mod N (DomainTracer.h:140)
-            t0 = time.perf_counter()
-            owner = schedulers.domain_owner(8, world) if a.owner == "mod" else schedulers.gyroid_balanced_owner(world)
-            mine = [k for k in range(8) if owner[k] == rank]
-            d = library.gyroid_scene(a.gyroid_res, 2, 3840, 2160, only_bricks=mine, brick_fn=lambda *args: library.gyroid_brick_torch(*args, device=dev))
-            boxes = schedulers.mesh_boxes_allgather(d, dist, world)
-            e, _ = schedulers.build_domain_rank(d, rank, world, boxes=boxes, owner=owner)
-            d.owner = [int(x) for x in owner]
-            n_tris = torch.tensor([sum(len(m.tris) for m in d.meshes if m.verts is not None)], dtype=torch.int64, device=dev)
-            if world > 1:
-                dist.all_reduce(n_tris)
-            d.n_tris = int(n_tris.item())
-            for m in d.meshes:
-                m.verts = m.tris = None  # the host copies are not needed any more
-            build_s[0] = time.perf_counter() - t0
-            return d, None, e
-        if weak and name == a.workload:
-            d0 = WORKLOADS[name]["make"]()
-            f = world ** 0.5
-            d = WORKLOADS[name]["make"](int(round(d0.width * f)), int(round(d0.height * f)))
-        else:
-            d = WORKLOADS[name]["make"]()
-        s = library.apply(d, g.GvtScene(flags=d.flags))
-        e = s.engine()
-        return d, s, e
-
     # one explicit stream for the engine, the L2 flush, NCCL's entry/exit events and the timing events
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    d, s, e = setup(a.workload)
-    W, H = d.width, d.height
-    e.set_stream(stream.cuda_stream)
-    fb_ptr, _ = e.device_framebuffer()
-    fb_t = schedulers.device_tensor(fb_ptr, (H, W, 4))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    if p2p:
-        schedulers.p2p_connect(e, dist, rank, world, dev)
-    rounds = [0]
-    board = schedulers.AsyncBoard.connect(dist, rank, world) if (domain and p2p) else None  # control plane of the asynchronous schedule
-    use_async = [a.domain_schedule == "async"]
-    frame_no = [0]
-
-    def step():
-        if not domain:
-            schedulers.render_image_schedule(e, W, H, dist if world > 1 else None, rank, world, a.tile_rows, fb_t, p2p=p2p)
-        elif world == 1:
-            e.render_async(H)  # one rank owns every brick: Tracer<DomainScheduler> degenerates to the local drain loop
-        elif p2p and use_async[0]:
-            frame_no[0] += 1
-            rounds[0] = schedulers.render_domain_schedule_async(e, board, rank, world, frame_no[0])
-        elif p2p:
-            rounds[0] = len(schedulers.render_domain_schedule_p2p(e, dist, rank, world))
-        else:
-            rounds[0] = len(schedulers.render_domain_schedule(e, dist, rank, world, dev, fb_t))
-
-    e.profile_launches(world == 1)  # an event pair around every kernel launch of the frame, on the launching stream
-    for _ in range(a.warmup):
-        step()
-    torch.cuda.synchronize()
-    ctr = e.counters()
-    # DomainScheduler: every rank generates all camera rays and keeps the ones that enter its bricks first (DomainTracer.h:148-181)
-    rays_local = ctr["shadow_generated"] + ctr["secondary_generated"] + (0 if (domain and world > 1) else ctr["camera_rays"])
     ctr_keys = ("camera_rays", "routed_initial", "primary_hits", "shadow_generated", "shadow_unoccluded", "secondary_generated", "fb_adds", "rays_exported", "queue_overflows", "stack_overflows")
-    rays_t = torch.tensor([rays_local] + [ctr[k] for k in ctr_keys], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(rays_t)
-    rays_frame = int(rays_t[0].item()) + (W * H * d.samples * d.samples if (domain and world > 1) else 0)
-    ctr_all = {k: int(v) for k, v in zip(ctr_keys, rays_t[1:].tolist())}
-    if domain and world > 1:
-        ctr_all["camera_rays"] = W * H * d.samples * d.samples
 
-    launches0 = g.lib().gvtb200_launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    trace_ms = []
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_wall0 = time.perf_counter()
-    for i in range(a.steps):
-        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the per-step events)
-        ev[i][0].record()
-        step()
-        ev[i][1].record()
-        if world == 1:
-            torch.cuda.synchronize()
-            trace_ms.append([(k, ms) for k, ms, _ in e.launch_records()])
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if sampler else None
-    launches = g.lib().gvtb200_launch_count() - launches0
-    ms_local = sum(x.elapsed_time(y) for x, y in ev)
-    ms_t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    total_ms = float(ms_t.item())
-    ms_per_step = total_ms / a.steps
-    value = rays_frame / (ms_per_step * 1e-3) / 1e6
-    polls_main = rounds[0]
+    def allsum(vals, op=None):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op or dist.ReduceOp.SUM)
+        return t.tolist()
 
-    other_sched = None
-    if domain and p2p:  # the other DomainScheduler schedule on the same scene, same protocol (reported beside the headline)
-        use_async[0] = not use_async[0]
-        for _ in range(2):
-            step()
-        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-        dist.barrier()
-        torch.cuda.synchronize()
-        for i in range(a.steps):
-            flush.fill_(i & 0xFF)
-            ev2[i][0].record()
-            step()
-            ev2[i][1].record()
-        dist.barrier()
-        torch.cuda.synchronize()
-        o_t = torch.tensor([sum(x.elapsed_time(y) for x, y in ev2)], dtype=torch.float64, device=dev)
-        dist.all_reduce(o_t, op=dist.ReduceOp.MAX)
-        other_sched = {"schedule": "async" if use_async[0] else "rounds", "ms_per_step": float(o_t.item()) / a.steps, "rounds_or_polls": rounds[0]}
-        use_async[0] = not use_async[0]
-
-    # ---- end to end through the public frame call, host buffers (N = 1: gvtb200_render_frame; N > 1: + gather) ----
-    host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
-    e2e_ms = []
-    for i in range(a.warmup + a.steps):
-        flush.fill_(i & 0xFF)
-        torch.cuda.synchronize()
+    def barrier():
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        if world == 1:
-            e.render_into(host.data_ptr(), H)  # parameters H2D, frame, image D2H, synchronous
-        else:
+
+    def timed(step, steps, warmup, sync_each=None):
+        """W untimed steps, then K steps bracketed by CUDA events on the launching stream; max over ranks of the total."""
+        for _ in range(warmup):
             step()
-            if rank == 0:
-                host.copy_(fb_t, non_blocking=True)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the per-step events)
+            ev[i][0].record()
+            step()
+            ev[i][1].record()
+            if sync_each:
+                torch.cuda.synchronize()
+                sync_each(i)
+        barrier()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = allsum([sum(x.elapsed_time(y) for x, y in ev)], dist.ReduceOp.MAX if world > 1 else None)[0]
+        return ms / steps, wall
+
+    def frame_rays(e, domain_sharded_camera=False):
+        c = e.counters()
+        local = c["camera_rays"] + c["shadow_generated"] + c["secondary_generated"]
+        tot = allsum([local] + [c[k] for k in ctr_keys])
+        return int(tot[0]), {k: int(v) for k, v in zip(ctr_keys, tot[1:])}
+
+    # ================= ImageScheduler workloads (sibenik, bunny, grid, incoherent) =========================================
+    def run_image(name, film=None, steps=None, warmup=None, headline=False, scaling="strong"):
+        steps, warmup = steps or a.steps, warmup or a.warmup
+        d = WORKLOADS[name]["make"](*film) if film else WORKLOADS[name]["make"]()
+        s = library.apply(d, g.GvtScene(flags=d.flags))
+        e = s.engine()
+        W, H = d.width, d.height
+        e.set_stream(stream.cuda_stream)
+        fb_ptr, _ = e.device_framebuffer()
+        fb_t = schedulers.device_tensor(fb_ptr, (H, W, 4))
+        if p2p:
+            schedulers.p2p_connect(e, dist, rank, world, dev)
+
+        def step():
+            schedulers.render_image_schedule(e, W, H, dist if world > 1 else None, rank, world, a.tile_rows, fb_t, p2p=p2p)
+
+        res = {"workload": WORKLOADS[name]["name"], "film": [W, H], "depth": d.depth, "samples": d.samples}
+        e.profile_launches(world == 1 and headline)
+        for _ in range(warmup):
+            step()
+        e.sync()
+        rays, ctr_all = frame_rays(e)
+        trace_ms = []
+        launches0 = g.lib().gvtb200_launch_count()
+        sampler = ClockSampler(local_rank) if (rank == 0 and headline) else None
+        ms, wall = timed(step, steps, 0, sync_each=(lambda i: trace_ms.append([(k, t) for k, t, _ in e.launch_records()])) if (world == 1 and headline) else None)
+        res["clocks"] = sampler.stop() if sampler else None
+        res["launches"] = int(g.lib().gvtb200_launch_count() - launches0)
+        e.sync()  # raises if a queue overflowed or a peer timed out
+        res.update(ms_per_frame=ms, rays_per_frame=rays, Mrays_per_s=rays / (ms * 1e-3) / 1e6, counters=ctr_all, wall_s=wall, trace_ms=trace_ms)
+        entered = ctr_all["routed_initial"] + ctr_all["shadow_generated"] + ctr_all["secondary_generated"]
+        res["Mrays_per_s_entered_an_instance"] = entered / (ms * 1e-3) / 1e6  # rays that were actually traced in a BLAS (background camera rays excluded)
+        # ---- end to end with host buffers -------------------------------------------------------------------------------
+        if world == 1:
+            host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+            cleanup = lambda: None  # noqa: E731
+        else:
+            host, host_np, cleanup, pinned = shared_host_image(dist, rank, world, H, W)
+            res["e2e_host_image"] = "one /dev/shm image mapped by all ranks, " + ("cudaHostRegister'ed by each" if pinned else "NOT pinned (cudaHostRegister failed)")
+        e2e_ms = []
+        for i in range(warmup + steps):
+            flush.fill_(i & 0xFF)
             torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) * 1e3
-        if i >= a.warmup:
-            e2e_ms.append(dt)
-    e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = rays_frame / (float(e2e_t.item()) / a.steps * 1e-3) / 1e6
+            barrier()
+            t0 = time.perf_counter()
+            if world == 1:
+                e.render_into(host.data_ptr(), H)  # parameters H2D, frame, image D2H, synchronous
+            else:
+                e.render_tiles(H, a.tile_rows, rank, world)  # this rank's rows ...
+                e.fb_read_rows(host.data_ptr(), a.tile_rows, rank, world)  # ... straight to their place in the host image
+                e.sync()
+            dt = (time.perf_counter() - t0) * 1e3
+            if i >= warmup:
+                e2e_ms.append(dt)
+        e2e = allsum([sum(e2e_ms)], dist.ReduceOp.MAX if world > 1 else None)[0] / steps
+        res["e2e"] = {"value": rays / (e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e, "h2d_bytes_per_step": 496 * world, "d2h_bytes_per_step": W * H * 16,
+                      "call": "gvtb200_render_frame (== api::render) into pinned host memory" if world == 1 else
+                      f"gvtb200_render_frame_tiles + gvtb200_framebuffer_read_rows on every rank: {world} PCIe links write one shared pinned host image"}
+        # ---- parity: the N-GPU image against the same film rendered by rank 0 alone ---------------------------------------
+        if world > 1:
+            barrier()
+            img_host = np.array(host_np) if rank == 0 else None  # what the last e2e frame left in the shared image
+            step()
+            e.sync()
+            barrier()
+            if rank == 0:
+                img_gather = e.fb_read(W, H)
+                e.render_async(H)
+                e.sync()
+                ref = e.fb_read(W, H)
+                res["parity"] = {"max_abs_err_gather": float(np.abs(img_gather - ref).max()), "max_abs_err_host_image": float(np.abs(img_host - ref).max()),
+                                 "reference": "the same film rendered by rank 0 alone (gvtb200_render_frame_async)", "lit_pixels": int((ref[..., 3] > 0).sum())}
+            barrier()
+        cleanup()
+        if p2p:
+            barrier()
+            e.p2p_detach()
+            barrier()
+        return res, e, d
+
+    # ================= BASELINE configs[3]: gyroid, Tracer<DomainScheduler> ==================================================
+    def run_gyroid(steps=None, warmup=None):
+        steps, warmup = steps or a.steps, warmup or a.warmup
+        t0 = time.perf_counter()
+        owner = schedulers.domain_owner(8, world) if a.owner == "mod" else schedulers.gyroid_balanced_owner(world)
+        mine = [k for k in range(8) if owner[k] == rank]
+        d = library.gyroid_scene(a.gyroid_res, 2, 3840, 2160, only_bricks=mine, brick_fn=lambda *args: library.gyroid_brick_torch(*args, device=dev))
+        gen_s = time.perf_counter() - t0
+        boxes = schedulers.mesh_boxes_allgather(d, dist, world)
+        e, _ = schedulers.build_domain_rank(d, rank, world, boxes=boxes, owner=owner)
+        n_tris = int(allsum([sum(len(m.tris) for m in d.meshes if m.verts is not None)])[0])
+        blas_ms = [e._keep[k].stats()["build_us"] * 1e-3 for k in range(8) if e._keep[k] is not None]
+        for m in d.meshes:
+            m.verts = m.tris = None  # the host copies are not needed any more
+        torch.cuda.empty_cache()
+        build_s = time.perf_counter() - t0
+        W, H = d.width, d.height
+        e.set_stream(stream.cuda_stream)
+        if world > 1:
+            schedulers.p2p_connect(e, dist, rank, world, dev)
+        if a.shade_sms:
+            e.domain_persist_config(0, a.shade_sms)
+        res = {"workload": f"gyroid isosurface {n_tris:,} tris in 2x2x2 bricks (res {a.gyroid_res}), 3840x2160, 1 point light, primary+shadow (configs[3])",
+               "film": [W, H], "n_tris": n_tris, "owner": [int(x) for x in owner], "scene_build_s": round(build_s, 2), "geometry_generation_s": round(gen_s, 2),
+               "blas_build_ms_per_brick_this_rank": [round(x, 1) for x in blas_ms],
+               "blas_build_Mtris_per_s_this_rank": round(n_tris / 8.0 * len(mine) / max(1e-9, sum(blas_ms) * 1e-3) / 1e6, 1)}
+
+        def persist():
+            schedulers.render_domain_persist(e, 0, a.tile_rows)
+
+        def persist_stats():
+            busy, inbox, _ = e.domain_persist_stats()
+            b = torch.zeros(world, dtype=torch.float64, device=dev)
+            b[rank] = busy
+            r = torch.zeros(world, dtype=torch.float64, device=dev)
+            r[rank] = inbox
+            if world > 1:
+                dist.all_reduce(b)
+                dist.all_reduce(r)
+            b, r = b.tolist(), r.tolist()
+            return {"busy_ms_per_rank": [round(x, 3) for x in b], "imbalance_max_over_mean": round(max(b) / max(1e-9, sum(b) / len(b)), 3), "inbox_rays_per_rank": [int(x) for x in r]}
+
+        def measure(label, step):
+            ms, _ = timed(step, steps, warmup)
+            e.sync()
+            _, ctr_all = frame_rays(e)
+            # persistent scheduler: every rank generates its own shard of the camera rays; round-synchronous: every rank
+            # generates all of them and keeps its own (DomainTracer.h:148-181) -- the film's rays are counted once either way
+            assert ctr_all["camera_rays"] in (W * H, W * H * world), ctr_all
+            ctr_all["camera_rays"] = W * H
+            rays = W * H + ctr_all["shadow_generated"] + ctr_all["secondary_generated"]
+            out = {"schedule": label, "ms_per_frame": ms, "rays_per_frame": rays, "Mrays_per_s": rays / (ms * 1e-3) / 1e6, "rays_exported": ctr_all["rays_exported"],
+                   "queue_overflows": ctr_all["queue_overflows"]}
+            return out, ctr_all
+
+        # (1) the persistent scheduler, every brick served by its owner alone
+        base, ctr_all = measure("persistent kernel, brick served by its owner", persist)
+        base.update(persist_stats())
+        res["persistent_owner_only"] = base
+        headline = base
+        descs = None
+        if world > 1:
+            # (2) shared BLAS: a counted frame gives the load per brick, the plan spreads the hot bricks over idle ranks
+            e.profile_counters(True)
+            persist()
+            e.sync()
+            load = e.domain_persist_stats(8)[2].astype(np.float64)
+            e.profile_counters(False)
+            load = np.array(allsum(load))
+            descs = schedulers.exchange_mesh_descs(dist, e._keep, e.recipe["inst"], owner, rank, world, dev)
+            if a.replicas > 0:
+                tab_r, tab_w = schedulers.plan_servers(load, owner, world, max_replicas=a.replicas)
+                t1 = time.perf_counter()
+                keep = schedulers.apply_server_plan(e, tab_r, tab_w, descs, rank, mode=g.IMPORT_COPY)
+                torch.cuda.synchronize()
+                barrier()
+                shared, _ = measure(f"persistent kernel, <= {a.replicas} BLAS replica(s) of other ranks' bricks per rank (copied from the owner over NVLink)", persist)
+                shared.update(persist_stats())
+                shared.update(servers=[[int(x) for x in row if x >= 0] for row in tab_r], shares=[[round(float(w), 3) for w, x in zip(wr, row) if x >= 0] for wr, row in zip(tab_w, tab_r)],
+                              node_visits_per_brick=[int(x) for x in load], replica_setup_s=round(time.perf_counter() - t1, 3))
+                res["persistent_shared_blas"] = shared
+                if shared["ms_per_frame"] < headline["ms_per_frame"]:
+                    headline = shared
+        # parity: the N-rank image (root's framebuffer) against ONE rank tracing every brick (the others' BLAS mapped over NVLink)
+        persist()
+        e.sync()
+        barrier()
+        if world > 1:
+            if rank == 0:
+                img = e.fb_read(W, H)
+                full, imported = schedulers.whole_scene_on_one_rank(e, descs, owner, rank, mode=g.IMPORT_MAP)
+                t1 = time.perf_counter()
+                ref, _ = full.render(W, H)
+                res["parity"] = {"max_abs_err": float(np.abs(img - ref).max()), "lit_pixels": int((ref[..., 3] > 0).sum()),
+                                 "reference": "rank 0 alone renders the whole scene through the wave path, the other ranks' bricks traversed through NVLink-mapped BLAS",
+                                 "reference_frame_s": round(time.perf_counter() - t1, 3)}
+                full.close()
+                del imported
+            barrier()
+        else:
+            img = e.fb_read(W, H)
+            ref, _ = e.render(W, H)  # the wave path on the same scene
+            res["parity"] = {"max_abs_err": float(np.abs(img - ref).max()), "lit_pixels": int((ref[..., 3] > 0).sum()), "reference": "the wave path (k_trace / k_shade launches) on the same scene"}
+        # (3) the other schedules, for comparison
+        if world > 1:
+            e.domain_set_servers(None)
+            rounds = [0]
+
+            def rounds_step():
+                rounds[0] = len(schedulers.render_domain_schedule_p2p(e, dist, rank, world))
+
+            rs, _ = measure("round-synchronous (Tracer<DomainScheduler>): one trace/shade/trace wave and an 8-byte all-reduce per exchange round, NVLink peer queues", rounds_step)
+            rs["rounds"] = rounds[0]
+            res["round_synchronous"] = rs
+        else:
+            ws, _ = measure("wave path (k_trace / k_shade launches per bounce level), all bricks on one GPU", lambda: e.render_async(H))
+            res["waves"] = ws
+            if ws["ms_per_frame"] < headline["ms_per_frame"]:
+                headline = ws
+        # ---- end to end: frame + parallel read-back of the root's image ---------------------------------------------------
+        if world > 1 and a.replicas > 0 and headline is res.get("persistent_shared_blas"):
+            e.domain_set_servers(tab_r, tab_w)
+        host, host_np, cleanup, pinned = shared_host_image(dist, rank, world, H, W)
+        use_waves = world == 1 and headline is res.get("waves")
+        e2e_ms = []
+        for i in range(warmup + steps):
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize()
+            barrier()
+            t1 = time.perf_counter()
+            if use_waves:
+                e.render_into(host.data_ptr(), H)
+            else:
+                persist()
+                e.fb_read_rows(host.data_ptr(), a.tile_rows, rank, world, src_rank=0 if world > 1 else -1)
+                e.sync()
+            dt = (time.perf_counter() - t1) * 1e3
+            if i >= warmup:
+                e2e_ms.append(dt)
+        e2e = allsum([sum(e2e_ms)], dist.ReduceOp.MAX if world > 1 else None)[0] / steps
+        barrier()
+        if rank == 0 and "parity" in res:
+            res["parity"]["max_abs_err_host_image"] = float(np.abs(np.array(host_np) - ref).max())
+        res["e2e"] = {"value": headline["rays_per_frame"] / (e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e, "h2d_bytes_per_step": 496 * world, "d2h_bytes_per_step": W * H * 16,
+                      "call": "gvtb200_render_frame into pinned host memory" if use_waves else "gvtb200_domain_frame_persist + gvtb200_framebuffer_read_rows on every rank (rows of the root's image over NVLink, then this rank's PCIe link)"}
+        cleanup()
+        res.update(ms_per_frame=headline["ms_per_frame"], Mrays_per_s=headline["Mrays_per_s"], rays_per_frame=headline["rays_per_frame"], schedule=headline["schedule"], counters=ctr_all)
+        if world > 1:
+            barrier()
+            e.p2p_detach()
+            barrier()
+        return res, e, d
+
+    # ================= the headline workload ========================================================================================
+    domain = a.workload == "gyroid"
+    weak = world > 1 and not domain and a.scaling == "weak"
+    if domain:
+        hres, e, d = run_gyroid()
+    else:
+        film = None
+        if weak:
+            d0 = WORKLOADS[a.workload]["make"]()
+            f = world ** 0.5
+            film = (int(round(d0.width * f)), int(round(d0.height * f)))
+        hres, e, d = run_image(a.workload, film, headline=True, scaling="weak" if weak else "strong")
+    W, H = d.width, d.height
+    ms_per_step, rays_frame = hres["ms_per_frame"], hres["rays_per_frame"]
 
     out = None
-    if rank == 0:
+    roof = None
+    cpu = None
+    if rank == 0 and world == 1 and not domain:
         pk, pk_kind = peaks()
-        roof = None
-        cpu = None
-        extra = {}
-        if world == 1:
-            # counted frame: per-launch snapshots of the device counters -> algorithmic bytes of every launch
-            e.profile_counters(True)
-            e.render_async(H)
-            e.sync()
-            recs = e.launch_records()
-            e.profile_counters(False)
-            names = {0: "k_camera_route", 1: "k_trace (closest hit)", 2: "k_shade", 3: "k_trace (any hit, shadow rays)"}
-            zero = {k: 0 for k in g.COUNTER_FIELDS}
-            launches_out = []
-            for i, (kind, _, after) in enumerate(recs):
-                before = recs[i - 1][2] if i else zero
-                dlt = {k: after[k] - before[k] for k in after}
-                ms_i = statistics.mean(t[i][1] for t in trace_ms)
-                # ray stream: 68 B read per queued ray (generated camera rays: 0), 84 B per hit record written + read by k_shade,
-                # 68 B per ray emitted, 16 B per framebuffer add; scene: 128 B per wide node, 48 B per triangle record
-                n_in = dlt["instance_visits"] if kind in (1, 3) else dlt["primary_hits"]
-                if kind == 1:
-                    ray_b = (0 if (i == 0) else 68) * n_in + 84 * (recs[i + 1][2]["primary_hits"] - after["primary_hits"] if i + 1 < len(recs) else 0)
-                elif kind == 3:
-                    ray_b = 68 * n_in + 16 * dlt["fb_adds"]
-                elif kind == 2:
-                    ray_b = 84 * dlt["primary_hits"] + 68 * (dlt["shadow_generated"] + dlt["secondary_generated"])
-                else:
-                    ray_b = 68 * dlt["routed_initial"]
-                scene_b = dlt["nodes_visited"] * 128 + dlt["tris_tested"] * 48
-                launches_out.append({"kernel": names[kind], "ms": ms_i, "share": ms_i / ms_per_step, "rays": n_in, "nodes_visited": dlt["nodes_visited"],
-                                     "tris_tested": dlt["tris_tested"], "algorithmic_bytes": ray_b + scene_b, "GBps": (ray_b + scene_b) / (ms_i * 1e-3) / 1e9})
-            dom = max(range(len(launches_out)), key=lambda i: launches_out[i]["ms"])
-            dl = launches_out[dom]
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "r1_ncu_dominant_kernel.json")
-            if os.path.exists(tp):
-                try:
-                    tj = json.load(open(tp))
-                    if tj.get("workload") == a.workload:
-                        traffic = tj.get("dram_bytes_per_launch")
-                except Exception:
-                    traffic = None
-            roof = {
-                "bound": "hbm", "achieved": dl["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dl["GBps"] / pk["hbm_gbs"], "traffic": traffic,
-                "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-                "kernel": f"{dl['kernel']}, launch {dom} of the frame ({100 * dl['share']:.0f}% of the step)",
-                "algorithmic_bytes_per_launch": dl["algorithmic_bytes"],
-                "per_ray": {"nodes_visited": dl["nodes_visited"] / max(1, dl["rays"]), "tris_tested": dl["tris_tested"] / max(1, dl["rays"])},
-                "launches": launches_out,
-                "note": "nodes + triangles are L1/L2 resident at this scene size: the kernel is bound by instruction issue, L1 wavefronts and warp divergence (profiles/), "
-                        "not by HBM; traffic = dram bytes of the same launch from the committed ncu capture",
-            }
-            if not a.no_cpu:
-                cpu_make = WORKLOADS[a.workload]["make"] or (lambda: library.gyroid_scene(128, 2, 3840, 2160))
-                v, sample, _, _ = cpu_reference(cpu_make, threads)
-                if domain:
-                    sample += "; gyroid at res 128 (1.8 M triangles): the CPU port cannot build the 100 M-triangle BVH inside a bench run"
-                cpu = {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample}
-            if not a.no_extra:
-                for name in EXTRA_WORKLOADS:
-                    if name == a.workload:
-                        continue
-                    try:
-                        d2, s2, e2 = setup(name)
-                        for _ in range(3):
-                            e2.render_async(d2.height)
-                        e2.sync()
-                        c2 = e2.counters()
-                        r2 = c2["camera_rays"] + c2["shadow_generated"] + c2["secondary_generated"]
-                        ms = []
-                        for i in range(10):
-                            flush.fill_(i)
-                            torch.cuda.synchronize()
-                            e2.render_async(d2.height)
-                            e2.sync()
-                            ms.append(e2.last_timing()[0])
-                        m = statistics.median(ms)
-                        extra[name] = {"workload": WORKLOADS[name]["name"], "Mrays_per_s": r2 / (m * 1e-3) / 1e6, "ms_per_frame": m, "rays_per_frame": r2}
-                    except Exception as ex:  # noqa: BLE001
-                        extra[name] = {"error": str(ex)}
-        if domain:
-            wl = dict(wl, name=f"gyroid isosurface {d.n_tris:,} tris in 2x2x2 bricks (res {a.gyroid_res}), 3840x2160, 1 point light, primary+shadow (configs[3])")
-            if world == 1:
-                sched_desc = "DomainScheduler, 1 rank owns all bricks"
-            elif not p2p:
-                sched_desc = f"DomainScheduler, {world} ranks, brick -> rank {d.owner}, NCCL all-to-all of 80-byte ray records, {polls_main} rounds, NCCL reduce"
-            elif a.domain_schedule == "async":
-                sched_desc = (f"asynchronous DomainScheduler (scheduler::AsyncDomain), {world} ranks, brick -> rank {d.owner}, rays stored into the owner's inbound region over NVLink "
-                              f"(CUDA IPC) by the trace kernel, no exchange rounds: free-running ranks, sent/received counters on a shared-memory board for termination ({polls_main} polls on rank 0), "
-                              "framebuffer accumulated into rank 0 over NVLink")
+        # counted frame: per-launch snapshots of the device counters -> algorithmic bytes of every launch
+        e.profile_launches(True)
+        e.profile_counters(True)
+        e.render_async(H)
+        e.sync()
+        recs = e.launch_records()
+        e.profile_counters(False)
+        names = {0: "k_camera_route", 1: "k_trace (closest hit)", 2: "k_shade", 3: "k_trace (any hit, shadow rays)"}
+        zero = {k: 0 for k in g.COUNTER_FIELDS}
+        cap, cap_src = ncu_capture(a.workload, "waves")
+        cap_l = cap["launches"] if cap else []
+        if cap and len(cap_l) != len(recs):
+            cap, cap_src, cap_l = None, f"capture has {len(cap_l)} launches, the frame has {len(recs)}", []
+        clk = (hres["clocks"] or {}).get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
+        sms = g.device_info()["sm_count"]
+        issue_peak = sms * 4 * clk * 1e6  # warp instructions per second: one per scheduler per clock
+        launches_out = []
+        for i, (kind, _, after) in enumerate(recs):
+            before = recs[i - 1][2] if i else zero
+            dlt = {k: after[k] - before[k] for k in after}
+            ms_i = statistics.mean(t[i][1] for t in hres["trace_ms"])
+            # ray stream: 68 B read per queued ray (generated camera rays: 0), 84 B per hit record written + read by k_shade,
+            # 68 B per ray emitted, 16 B per framebuffer add; scene: 128 B per wide node, 48 B per triangle record
+            n_in = dlt["instance_visits"] if kind in (1, 3) else dlt["primary_hits"]
+            if kind == 1:
+                ray_b = (0 if (i == 0) else 68) * n_in + 84 * (recs[i + 1][2]["primary_hits"] - after["primary_hits"] if i + 1 < len(recs) else 0)
+            elif kind == 3:
+                ray_b = 68 * n_in + 16 * dlt["fb_adds"]
+            elif kind == 2:
+                ray_b = 84 * dlt["primary_hits"] + 68 * (dlt["shadow_generated"] + dlt["secondary_generated"])
             else:
-                sched_desc = (f"DomainScheduler, {world} ranks, brick -> rank {d.owner}, rays stored into the owner's queue over NVLink (CUDA IPC) by the trace kernel, "
-                              f"8-byte all-reduce per round, {polls_main} rounds, framebuffer accumulated into rank 0 over NVLink")
+                ray_b = 68 * dlt["routed_initial"]
+            scene_b = dlt["nodes_visited"] * 128 + dlt["tris_tested"] * 48
+            lo = {"kernel": names[kind], "ms": ms_i, "share": ms_i / ms_per_step, "rays": n_in, "nodes_visited": dlt["nodes_visited"], "tris_tested": dlt["tris_tested"],
+                  "algorithmic_bytes": ray_b + scene_b, "algorithmic_GBps_through_L1_L2": (ray_b + scene_b) / (ms_i * 1e-3) / 1e9}
+            if cap:
+                c = cap_l[i]
+                inst, dram = c.get("smsp__inst_executed.sum"), (c.get("dram__bytes_read.sum", 0.0) + c.get("dram__bytes_write.sum", 0.0))
+                lo.update(warp_inst=inst, issue_frac=inst / (ms_i * 1e-3) / issue_peak, dram_bytes=dram, hbm_frac=dram / (ms_i * 1e-3) / 1e9 / pk["hbm_gbs"],
+                          simt_lanes_per_inst=c.get("smsp__thread_inst_executed_per_inst_executed.ratio"), l1_wavefronts_pct_of_peak=c.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                          ncu_ms=c.get("gpu__time_duration.sum", 0.0) * 1e3, ncu_kernel=c.get("kernel"))
+            launches_out.append(lo)
+        dom = max(range(len(launches_out)), key=lambda i: launches_out[i]["ms"])
+        dl = launches_out[dom]
+        roof = {"kernel": f"{dl['kernel']}, launch {dom} of the frame ({100 * dl['share']:.0f}% of the step)",
+                "per_ray": {"nodes_visited": dl["nodes_visited"] / max(1, dl["rays"]), "tris_tested": dl["tris_tested"] / max(1, dl["rays"])},
+                "algorithmic_bytes_per_launch": dl["algorithmic_bytes"], "launches": launches_out, "counters_source": cap_src}
+        if cap:
+            issue, hbm = dl["issue_frac"], dl["hbm_frac"]
+            wi = sum(l["warp_inst"] for l in launches_out)
+            roof.update({
+                "bound": "issue" if issue >= hbm else "hbm", "frac": max(issue, hbm),
+                "achieved": dl["warp_inst"] / (dl["ms"] * 1e-3) / 1e9 if issue >= hbm else dl["dram_bytes"] / (dl["ms"] * 1e-3) / 1e9,
+                "peak": issue_peak / 1e9 if issue >= hbm else pk["hbm_gbs"], "unit": "Gwarp-inst/s" if issue >= hbm else "GB/s",
+                "traffic": dl["dram_bytes"], "issue_frac": issue, "hbm_frac": hbm, "simt_lanes_per_inst": dl["simt_lanes_per_inst"], "l1_wavefronts_pct_of_peak": dl["l1_wavefronts_pct_of_peak"],
+                "peak_source": f"issue: {sms} SMs x 4 schedulers x {clk:.0f} MHz (SM clock sampled during the timed region); hbm: {pk_kind} MEASURED_PEAKS.json hbm_gbs (burst copy)",
+                "frame": {"issue_frac": wi / (ms_per_step * 1e-3) / issue_peak, "hbm_frac": sum(l["dram_bytes"] for l in launches_out) / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+                          "lane_issue_frac": sum(l["warp_inst"] * l["simt_lanes_per_inst"] for l in launches_out) / 32.0 / (ms_per_step * 1e-3) / issue_peak},
+                "note": "SURVEY 8(d): frac = max(issue term, HBM term) of the dominant launch; nodes + triangles are L1/L2 resident at this scene size, so DRAM carries the ray stream only",
+            })
+        else:
+            roof.update({"bound": "issue", "frac": None, "achieved": None, "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s", "traffic": None,
+                         "note": "no ncu capture of THESE kernel sources is committed (" + str(cap_src) + "): the issue and HBM terms are not reported rather than taken from a stale file"})
+        if not a.no_cpu:
+            v, sample, _, _ = cpu_reference(WORKLOADS[a.workload]["make"], threads)
+            cpu = {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample, "note": vs_note}
+    if rank == 0 and world == 1 and domain and not a.no_cpu:
+        v, sample, _, _ = cpu_reference(lambda: library.gyroid_scene(128, 2, 3840, 2160), threads)
+        cpu = {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "note": vs_note,
+               "sample": sample + "; gyroid at res 128 (1.8 M triangles): the CPU port cannot build the 100 M-triangle BVH inside a bench run"}
+    del e
+
+    # ================= the other BASELINE workloads ================================================================================
+    extra = {}
+    wanted = None if a.extra is None else set(x for x in a.extra.split(",") if x)
+    if not a.no_extra:
+        names = [n for n in EXTRA_ALL_N + (EXTRA_N1 if world == 1 else ()) if n != a.workload and (wanted is None or n in wanted)]
+        if world > 1 and a.workload == "sibenik" and weak and (wanted is None or "sibenik_strong" in wanted):
+            names.append("sibenik_strong")
+        for name in names:
+            try:
+                if name == "gyroid":
+                    r2, e2, _ = run_gyroid(steps=10, warmup=3)
+                elif name == "sibenik_strong":
+                    r2, e2, _ = run_image("sibenik", None, steps=10, warmup=3)
+                    r2["scaling"] = "strong: the 1920x1080 film dealt over the ranks"
+                else:
+                    r2, e2, _ = run_image(name, None, steps=10, warmup=3)
+                del e2
+                r2.pop("trace_ms", None), r2.pop("clocks", None), r2.pop("wall_s", None)
+                if world > 1:
+                    r2.setdefault("scaling", "strong")
+                extra[name] = r2
+            except Exception as ex:  # noqa: BLE001
+                extra[name] = {"error": f"{type(ex).__name__}: {ex}"}
+                if world > 1:
+                    raise  # a rank that left a collective sequence cannot rejoin it
+
+    if rank == 0:
+        if domain:
+            sched_desc = hres["schedule"]
+            wl = dict(wl, name=hres["workload"])
         else:
             sched_desc = "ImageScheduler" + (f", {world} ranks, row tiles of {a.tile_rows} dealt round-robin, " + ("rows stored into rank 0's framebuffer over NVLink (CUDA IPC), no collective" if p2p else "NCCL reduce to rank 0") if world > 1 else "")
         out = {
-            "metric": "Mrays/s (primary+shadow+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps,
+            "metric": "Mrays/s (primary+shadow+secondary)", "value": hres["Mrays_per_s"], "unit": "Mrays/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": wl["name"] + (f"; weak scaling: film {W}x{H} = {world} x the N=1 film's pixels, same camera and aspect" if weak else ""), "film": [W, H], "depth": d.depth, "samples": d.samples, "rays_per_frame": rays_frame, "bvh": "binned SAH, 8-wide, 128 B nodes",
                 "scheduler": sched_desc,
                 "l2": "256 MiB buffer rewritten between timed frames (L2 flush)", "timing": "CUDA events per frame on the launching stream, max over ranks",
+                "reference_arm": vs_note,
             },
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 496, "d2h_bytes_per_step": W * H * 16,
-                    "call": "gvtb200_render_frame (== api::render) into pinned host memory" if world == 1 else "scheduler step + framebuffer to pinned host memory on rank 0"},
-            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
-            "counters": ctr_all,
+            "e2e": hres["e2e"],
+            "gpu_launches": int(hres.get("launches", a.steps)), "clocks": hres.get("clocks"), "wall_s_timed_region": hres.get("wall_s"),
+            "counters": hres["counters"], "Mrays_per_s_entered_an_instance": hres.get("Mrays_per_s_entered_an_instance"),
         }
+        if "parity" in hres:
+            out["parity"] = hres["parity"]
         if domain:
-            out["config"]["scene_build_s"] = round(build_s[0], 2)
-        if other_sched:
-            out["config"]["other_schedule"] = other_sched
+            out["config"]["gyroid"] = {k: v for k, v in hres.items() if k not in ("counters", "e2e")}
         if roof:
             out["roofline"] = roof
         if cpu:

@@ -332,7 +332,28 @@ def build_domain_rank(desc, rank, world, flags=None, boxes=None, owner=None):
         meshes.append(g.Mesh(m.verts, faces, normals=normals, material=(0, tuple(m.kd or (0.5, 0.5, 0.5)), (0.5, 0.5, 0.5), 1.0)))
     cam = (desc.eye, desc.focus, desc.up, desc.fov, desc.depth, desc.samples, desc.jitter)
     scene = g.StandaloneScene(meshes, inst, lights, cam, (desc.width, desc.height), flags=flags, owner=owner, rank=rank, world=world)
+    scene.recipe = dict(inst=inst, lights=lights, cam=cam, film=(desc.width, desc.height), flags=flags)  # what a second scene over the same meshes needs
     return scene, owner
+
+
+def whole_scene_on_one_rank(scene, descs, owner, rank, mode=1):
+    """A single-rank scene over ALL instances of a domain-partitioned scene: this rank's own meshes plus the other ranks'
+    BLAS imported through their descriptors (mode 1: mapped over NVLink, no copy).  Used as the parity reference of a
+    multi-GPU DomainScheduler frame: one GPU tracing everything, however slowly.  Returns (scene, imported meshes)."""
+    import gravit_b200 as g
+
+    rc = scene.recipe
+    meshes, imported = [], []
+    for k, (mi, *_rest) in enumerate(rc["inst"]):
+        if owner[k] == rank:
+            meshes.append(scene._keep[mi])
+        else:
+            m = g.Mesh.from_desc(descs[k], mode)
+            imported.append(m)
+            meshes.append(m)
+    inst = [(k,) + tuple(x[1:]) for k, x in enumerate(rc["inst"])]
+    full = g.StandaloneScene(meshes, inst, rc["lights"], rc["cam"], rc["film"], flags=rc["flags"])
+    return full, imported
 
 
 def mesh_boxes_allgather(desc, dist, world):
