@@ -516,6 +516,12 @@ def main():
         # (1) the persistent scheduler, every brick served by its owner alone
         base, ctr_all = measure("persistent kernel, brick served by its owner", persist)
         base.update(persist_stats())
+        if world == 1:
+            e.profile_counters(True)
+            persist()
+            e.sync()
+            res["cycle_profile_counted_frame"] = [e.domain_persist_profile()]
+            e.profile_counters(False)
         res["persistent_owner_only"] = base
         headline = base
         descs = None
@@ -525,6 +531,9 @@ def main():
             persist()
             e.sync()
             load = e.domain_persist_stats(8)[2].astype(np.float64)
+            prof = [None] * world
+            dist.all_gather_object(prof, e.domain_persist_profile())
+            res["cycle_profile_owner_only_counted_frame"] = prof
             e.profile_counters(False)
             load = np.array(allsum(load))
             descs = schedulers.exchange_mesh_descs(dist, e._keep, e.recipe["inst"], owner, rank, world, dev)
@@ -536,6 +545,13 @@ def main():
                 barrier()
                 shared, _ = measure(f"persistent kernel, <= {a.replicas} BLAS replica(s) of other ranks' bricks per rank (copied from the owner over NVLink)", persist)
                 shared.update(persist_stats())
+                e.profile_counters(True)
+                persist()
+                e.sync()
+                prof = [None] * world
+                dist.all_gather_object(prof, e.domain_persist_profile())
+                shared["cycle_profile_counted_frame"] = prof
+                e.profile_counters(False)
                 shared.update(servers=[[int(x) for x in row if x >= 0] for row in tab_r], shares=[[round(float(w), 3) for w, x in zip(wr, row) if x >= 0] for wr, row in zip(tab_w, tab_r)],
                               node_visits_per_brick=[int(x) for x in load], replica_setup_s=round(time.perf_counter() - t1, 3))
                 res["persistent_shared_blas"] = shared

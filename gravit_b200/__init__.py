@@ -59,7 +59,7 @@ C_ABI_SYMBOLS = (
     "gvtb200_framebuffer_clamp gvtb200_scene_last_timing gvtb200_domain_set_owner gvtb200_domain_begin_frame "
     "gvtb200_domain_drain_local gvtb200_domain_export gvtb200_domain_import gvtb200_domain_pending "
     "gvtb200_p2p_export gvtb200_p2p_attach gvtb200_p2p_detach gvtb200_image_frame_p2p gvtb200_domain_round_p2p gvtb200_domain_composite_p2p "
-    "gvtb200_domain_frame_persist gvtb200_domain_persist_config gvtb200_domain_persist_stats gvtb200_domain_set_servers "
+    "gvtb200_domain_frame_persist gvtb200_domain_persist_config gvtb200_domain_persist_stats gvtb200_domain_persist_profile gvtb200_domain_set_servers "
     "gvtb200_scene_set_instance_mesh gvtb200_mesh_export gvtb200_mesh_import"
 ).split()
 PEER_DESC_BYTES = 64 * 4 + 8 * 4 + 8 + 8 + 8 + 4 + 4  # sizeof(gvtb200_peer_desc)
@@ -160,6 +160,7 @@ def lib():
         L.gvtb200_domain_persist_config.argtypes = [vp, i32, i32]
         L.gvtb200_domain_persist_stats.argtypes = [vp, vp, vp, vp, i32]
         L.gvtb200_domain_set_servers.argtypes = [vp, vp, vp, i32]
+        L.gvtb200_domain_persist_profile.argtypes = [vp, vp]
         L.gvtb200_scene_set_instance_mesh.argtypes = [vp, i32, vp]
         L.gvtb200_mesh_export.argtypes = [vp, vp]
         L.gvtb200_mesh_import.argtypes = [vp, i32, vp]
@@ -565,6 +566,16 @@ class EngineScene:
         load = np.zeros(n_instances, np.uint64) if n_instances else None
         check(lib().gvtb200_domain_persist_stats(self.h, C.byref(busy), C.byref(rays), _fp(load), n_instances))
         return busy.value, int(rays.value), load
+
+    def domain_persist_profile(self):
+        """Cycle breakdown of a counted persistent frame (gvtb200_domain_persist_profile), as fractions per role."""
+        p = np.zeros(16, np.uint64)
+        check(lib().gvtb200_domain_persist_profile(self.h, _fp(p)))
+        p = p.astype(np.float64)
+        tr, sh = max(1.0, p[1] + p[2] + p[3] + p[4]), max(1.0, p[5] + p[6])
+        return {"tracer_warps": int(p[9]), "shader_warps": int(p[8]), "camera_phase_Mcycles_per_warp": p[0] / max(1.0, p[7]) / 1e6,
+                "tracer": {"waiting_for_rays": p[1] / tr, "traversal": p[2] / tr, "finishing_rays": p[3] / tr, "tickets": p[4] / tr, "Mcycles_per_warp": tr / max(1.0, p[9]) / 1e6},
+                "shader": {"shading": p[5] / sh, "waiting_for_hits": p[6] / sh, "Mcycles_per_warp": sh / max(1.0, p[8]) / 1e6}}
 
     def domain_set_servers(self, ranks=None, weights=None):
         """ranks: (n_instances, <= 4) serving ranks per instance (-1 = unused), weights: the same shape or None."""

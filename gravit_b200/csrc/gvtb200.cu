@@ -1964,6 +1964,13 @@ int gvtb200_domain_frame_persist(gvtb200_scene s, int root, int tile_rows) {
   s->timing_valid = true;
   return GVTB200_OK;
 }
+int gvtb200_domain_persist_profile(gvtb200_scene s, uint64_t prof[16]) {
+  NEED_SCENE();
+  if (!s->p2p.d_mail || !prof) return fail(GVTB200_ERR_INVALID, "no persistent frame has run / NULL argument");
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaMemcpy(prof, s->p2p.d_mail->pc.prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return GVTB200_OK;
+}
 int gvtb200_domain_persist_stats(gvtb200_scene s, double *busy_ms, uint64_t *inbox_rays, uint64_t *instance_load, int n_instances) {
   NEED_SCENE();
   if (!s->p2p.d_mail) return fail(GVTB200_ERR_INVALID, "no persistent frame has run");

@@ -1049,13 +1049,17 @@ struct PersistCtl {
   unsigned hit_head; // hit-queue tickets handed out
   unsigned cam_warps; // warps that have finished phase 1 (camera rays)
   unsigned pad4[30];
+  // counted frames only (k_persist<true>): SM cycles summed over warps -- [0] camera phase, tracer warps: [1] waiting for
+  // rays, [2] in the traversal loop, [3] finishing rays (routing, sends, hit records), [4] drawing / polling tickets;
+  // shader warps: [5] shading, [6] waiting for hits; [7] warps counted
+  unsigned long long prof[16];
   // ---- not reset between frames: values are frame sequence numbers ----
   unsigned cam_done; // every camera ray of this rank's shard has been handed out
   unsigned go, stop, done_seq;
   unsigned long long t_go, t_last; // globaltimer at the start barrier / at the last retire flush (per-rank busy time)
   unsigned arrive[GVT_P2P_MAX];    // start barrier: arrive[r] = frame number, written by rank r
 };
-#define GVT_PERSIST_RESET_BYTES 640 /* tail .. pad4 */
+#define GVT_PERSIST_RESET_BYTES 768 /* tail .. prof */
 struct Mailbox {
   unsigned go, err, cta_done, pad;
   unsigned done[GVT_P2P_MAX];
@@ -1322,6 +1326,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
   unsigned c_cons = 0; // retired since the last flush
   bool dirty = false;  // this lane has stored into another GPU's memory since the last flush
 
+  // A stored ray becomes visible when its slot's `ready` word is written with release semantics (MEMBAR.ALL + store): done
+  // right after the payload stores, the barrier waits for their acknowledgement -- an NVLink round trip for a remote inbox,
+  // during which the other 31 lanes of the warp stand still.  The word is therefore written one or two loop iterations
+  // later, when the payload has long arrived and the barrier finds nothing outstanding.
+  unsigned *pend[2] = { nullptr, nullptr };
+  bool pend_far[2] = { false, false };
+  auto publish = [&]() {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (pend[k]) {
+        if (pend_far[k]) st_release_sys(pend[k], seq); else st_release_gpu(pend[k], seq);
+        pend[k] = nullptr;
+      }
+  };
   // SendRays: into the inbox of `dest` (this rank's own inbox for the rays it makes)
   auto send = [&](const Ray &r, int target, int dest) {
     const RayQueue q = dest == me ? pp.inbox : pp.peer_inbox[dest];
@@ -1335,7 +1353,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
     }
     if (pos < q.cap) {
       queue_store(q, pos, r, target);
-      if (dest == me) st_release_gpu(q.ready + pos, seq); else st_release_sys(q.ready + pos, seq);
+      if (pend[0] && pend[1]) publish();
+      const int k = pend[0] ? 1 : 0;
+      pend[k] = q.ready + pos, pend_far[k] = dest != me;
     } else { // never silently: the frame fails with GVTB200_ERR_CAPACITY; the count stays balanced so that it still ends
       c_qovf++;
       atomicOr(&ctl->err, 2u);
@@ -1357,6 +1377,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
   };
 
   // ---- phase 1: gvtPerspectiveCamera::generateRays + FilterRaysLocally (first routing hop) for this rank's film shard ------
+  long long pc0 = COUNT ? clock64() : 0;
   {
     const bool enter_inside = (fp.flags & FLAG_ENTER_INSIDE) != 0;
     const size_t per_row = (size_t)fp.cam.W * fp.cam.samples * fp.cam.samples;
@@ -1376,6 +1397,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       if (dest != me) c_exp++;
       send(r, next, dest);
     }
+    publish();
     __syncwarp();
     // (a lane's remote stores are ordered by its release stores of the ready words; the warp count below only tells the
     // root that no more camera rays will be handed out by this rank)
@@ -1387,11 +1409,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
     __syncwarp();
   }
 
+  if (COUNT && lane == 0) atomicAdd(&ctl->prof[0], (unsigned long long)(clock64() - pc0)), atomicAdd(&ctl->prof[7], 1ull);
+  long long p_wait = 0, p_trav = 0, p_post = 0, p_poll = 0; // COUNT: cycles of this warp per activity
   const bool shader = pp.shade_sms > 0 ? (int)sm_id() < pp.shade_sms : (blockIdx.x % (unsigned)pp.shade_mod) == 1u;
   unsigned iter = 0;
   unsigned long long t_idle0 = 0;
   const unsigned long long t_start = global_ns();
-  enum { L_IDLE = 0, L_WAIT = 1, L_ACTIVE = 2 };
+  enum { L_IDLE = 0, L_WAIT = 1, L_ACTIVE = 2, L_DEAD = 3 };
   int st = L_IDLE;
   unsigned idx = 0; // the lane's ticket: inbox slot (tracer) or hit-queue slot (shader)
 
@@ -1399,23 +1423,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
     // ================= shader SMs: EmbreeMeshAdapter.cpp:491-601 for every closest hit of this rank ==========================
     for (;;) {
       ++iter;
+      if (COUNT) pc0 = clock64();
+      if (__any_sync(FULL, pend[0] != nullptr)) publish();
       const unsigned idle = __ballot_sync(FULL, st == L_IDLE);
-      if (idle != 0u) {
-        unsigned take = 0, base = 0;
-        if (lane == 0) {
-          const unsigned t = ld_volatile_u32(&ctl->hit_tail), h = ld_volatile_u32(&ctl->hit_head);
-          take = t > h ? min(t - h, (unsigned)__popc(idle)) : 0u;
-          if (take) base = atomicAdd(&ctl->hit_head, take);
-        }
-        take = __shfl_sync(FULL, take, 0), base = __shfl_sync(FULL, base, 0);
-        if (st == L_IDLE) {
-          const unsigned k = (unsigned)__popc(idle & ltmask);
-          if (k < take) idx = base + k, st = L_WAIT;
-        }
+      if (idle != 0u) { // tickets are drawn ahead of the hits, like the tracers' (one per lane at most)
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->hit_head, (unsigned)__popc(idle));
+        base = __shfl_sync(FULL, base, 0);
+        if (st == L_IDLE) idx = base + (unsigned)__popc(idle & ltmask), st = L_WAIT;
       }
       bool got = false;
       if (st == L_WAIT) {
-        if (idx >= pp.hitq.cap) st = L_IDLE; // the producer found the queue full (it has flagged the frame)
+        if (idx >= pp.hitq.cap) st = L_DEAD;
         else got = ld_volatile_u32(pp.hitq.ready + idx) == seq;
       }
       if (__ballot_sync(FULL, got) == 0u) {
@@ -1423,7 +1442,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         unsigned stop = 0;
         if (lane == 0) stop = ld_volatile_u32(&ctl->stop) == seq ? 1u : 0u;
         if (__shfl_sync(FULL, stop, 0)) break;
-        __nanosleep(__any_sync(FULL, st == L_WAIT) ? 32 : 200);
+        __nanosleep(256);
         if ((iter & 255u) == 0u) {
           const unsigned long long now = __shfl_sync(FULL, global_ns(), 0);
           if (t_idle0 == 0) t_idle0 = now;
@@ -1432,6 +1451,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
             break;
           }
         }
+        if (COUNT) p_wait += clock64() - pc0;
         continue;
       }
       t_idle0 = 0;
@@ -1473,7 +1493,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         st = L_IDLE;
       }
       flush();
+      if (COUNT) p_trav += clock64() - pc0;
     }
+    publish();
+    if (COUNT && lane == 0) atomicAdd(&ctl->prof[5], (unsigned long long)p_trav), atomicAdd(&ctl->prof[6], (unsigned long long)p_wait), atomicAdd(&ctl->prof[8], 1ull);
   } else {
     // ================= tracer SMs ========================================================================================
     TravCounters tc;
@@ -1519,27 +1542,24 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
           break;
         }
       }
+      if (COUNT) pc0 = clock64();
+      if (__any_sync(FULL, pend[0] != nullptr)) publish(); // what the previous iteration stored
       // ---- idle lanes draw inbox tickets ---------------------------------------------------------------------------
       const unsigned idle = __ballot_sync(FULL, st == L_IDLE);
       const unsigned tracing = __ballot_sync(FULL, st == L_ACTIVE);
       const bool starved = 32 - __popc(tracing) >= tune.exit_at; // the traversal loop would come straight back
+      // (a ticket is drawn without looking whether its ray exists yet: a lane keeps its ticket until the ray lands, so at most
+      // one ticket per lane is ever ahead of `tail`, arriving rays find a lane waiting, and a refill costs one L2 round trip)
       if (idle != 0u && (tracing == 0u || starved || __popc(idle) >= tune.refill_at)) {
-        unsigned take = 0, base = 0;
-        if (lane == 0) {
-          const unsigned t = ld_volatile_u32(&ctl->tail), h = ld_volatile_u32(&ctl->head);
-          take = t > h ? min(t - h, (unsigned)__popc(idle)) : 0u;
-          if (take) base = atomicAdd(&ctl->head, take);
-        }
-        take = __shfl_sync(FULL, take, 0), base = __shfl_sync(FULL, base, 0);
-        if (st == L_IDLE) {
-          const unsigned k = (unsigned)__popc(idle & ltmask);
-          if (k < take) idx = base + k, st = L_WAIT;
-        }
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->head, (unsigned)__popc(idle));
+        base = __shfl_sync(FULL, base, 0);
+        if (st == L_IDLE) idx = base + (unsigned)__popc(idle & ltmask), st = L_WAIT;
       }
       // ---- lanes that hold a ticket: has the ray landed? ------------------------------------------------------------
       if (st == L_WAIT) {
         if (idx >= pp.inbox.cap) {
-          st = L_IDLE; // the producer found the inbox full (it has flagged the frame and balanced the count)
+          st = L_DEAD; // beyond the inbox: no ray will ever land there (a producer that finds the inbox full flags the frame)
         } else if (ld_volatile_u32(pp.inbox.ready + idx) == seq) {
           const float4 c0 = __ldcg(pp.inbox.c0 + idx), c1 = __ldcg(pp.inbox.c1 + idx);
           type = __ldcg(&pp.inbox.c3[idx].w);
@@ -1555,7 +1575,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         unsigned stop = 0;
         if (lane == 0) stop = ld_volatile_u32(&ctl->stop) == seq ? 1u : 0u;
         if (__shfl_sync(FULL, stop, 0)) break;
-        __nanosleep(__any_sync(FULL, st == L_WAIT) ? 32 : 128);
+        __nanosleep(256);
         if ((iter & 255u) == 0u) { // a peer died, or a bug: never spin for ever
           const unsigned long long now = __shfl_sync(FULL, global_ns(), 0);
           if (t_idle0 == 0) t_idle0 = now;
@@ -1564,13 +1584,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
             break;
           }
         }
+        if (COUNT) p_wait += clock64() - pc0;
         continue;
       }
       t_idle0 = 0;
+      long long pc1 = 0;
+      if (COUNT) pc1 = clock64(), p_poll += pc1 - pc0;
       // ---- traverse in lock step (comes back after PERSIST_TRIPS iterations at the latest: tickets get polled and new
       // arrivals get lanes; whether the inbox holds rays is not known without asking, so it never leaves early for a refill)
       const unsigned resting = __ballot_sync(FULL, st != L_ACTIVE);
       const bool done = warp_traverse<COUNT, PERSIST_TRIPS>(st == L_ACTIVE, resting, false, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
+      long long pc2 = 0;
+      if (COUNT) pc2 = clock64(), p_trav += pc2 - pc1;
       // ---- rays that finished their instance -------------------------------------------------------------------------
       if (st == L_ACTIVE && done) {
         if (COUNT && pp.inst_load) atomicAdd(pp.inst_load + inst, (unsigned long long)(tc.nodes - nodes0));
@@ -1583,7 +1608,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
             if (pos < pp.hitq.cap) {
               queue_store(pp.hitq, pos, r, inst);
               pp.hit[pos] = make_int4(tv.hit.prim, tv.hit.slot, (int)f2u(tv.hit.u), (int)f2u(tv.hit.v));
-              st_release_gpu(pp.hitq.ready + pos, seq);
+              if (pend[0] && pend[1]) publish();
+              const int k = pend[0] ? 1 : 0;
+              pend[k] = pp.hitq.ready + pos, pend_far[k] = false;
             } else {
               c_qovf++;
               atomicOr(&ctl->err, 2u);
@@ -1631,8 +1658,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         }
       }
       if ((iter & 63u) == 0u) flush();
+      if (COUNT) p_post += clock64() - pc2;
     }
+    publish();
     flush();
+    if (COUNT && lane == 0) {
+      atomicAdd(&ctl->prof[1], (unsigned long long)p_wait), atomicAdd(&ctl->prof[2], (unsigned long long)p_trav);
+      atomicAdd(&ctl->prof[3], (unsigned long long)p_post), atomicAdd(&ctl->prof[4], (unsigned long long)p_poll), atomicAdd(&ctl->prof[9], 1ull);
+    }
     if (stack.overflow) c_ovf = 1;
     if (COUNT) {
       count_add(&sd.ctr->nodes_visited, tc.nodes);

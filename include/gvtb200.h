@@ -305,6 +305,10 @@ GVTB200_API int gvtb200_domain_persist_config(gvtb200_scene scene, int grid_ctas
  * inbound queue received and -- for a frame rendered with gvtb200_scene_profile_counters on -- the wide BVH nodes visited per
  * instance on this rank (n_instances entries; input of a replica plan).  Any pointer may be NULL. */
 GVTB200_API int gvtb200_domain_persist_stats(gvtb200_scene scene, double *busy_ms, uint64_t *inbox_rays, uint64_t *instance_load, int n_instances);
+/* after a persistent frame rendered with gvtb200_scene_profile_counters on: SM cycles summed over this rank's warps --
+ * [0] camera phase; tracer warps: [1] waiting for rays, [2] traversal loop, [3] finishing rays (routing, sends, hit records),
+ * [4] drawing / polling tickets; shader warps: [5] shading, [6] waiting for hits; [7] warps, [8] shader warps, [9] tracer warps */
+GVTB200_API int gvtb200_domain_persist_profile(gvtb200_scene scene, uint64_t prof[16]);
 /* Which ranks serve an instance (persistent scheduler only; default: its owner).  ranks[4*i+j], j < 4, are the ranks that
  * hold a BLAS for instance i (-1 = unused), weights[4*i+j] their shares (NULL = equal); a ray bound for the instance picks
  * one by a hash of its direction bits, so the choice is reproducible.  This is how the work of a hot domain is spread:

@@ -1317,6 +1317,24 @@ OR_API int gvto_shade(int mtype, const float *kd, const float *ks, float alpha, 
   out[0] = c.x, out[1] = c.y, out[2] = c.z;
   return ok;
 }
+// Box3D::merge / surfaceArea / wideRangingBoxDir (BBox.cpp:55-63,118-133) alone, for cross-checks against oracle/_ref
+OR_API float gvto_box_merge_area(const float *a6, const float *b6, float *out6, int *widest) {
+  Box a, b;
+  a.lo = v3(a6[0], a6[1], a6[2]), a.hi = v3(a6[3], a6[4], a6[5]);
+  b.lo = v3(b6[0], b6[1], b6[2]), b.hi = v3(b6[3], b6[4], b6[5]);
+  a.merge(b);
+  out6[0] = a.lo.x, out6[1] = a.lo.y, out6[2] = a.lo.z, out6[3] = a.hi.x, out6[4] = a.hi.y, out6[5] = a.hi.z;
+  *widest = a.wideRangingBoxDir();
+  return a.surfaceArea();
+}
+// normalize(normi * v) as the adapter applies it to normals (EmbreeMeshAdapter.cpp:504,518), for the same cross-check
+OR_API void gvto_normal(const float *normi9, const float *v3in, float *out3) {
+  M3 n;
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) n.c[c][r] = normi9[3 * c + r];
+  V3 r = normalize(m3_mul_v3(n, v3(v3in[0], v3in[1], v3in[2])));
+  out3[0] = r.x, out3[1] = r.y, out3[2] = r.z;
+}
 // Morton keys: centroid of the triangle's AABB (0.5f*lo + 0.5f*hi), normalised by the mesh bbox
 // (c - lo) / (hi - lo) (IEEE division; 0 where the extent is 0), scaled by 1024, clamped to [0,1023], truncated.
 OR_API void gvto_morton(void *p, int mesh, uint32_t *codes) {

@@ -102,3 +102,123 @@ def test_oracle_vs_compiled_reference_pieces(built):
                     assert np.array_equal(o1, o2)
                 else:
                     assert np.allclose(o1, o2, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.skipif(po.ref_lib() is None, reason="oracle/_ref not built (no /root/reference here)")
+def test_oracle_routing_vs_reference_packet_box_test(built):
+    """RayPacketIntersection<8>::intersect (actor/RayPacket.h:111-211) of the compiled reference against the oracle's routing of
+    a one-instance scene whose instance box is the same box: same hit lanes, same entry t (update = true: the lane's t
+    becomes the entry distance, :202), for rays from outside, from inside the box, parallel to faces and with zero
+    components."""
+    import ctypes as C
+
+    R = po.ref_lib()
+    R.gvtref_packet_box.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(3)
+    lo, hi = np.array([-0.5, -0.25, 0.1], np.float32), np.array([0.75, 0.5, 0.9], np.float32)
+    verts = np.stack([lo, hi, np.array([lo[0], hi[1], lo[2]], np.float32)])
+    s = po.OracleScene(flags=0)
+    s.add_mesh(verts, np.array([[1, 2, 3]], np.uint32), one_based=True)
+    s.add_instance(0, np.eye(4, dtype=np.float32).T.reshape(16))
+    s.add_point_light((0, 0, 5), (1, 1, 1))
+    s.set_camera((0, 0, 3), (0, 0, 0), (0, 1, 0), 0.8, 1, 1, 0.0)
+    s.set_film(8, 8)
+    s.commit()
+    box6 = np.concatenate([lo, hi]).astype(np.float32)
+    n_checked = n_hit = 0
+    for trial in range(300):
+        rays = np.zeros(8, po.RAY_DTYPE)
+        o = rng.uniform(-2, 2, (8, 3)).astype(np.float32)
+        if trial % 3 == 0:
+            o[:4] = rng.uniform(lo, hi, (4, 3)).astype(np.float32)  # origins inside the box: never entered (Q6)
+        d = rng.normal(size=(8, 3)).astype(np.float32)
+        if trial % 5 == 0:
+            d[:, rng.integers(0, 3)] = 0.0  # axis-parallel: 1/0 = inf in the slab test
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        rays["origin"], rays["direction"] = o, d
+        rays["t_min"], rays["t_max"], rays["t"] = 1e-6, np.float32(3.4028235e38), np.float32(3.4028235e38)
+        if trial % 7 == 0:
+            rays["t_max"][:3] = 3.0  # shadow rays carry t_max = 3 (Q2): boxes further away are not entered
+        hit, t = np.zeros(8, np.int32), np.zeros(8, np.float32)
+        R.gvtref_packet_box(po._fp(rays), 8, po._fp(box6), 1, po._fp(hit), po._fp(t))
+        nxt, to = s.route(rays, -1)
+        assert np.array_equal(hit == 1, nxt == 0) and set(np.unique(hit)) <= {1, -1}, (trial, hit, nxt)  # :194: 1 = hit, -1 = miss
+        assert np.array_equal(t[hit == 1], to[nxt == 0])
+        n_checked += 8
+        n_hit += int((hit == 1).sum())
+    assert 0 < n_hit < n_checked
+
+
+@pytest.mark.skipif(po.ref_lib() is None, reason="oracle/_ref not built (no /root/reference here)")
+def test_oracle_mesh_and_instance_vs_reference(built):
+    """Mesh::addFace's degenerate-face filter, generateNormals and computeBoundingBox (data/primitives/Mesh.cpp:102-154,186-199)
+    and api::addInstance's arithmetic (api/api.cpp:300-321: glm::inverse, transpose(inverse(mat3)), two-corner instance box,
+    centroid) of the compiled reference against the oracle, bit for bit."""
+    import ctypes as C
+
+    R = po.ref_lib()
+    rng = np.random.default_rng(11)
+    for trial in range(20):
+        nv, nt = int(rng.integers(4, 60)), int(rng.integers(1, 120))
+        verts = rng.normal(size=(nv, 3)).astype(np.float32)
+        verts[rng.integers(0, nv)] = verts[0]  # two vertices at one position: faces joining them are dropped
+        tris = rng.integers(1, nv + 1, (nt, 3)).astype(np.uint32)
+        tris[::7, 1] = tris[::7, 0]  # repeated index
+        f_ref, n_ref, b_ref = np.zeros((nt, 3), np.int32), np.zeros((nv, 3), np.float32), np.zeros(6, np.float32)
+        nf = R.gvtref_mesh(po._fp(verts), nv, po._fp(tris), nt, po._fp(f_ref), po._fp(n_ref), po._fp(b_ref))
+        s = po.OracleScene(flags=0)
+        s.add_mesh(verts, tris, one_based=True)
+        f_o, n_o, b_o = s.mesh_get(0, nv)
+        assert nf == len(f_o) <= nt and np.array_equal(f_ref[:nf], f_o)
+        assert np.array_equal(n_ref.view(np.uint32), n_o.view(np.uint32)) or np.array_equal(np.isnan(n_ref), np.isnan(n_o)) and np.array_equal(n_ref[~np.isnan(n_ref)], n_o[~np.isnan(n_o)])
+        assert np.array_equal(b_ref, b_o)
+        # an affine instance matrix: rotation * non-uniform scale + translation (column-major, glm::make_mat4)
+        a = rng.normal(size=(3, 3)).astype(np.float32)
+        q, _ = np.linalg.qr(a.astype(np.float64))
+        m = np.eye(4, dtype=np.float32)
+        m[:3, :3] = (q * rng.uniform(0.3, 2.5, 3)).astype(np.float32)
+        m[:3, 3] = rng.uniform(-3, 3, 3).astype(np.float32)
+        m16 = np.ascontiguousarray(m.T).reshape(16)
+        minv_r, normi_r, box_r, cen_r = np.zeros(16, np.float32), np.zeros(9, np.float32), np.zeros(6, np.float32), np.zeros(3, np.float32)
+        R.gvtref_instance(po._fp(m16), po._fp(b_ref), po._fp(minv_r), po._fp(normi_r), po._fp(box_r), po._fp(cen_r))
+        s.add_instance(0, m16)
+        _, minv_o, normi_o, box_o = s.instance_get(0)
+        assert np.array_equal(minv_r, minv_o) and np.array_equal(normi_r, normi_o) and np.array_equal(box_r, box_o)
+        # normalize(normi * n) as applied to normals (EmbreeMeshAdapter.cpp:504,518)
+        R.gvtref_normal.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        po.lib().gvto_normal.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        for _ in range(10):
+            v = rng.normal(size=3).astype(np.float32)
+            o1, o2 = np.zeros(3, np.float32), np.zeros(3, np.float32)
+            R.gvtref_normal(po._fp(normi_r), po._fp(v), po._fp(o1))
+            po.lib().gvto_normal(po._fp(normi_o), po._fp(v), po._fp(o2))
+            assert np.array_equal(o1, o2)
+
+
+@pytest.mark.skipif(po.ref_lib() is None, reason="oracle/_ref not built (no /root/reference here)")
+def test_oracle_box_ops_vs_reference(built):
+    """Box3D::merge, surfaceArea and wideRangingBoxDir (data/primitives/BBox.cpp:55-63,118-133) -- what the top-level BVH build
+    (data/accel/BVH.cpp:77-216) is made of -- of the compiled reference against the oracle's Box, including point boxes and
+    boxes whose extent overflows."""
+    import ctypes as C
+
+    R = po.ref_lib()
+    for L in (R, po.lib()):
+        fn = L.gvtref_box_merge_area if L is R else L.gvto_box_merge_area
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        fn.restype = C.c_float
+    rng = np.random.default_rng(5)
+    FM = np.float32(3.4028235e38)
+    for trial in range(400):
+        a = np.sort(rng.normal(size=(2, 3)).astype(np.float32), axis=0).reshape(6)
+        b = np.sort((rng.normal(size=(2, 3)) * rng.uniform(0.01, 5)).astype(np.float32), axis=0).reshape(6)
+        if trial % 10 == 0:
+            a = np.array([-FM, -FM, -FM, FM, FM, FM], np.float32)  # the largest box (the two-corner constructor sorts its corners,
+            #                                                        BBox.cpp:41-46, so the empty accumulator cannot be passed in)
+        if trial % 13 == 0:
+            b[3:] = b[:3]  # a degenerate (point) box
+        o1, o2, w1, w2 = np.zeros(6, np.float32), np.zeros(6, np.float32), C.c_int(-1), C.c_int(-2)
+        s1 = R.gvtref_box_merge_area(po._fp(a), po._fp(b), po._fp(o1), C.byref(w1))
+        s2 = po.lib().gvto_box_merge_area(po._fp(a), po._fp(b), po._fp(o2), C.byref(w2))
+        assert np.array_equal(o1, o2) and w1.value == w2.value
+        assert np.float32(s1) == np.float32(s2) or (np.isnan(s1) and np.isnan(s2))

@@ -18,7 +18,8 @@ import gravit_b200 as g  # noqa: E402
 from gravit_b200 import schedulers  # noqa: E402
 from scenes import library  # noqa: E402
 
-names = sys.argv[1:] or ["sibenik", "bunny", "grid"]
+names = [x for x in sys.argv[1:] if not x.startswith("--")] or ["sibenik", "bunny", "grid"]
+film = next((tuple(int(v) for v in x[7:].split("x")) for x in sys.argv[1:] if x.startswith("--film=")), None)  # e.g. --film=480x270: the frame's latency chain
 g.init(0)
 dev = torch.device("cuda", 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -26,12 +27,12 @@ for name in names:
     t0 = time.perf_counter()
     if name.startswith("gyroid"):
         res = int(name.split(":")[1]) if ":" in name else library.GYROID_RES_100M
-        d = library.gyroid_scene(res, 2, 3840, 2160, brick_fn=lambda *a: library.gyroid_brick_torch(*a, device=dev))
+        d = library.gyroid_scene(res, 2, *(film or (3840, 2160)), brick_fn=lambda *a: library.gyroid_brick_torch(*a, device=dev))
         e, _ = schedulers.build_domain_rank(d, 0, 1)
         for m in d.meshes:
             m.verts = m.tris = None
     else:
-        d = bench.WORKLOADS[name]["make"]()
+        d = bench.WORKLOADS[name]["make"](*film) if film else bench.WORKLOADS[name]["make"]()
         s = library.apply(d, g.GvtScene(flags=d.flags))
         e = s.engine()
     build_s = time.perf_counter() - t0
@@ -58,5 +59,10 @@ for name in names:
             out["rays"] = c["camera_rays"] + c["shadow_generated"] + c["secondary_generated"]
             fbs[mode] = e.fb_read(d.width, d.height)
     out["max_abs_diff"] = float(np.abs(fbs["waves"] - fbs["persist"]).max())
+    e.profile_counters(True)
+    e.domain_frame_persist(0, 8)
+    e.sync()
+    out["persist_profile"] = e.domain_persist_profile()
+    e.profile_counters(False)
     print(json.dumps(out), flush=True)
     del e
