@@ -269,7 +269,7 @@ int scan_inplace(unsigned *d, size_t n, std::vector<unsigned *> &levels, size_t 
   return 0;
 }
 
-TraceTune g_tune = { 16, 20, 2, 2 };
+TraceTune g_tune = { 16, 20, 2, 2, 0 };
 
 int trace_grid(int dev, bool count) {
   DevState &D = g_dev[dev];
@@ -488,6 +488,7 @@ int gvtb200_init(int device) {
     if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &d) >= 3 && gvtb200_set_tuning(a, b, c, d)) return GVTB200_ERR_INVALID;
   }
   if (const char *e = getenv("GVTB200_PEER_TIMEOUT_MS")) gvtb200_set_peer_timeout_ms(atoi(e));
+  if (const char *e = getenv("GVTB200_TAIL_PREFETCH")) gvtb200_set_tail_prefetch(atoi(e));
   CU(cudaFree(0));
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { // keep up to 8 GiB of freed build scratch in the pool
@@ -502,6 +503,11 @@ int gvtb200_init(int device) {
 
 const char *gvtb200_last_error(void) { return t_err.c_str(); }
 int gvtb200_current_device(void) { return cur_device(); }
+int gvtb200_set_tail_prefetch(int max_lanes) {
+  if (max_lanes < 0 || max_lanes > 32) return fail(GVTB200_ERR_INVALID, "lanes %d outside 0..32", max_lanes);
+  g_tune.prefetch_below = max_lanes;
+  return GVTB200_OK;
+}
 int gvtb200_set_peer_timeout_ms(int ms) {
   if (ms < 1) return fail(GVTB200_ERR_INVALID, "timeout %d ms", ms);
   g_peer_timeout_ns = (unsigned long long)ms * 1000000ull;

@@ -591,6 +591,7 @@ struct TraceTune {
   int postpone_num; // postpone triangle tests while lanes_with_triangles * 8 < traversing_lanes * postpone_num
   int node_burst;   // node visits a lane may make per lock-step iteration before the warp votes again (it stops at the
                     // first triangle group)
+  int prefetch_below; // lanes: a warp with at most this many traversing lanes prefetches the siblings it pushes (0 = never)
 };
 
 struct CameraGen { // in-kernel camera-ray source (replaces reading a queue of camera rays back from HBM)
@@ -658,6 +659,7 @@ __device__ __forceinline__ bool warp_traverse(bool active, unsigned resting, boo
     // (the persistent kernel always advances one step per call: its callers' lanes can rest in states a refill cannot end)
     if ((BUDGET == 0 || trips > 0) && waiting >= (unsigned)tune.exit_at && ((~tm & ~resting) != 0u || more_input)) break;
     if (BUDGET > 0 && ++trips > BUDGET) break;
+    const bool pf = __popc(tm) <= tune.prefetch_below;
     if (trav) {
 #pragma unroll 1
       for (int k = 0; k < tune.node_burst; ++k) {
@@ -669,7 +671,7 @@ __device__ __forceinline__ bool warp_traverse(bool active, unsigned resting, boo
           }
           if (!trav_has_nodes(tv)) break; // popped a postponed triangle group
         }
-        node_step<COUNT, true>(nodes, rl, GVT_RAY_EPSILON, tv, stack, &tc, s_lut);
+        node_step<COUNT, true>(nodes, rl, GVT_RAY_EPSILON, tv, stack, &tc, s_lut, pf);
         if (trav_has_tris(tv)) break;
       }
     }

@@ -188,14 +188,30 @@ GVT_HD bool trav_has_tris(const Trav &tv) { return (tv.tg.y & 0x00FFFFFFu) != 0u
 
 // Visits the nearest pending child of the node group.  Precondition: trav_has_nodes(tv).  lut: optional table
 // lut[octinv * 256 + hits8] = best_slot(hits8, octinv) (the trace kernel keeps it in shared memory).
+// prefetch = the warp is nearly empty (the tail of a frame: what is left is a few long rays whose time is a chain of dependent
+// node fetches from HBM): the siblings that go onto the stack are requested into L2 now, so that the pop that visits them
+// later waits for L2 instead of HBM.  Not worth its traffic while the warp is full and the kernel is bandwidth bound.
 template <bool COUNT, bool LUT, class Stack>
 GVT_HD void node_step(const float4 *nodes, const RayLocal &rl, float tnear, Trav &tv, Stack &stack, TravCounters *ctr,
-                      const unsigned char *lut = nullptr) {
+                      const unsigned char *lut = nullptr, bool prefetch = false) {
   const uint32_t hits8 = tv.ng.y >> 24;
   const uint32_t imask = tv.ng.y & 0xFFu;
   const uint32_t s = LUT ? (uint32_t)lut[rl.octinv * 256u + hits8] : best_slot(hits8, rl.octinv);
   tv.ng.y &= ~(0x01000000u << s);
-  if (trav_has_nodes(tv)) stack.push(tv.sp, tv.ng);
+  if (trav_has_nodes(tv)) {
+    stack.push(tv.sp, tv.ng);
+#if defined(__CUDA_ARCH__)
+    if (prefetch) {
+      uint32_t rest = tv.ng.y >> 24;
+      while (rest) {
+        const uint32_t b = (uint32_t)__ffs((int)rest) - 1u;
+        rest &= rest - 1u;
+        const float4 *pn = nodes + GVT_NODE_WORDS * (size_t)(tv.ng.x + (uint32_t)popc32(imask & ((1u << b) - 1u)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pn));
+      }
+    }
+#endif
+  }
   const uint32_t ni = tv.ng.x + (uint32_t)popc32(imask & ((1u << s) - 1u));
   const float4 *np = nodes + GVT_NODE_WORDS * (size_t)ni;
   // direction signs pick the near / far plane block of every axis

@@ -95,6 +95,10 @@ GVTB200_API int gvtb200_device_info(int *sm_count, size_t *hbm_bytes, int *cc_ma
  * postpone_num/8 of the traversing lanes hold a triangle, let a lane visit up to node_burst nodes between two warp votes.
  * Replaces the TBB grain size of EmbreeMeshAdapter.cpp:648. */
 GVTB200_API int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num, int node_burst);
+/* tail prefetch: a warp of the trace kernels with at most max_lanes traversing rays (the end of a frame: a few long rays,
+ * each a chain of dependent node fetches) requests the sibling nodes it pushes onto its stack into L2 (0 = off; also
+ * GVTB200_TAIL_PREFETCH).  Results do not depend on it. */
+GVTB200_API int gvtb200_set_tail_prefetch(int max_lanes);
 /* how long a kernel of the NVLink peer path waits for another GPU before it gives up and flags the frame (default 4000 ms;
  * also GVTB200_PEER_TIMEOUT_MS).  The reference blocks in MPI_Wait for ever (DomainTracer.h:480-486). */
 GVTB200_API int gvtb200_set_peer_timeout_ms(int ms);

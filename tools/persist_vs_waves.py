@@ -38,11 +38,12 @@ for name in names:
     build_s = time.perf_counter() - t0
     out = {"workload": name, "film": [d.width, d.height], "build_s": round(build_s, 2)}
     fbs = {}
-    for mode in ("waves", "persist"):
-        for shade_at in ((8,) if mode == "waves" else (8, 14, 24)):
-            if mode == "persist":
+    for mode in ("waves", "persist", "waves_pf8", "persist_pf4", "persist_pf8", "persist_pf16"):
+        g.check(g.lib().gvtb200_set_tail_prefetch(int(mode.split("_pf")[1]) if "_pf" in mode else 0))
+        for shade_at in ((8,) if mode.startswith("waves") else ((8, 14) if mode == "persist" else (8,))):
+            if mode.startswith("persist"):
                 e.domain_persist_config(0, shade_at)
-            frame = (lambda: e.render_async(d.height)) if mode == "waves" else (lambda: e.domain_frame_persist(0, 8))
+            frame = (lambda: e.render_async(d.height)) if mode.startswith("waves") else (lambda: e.domain_frame_persist(0, 8))
             for _ in range(3):
                 frame()
             e.sync()
@@ -54,11 +55,12 @@ for name in names:
                 frame()
                 e.sync()
                 ms.append(e.last_timing()[0])
-            key = mode if mode == "waves" else f"persist_shadesms{shade_at}"
+            key = mode if mode.startswith("waves") else f"{mode}_shadesms{shade_at}"
             out[key + "_ms"] = round(statistics.median(ms), 4)
             out["rays"] = c["camera_rays"] + c["shadow_generated"] + c["secondary_generated"]
-            fbs[mode] = e.fb_read(d.width, d.height)
+            fbs[mode.split("_")[0]] = e.fb_read(d.width, d.height)
     out["max_abs_diff"] = float(np.abs(fbs["waves"] - fbs["persist"]).max())
+    g.check(g.lib().gvtb200_set_tail_prefetch(0))
     e.profile_counters(True)
     e.domain_frame_persist(0, 8)
     e.sync()
