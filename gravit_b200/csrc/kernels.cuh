@@ -1222,6 +1222,25 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// What a `ready` word guards is read with volatile asm loads as well: a plain __ldcg may be hoisted by the compiler above the
+// test of the flag value (it was, once the flag was polled ahead of the traversal burst: the payload was then fetched
+// together with the flag and a slot that had just been reserved was read before it was written).  asm volatile keeps the
+// loads behind the branch, LDG.STRONG reads L2.
+__device__ __forceinline__ float4 ld_strong_f4(const float4 *p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int4 ld_strong_i4(const int4 *p) {
+  int4 v;
+  asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_strong_i32(const int *p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_release_sys_add(unsigned *p, unsigned v) { asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -1332,15 +1351,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
   // right after the payload stores, the barrier waits for their acknowledgement -- an NVLink round trip for a remote inbox,
   // during which the other 31 lanes of the warp stand still.  The word is therefore written one or two loop iterations
   // later, when the payload has long arrived and the barrier finds nothing outstanding.
-  unsigned *pend[2] = { nullptr, nullptr };
-  bool pend_far[2] = { false, false };
+  unsigned *pend0 = nullptr, *pend1 = nullptr; // (scalars: a dynamically indexed array would live in local memory)
+  bool far0 = false, far1 = false;
   auto publish = [&]() {
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-      if (pend[k]) {
-        if (pend_far[k]) st_release_sys(pend[k], seq); else st_release_gpu(pend[k], seq);
-        pend[k] = nullptr;
-      }
+    if (pend0) {
+      if (far0) st_release_sys(pend0, seq); else st_release_gpu(pend0, seq);
+      pend0 = nullptr;
+    }
+    if (pend1) {
+      if (far1) st_release_sys(pend1, seq); else st_release_gpu(pend1, seq);
+      pend1 = nullptr;
+    }
+  };
+  auto pend_add = [&](unsigned *flag, bool far) {
+    if (pend0 && pend1) publish();
+    if (!pend0) pend0 = flag, far0 = far; else pend1 = flag, far1 = far;
   };
   // SendRays: into the inbox of `dest` (this rank's own inbox for the rays it makes)
   auto send = [&](const Ray &r, int target, int dest) {
@@ -1355,9 +1380,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
     }
     if (pos < q.cap) {
       queue_store(q, pos, r, target);
-      if (pend[0] && pend[1]) publish();
-      const int k = pend[0] ? 1 : 0;
-      pend[k] = q.ready + pos, pend_far[k] = dest != me;
+      pend_add(q.ready + pos, dest != me);
     } else { // never silently: the frame fails with GVTB200_ERR_CAPACITY; the count stays balanced so that it still ends
       c_qovf++;
       atomicOr(&ctl->err, 2u);
@@ -1379,34 +1402,93 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
   };
 
   // ---- phase 1: gvtPerspectiveCamera::generateRays + FilterRaysLocally (first routing hop) for this rank's film shard ------
+  // Two passes over chunks of CAM_CHUNK rays per lane: (A) generate, route, pick the serving rank, count per destination
+  // inside the warp; ONE slot reservation per warp and destination (same-address atomics on an inbox's `tail` serialise at
+  // about a nanosecond each -- over NVLink too -- and one per ray group made this phase 0.3 ms long whatever the number of
+  // GPUs); (B) regenerate the ray (cheaper than keeping it) and store it into its slot.
   long long pc0 = COUNT ? clock64() : 0;
   {
+    constexpr int CAM_CHUNK = 8;
+    __shared__ unsigned s_cnt[TRACE_THREADS / 32][GVT_P2P_MAX], s_base[TRACE_THREADS / 32][GVT_P2P_MAX];
+    const unsigned warp = threadIdx.x >> 5;
     const bool enter_inside = (fp.flags & FLAG_ENTER_INSIDE) != 0;
     const size_t per_row = (size_t)fp.cam.W * fp.cam.samples * fp.cam.samples;
-    const size_t stride = (size_t)gridDim.x * TRACE_THREADS - 32; // every thread but the control warp's
-    for (size_t i = blockIdx.x * (size_t)TRACE_THREADS + threadIdx.x - 32; i < pp.cam_count; i += stride) {
+    const size_t n_warps = (size_t)gridDim.x * (TRACE_THREADS / 32) - 1, wg = (size_t)blockIdx.x * (TRACE_THREADS / 32) + warp - 1; // workers only
+    auto cam_index = [&](size_t i) -> size_t { // shard ray i -> global camera-ray index (RowTiles arithmetic)
       const size_t lr = i / per_row, within = i - lr * per_row;
-      const size_t b = lr / pp.tiles.tile_rows, k = lr - b * pp.tiles.tile_rows;
-      const size_t row = (size_t)pp.tiles.row0 + (b * pp.tiles.stride + pp.tiles.index) * pp.tiles.tile_rows + k;
-      Ray r;
-      camera_ray(fp.cam, row * per_row + within, r);
-      float t;
-      const int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, -1, enter_inside, t);
-      if (next < 0) continue; // background
-      c_routed++;
-      r.o = xadd(r.o, xmul(r.d, xmul(t, 0.95f))); // TracerBase.h:394
-      const int dest = multi ? pick_server(pp.servers, next, sd.inst[next].owner, r.d) : me;
-      if (dest != me) c_exp++;
-      send(r, next, dest);
+      const size_t bb = lr / pp.tiles.tile_rows, k = lr - bb * pp.tiles.tile_rows;
+      return ((size_t)pp.tiles.row0 + (bb * pp.tiles.stride + pp.tiles.index) * pp.tiles.tile_rows + k) * per_row + within;
+    };
+    // per-lane notes of a chunk live in the traversal stack's shared memory (unused until phase 2): entry j = {first
+    // instance, destination | position in the warp's reservation << 8}, entries CAM_CHUNK.. = the routing distances
+    uint2 *note = s_stack + threadIdx.x;
+    float *note_t = reinterpret_cast<float *>(s_stack + CAM_CHUNK * TRACE_THREADS);
+    static_assert(CAM_CHUNK + CAM_CHUNK / 2 <= TRACE_SM_STACK, "camera notes must fit the shared stack");
+    for (size_t it0 = 0; (it0 * n_warps) * 32 < pp.cam_count; it0 += CAM_CHUNK) {
+      if (lane < GVT_P2P_MAX) s_cnt[warp][lane] = 0u;
+      __syncwarp();
+#pragma unroll 1
+      for (int j = 0; j < CAM_CHUNK; ++j) {
+        const size_t i = ((it0 + j) * n_warps + wg) * 32 + lane;
+        uint2 nt = make_uint2(0xFFFFFFFFu, 0u); // background / beyond the shard
+        float t = 0.f;
+        if (i < pp.cam_count) {
+          Ray r;
+          camera_ray(fp.cam, cam_index(i), r);
+          const int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, -1, enter_inside, t);
+          if (next >= 0) {
+            c_routed++;
+            const int dest = multi ? pick_server(pp.servers, next, sd.inst[next].owner, r.d) : me;
+            if (dest != me) c_exp++;
+            nt = make_uint2((unsigned)next, (unsigned)dest | (atomicAdd(&s_cnt[warp][dest], 1u) << 8));
+          }
+        }
+        note[j * TRACE_THREADS] = nt;
+        note_t[j * TRACE_THREADS + threadIdx.x] = t;
+      }
+      __syncwarp();
+      if ((int)lane < pp.world) {
+        const unsigned n = s_cnt[warp][lane];
+        if (n) s_base[warp][lane] = (int)lane == me ? atomicAdd(&ctl->tail, n) : atomicAdd_system(&pp.mail.m[lane]->pc.tail, n);
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int j = 0; j < CAM_CHUNK; ++j) {
+        uint2 nt = note[j * TRACE_THREADS];
+        if (nt.x == 0xFFFFFFFFu) continue;
+        const size_t i = ((it0 + j) * n_warps + wg) * 32 + lane;
+        Ray r;
+        camera_ray(fp.cam, cam_index(i), r);
+        r.o = xadd(r.o, xmul(r.d, xmul(note_t[j * TRACE_THREADS + threadIdx.x], 0.95f))); // TracerBase.h:394
+        const int dest = (int)(nt.y & 0xFFu);
+        const RayQueue q = dest == me ? pp.inbox : pp.peer_inbox[dest];
+        const unsigned pos = s_base[warp][dest] + (nt.y >> 8);
+        if (pos < q.cap) {
+          queue_store(q, pos, r, (int)nt.x);
+          if (dest != me) dirty = true;
+        } else { // the frame fails with GVTB200_ERR_CAPACITY; the count stays balanced so that it still ends
+          c_qovf++;
+          atomicOr(&ctl->err, 2u);
+          if (dest == me) atomicAdd(&ctl->consumed, 1u); else atomicAdd_system(&pp.mail.m[dest]->pc.consumed, 1u);
+          note[j * TRACE_THREADS] = make_uint2(0xFFFFFFFFu, 0u);
+        }
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int j = 0; j < CAM_CHUNK; ++j) { // the first release waits for this lane's payload stores, the others find nothing outstanding
+        const uint2 nt = note[j * TRACE_THREADS];
+        if (nt.x == 0xFFFFFFFFu) continue;
+        const int dest = (int)(nt.y & 0xFFu);
+        const RayQueue q = dest == me ? pp.inbox : pp.peer_inbox[dest];
+        st_release_sys(q.ready + s_base[warp][dest] + (nt.y >> 8), seq);
+      }
+      __syncwarp();
     }
-    publish();
     __syncwarp();
-    // (a lane's remote stores are ordered by its release stores of the ready words; the warp count below only tells the
-    // root that no more camera rays will be handed out by this rank)
+    // (the warp count below only tells the root that no more camera rays will be handed out by this rank)
     if (lane == 0) {
       __threadfence();
-      const unsigned total = gridDim.x * (TRACE_THREADS / 32) - 1u; // every warp but the control warp
-      if (atomicAdd(&ctl->cam_warps, 1u) == total - 1u) st_release_sys(&ctl->cam_done, seq);
+      if (atomicAdd(&ctl->cam_warps, 1u) == (unsigned)n_warps - 1u) st_release_sys(&ctl->cam_done, seq);
     }
     __syncwarp();
   }
@@ -1426,7 +1508,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
     for (;;) {
       ++iter;
       if (COUNT) pc0 = clock64();
-      if (__any_sync(FULL, pend[0] != nullptr)) publish();
       const unsigned idle = __ballot_sync(FULL, st == L_IDLE);
       if (idle != 0u) { // tickets are drawn ahead of the hits, like the tracers' (one per lane at most)
         unsigned base = 0;
@@ -1460,14 +1541,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       if (got) {
         Ray r;
         {
-          const float4 a = __ldcg(pp.hitq.c0 + idx), b = __ldcg(pp.hitq.c1 + idx), c = __ldcg(pp.hitq.c2 + idx);
-          const int4 e = __ldcg(pp.hitq.c3 + idx);
+          const float4 a = ld_strong_f4(pp.hitq.c0 + idx), b = ld_strong_f4(pp.hitq.c1 + idx), c = ld_strong_f4(pp.hitq.c2 + idx);
+          const int4 e = ld_strong_i4(pp.hitq.c3 + idx);
           r.o = v3(a.x, a.y, a.z), r.t_min = a.w, r.d = v3(b.x, b.y, b.z), r.t_max = b.w;
           r.color = v3(c.x, c.y, c.z), r.t = c.w;
           r.id = e.x, r.depth = e.y, r.w = u2f((uint32_t)e.z), r.type = e.w;
         }
-        const int inst = __ldcg(pp.hitq.inst + idx);
-        const int4 hc = __ldcg(pp.hit + idx);
+        const int inst = ld_strong_i32(pp.hitq.inst + idx);
+        const int4 hc = ld_strong_i4(pp.hit + idx);
         Hit h;
         h.prim = hc.x, h.slot = hc.y, h.t = r.t, h.u = u2f((uint32_t)hc.z), h.v = u2f((uint32_t)hc.w);
         const Instance in = sd.inst[inst];
@@ -1494,6 +1575,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         c_cons++;
         st = L_IDLE;
       }
+      publish();
       flush();
       if (COUNT) p_trav += clock64() - pc0;
     }
@@ -1529,8 +1611,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       if (COUNT) nodes0 = tc.nodes;
     };
     auto reload = [&](Ray &r) { // the columns that are not kept in registers stay in the lane's inbox slot
-      const float4 c2 = __ldcg(pp.inbox.c2 + idx);
-      const int4 c3 = __ldcg(pp.inbox.c3 + idx);
+      const float4 c2 = ld_strong_f4(pp.inbox.c2 + idx);
+      const int4 c3 = ld_strong_i4(pp.inbox.c3 + idx);
       r.color = v3(c2.x, c2.y, c2.z), r.t = c2.w;
       r.id = c3.x, r.depth = c3.y, r.w = u2f((uint32_t)c3.z), r.type = c3.w;
       r.o = o, r.t_min = t_min, r.d = d, r.t_max = t_max;
@@ -1545,7 +1627,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         }
       }
       if (COUNT) pc0 = clock64();
-      if (__any_sync(FULL, pend[0] != nullptr)) publish(); // what the previous iteration stored
+      if (__any_sync(FULL, pend0 != nullptr)) publish(); // what the previous iteration stored: its payload has arrived by now
       // ---- idle lanes draw inbox tickets ---------------------------------------------------------------------------
       const unsigned idle = __ballot_sync(FULL, st == L_IDLE);
       const unsigned tracing = __ballot_sync(FULL, st == L_ACTIVE);
@@ -1558,19 +1640,31 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         base = __shfl_sync(FULL, base, 0);
         if (st == L_IDLE) idx = base + (unsigned)__popc(idle & ltmask), st = L_WAIT;
       }
-      // ---- lanes that hold a ticket: has the ray landed? ------------------------------------------------------------
+      // ---- lanes that hold a ticket: has the ray landed?  While other lanes of the warp trace, the question is asked now
+      // and the answer is looked at after the traversal burst (an L2 round trip the whole warp would otherwise wait for)
+      unsigned landed = 0u;
       if (st == L_WAIT) {
-        if (idx >= pp.inbox.cap) {
-          st = L_DEAD; // beyond the inbox: no ray will ever land there (a producer that finds the inbox full flags the frame)
-        } else if (ld_volatile_u32(pp.inbox.ready + idx) == seq) {
-          const float4 c0 = __ldcg(pp.inbox.c0 + idx), c1 = __ldcg(pp.inbox.c1 + idx);
-          type = __ldcg(&pp.inbox.c3[idx].w);
-          inst = __ldcg(pp.inbox.inst + idx);
+        if (idx >= pp.inbox.cap) st = L_DEAD; // beyond the inbox: no ray will ever land there (a producer that finds the inbox full flags the frame)
+        else landed = ld_volatile_u32(pp.inbox.ready + idx);
+      }
+      auto start_landed = [&]() {
+        if (st == L_WAIT && landed == seq) {
+          const float4 c0 = ld_strong_f4(pp.inbox.c0 + idx), c1 = ld_strong_f4(pp.inbox.c1 + idx);
+          type = ld_strong_i32(&pp.inbox.c3[idx].w);
+          inst = ld_strong_i32(pp.inbox.inst + idx);
+#ifdef GVT_DEBUG_PERSIST
+          if ((unsigned)inst >= (unsigned)sd.tlas.n_inst) {
+            printf("BAD inst %d at idx %u type %d landed %u seq %u tail %u head %u o %f %f %f blk %d thr %d iter %u\n", inst, idx, type, landed, seq, ld_volatile_u32(&ctl->tail), ld_volatile_u32(&ctl->head), c0.x, c0.y, c0.z, blockIdx.x, threadIdx.x, iter);
+            st = L_DEAD;
+            return;
+          }
+#endif
           o = v3(c0.x, c0.y, c0.z), t_min = c0.w, d = v3(c1.x, c1.y, c1.z), t_max = c1.w;
           any = (type == RAY_SHADOW), first = true, st = L_ACTIVE;
           begin_instance();
         }
-      }
+      };
+      if (tracing == 0u) start_landed(); // nothing to overlap with
       // ---- nothing to trace in this warp ----------------------------------------------------------------------------------
       if (__ballot_sync(FULL, st == L_ACTIVE) == 0u) {
         flush();
@@ -1610,9 +1704,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
             if (pos < pp.hitq.cap) {
               queue_store(pp.hitq, pos, r, inst);
               pp.hit[pos] = make_int4(tv.hit.prim, tv.hit.slot, (int)f2u(tv.hit.u), (int)f2u(tv.hit.v));
-              if (pend[0] && pend[1]) publish();
-              const int k = pend[0] ? 1 : 0;
-              pend[k] = pp.hitq.ready + pos, pend_far[k] = false;
+              pend_add(pp.hitq.ready + pos, false);
             } else {
               c_qovf++;
               atomicOr(&ctl->err, 2u);
@@ -1659,6 +1751,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
           }
         }
       }
+      start_landed();
       if ((iter & 63u) == 0u) flush();
       if (COUNT) p_post += clock64() - pc2;
     }
