@@ -50,7 +50,7 @@ ADAPTER_B200 = 8  # gvt::render::adapter::B200 (gravit_b200/host/api.h)
 
 # every symbol include/gvtb200.h declares (tests check that the library exports all of them)
 C_ABI_SYMBOLS = (
-    "gvtb200_init gvtb200_last_error gvtb200_current_device gvtb200_device_info gvtb200_set_tuning gvtb200_set_tail_prefetch gvtb200_set_peer_timeout_ms gvtb200_mesh_create gvtb200_mesh_destroy gvtb200_mesh_morton "
+    "gvtb200_init gvtb200_last_error gvtb200_current_device gvtb200_device_info gvtb200_set_tuning gvtb200_set_tail_split gvtb200_set_tail_prefetch gvtb200_set_peer_timeout_ms gvtb200_mesh_create gvtb200_mesh_destroy gvtb200_mesh_morton "
     "gvtb200_mesh_stats gvtb200_trace gvtb200_intersect gvtb200_occluded gvtb200_scene_create gvtb200_scene_destroy "
     "gvtb200_scene_add_instance gvtb200_scene_set_lights gvtb200_scene_set_camera gvtb200_scene_set_film "
     "gvtb200_scene_set_flags gvtb200_scene_set_queue_limit gvtb200_scene_commit gvtb200_scene_tlas_order gvtb200_camera_rays gvtb200_route "
@@ -157,6 +157,7 @@ def lib():
         L.gvtb200_domain_composite_p2p.argtypes = [vp, i32]
         L.gvtb200_set_peer_timeout_ms.argtypes = [i32]
         L.gvtb200_set_tail_prefetch.argtypes = [i32]
+        L.gvtb200_set_tail_split.argtypes = [i32]
         L.gvtb200_domain_frame_persist.argtypes = [vp, i32, i32]
         L.gvtb200_domain_persist_config.argtypes = [vp, i32, i32]
         L.gvtb200_domain_persist_stats.argtypes = [vp, vp, vp, vp, i32]

@@ -269,7 +269,7 @@ int scan_inplace(unsigned *d, size_t n, std::vector<unsigned *> &levels, size_t 
   return 0;
 }
 
-TraceTune g_tune = { 16, 20, 2, 2, 0 };
+TraceTune g_tune = { 16, 20, 2, 2, 0, 16 };
 
 int trace_grid(int dev, bool count) {
   DevState &D = g_dev[dev];
@@ -489,6 +489,7 @@ int gvtb200_init(int device) {
   }
   if (const char *e = getenv("GVTB200_PEER_TIMEOUT_MS")) gvtb200_set_peer_timeout_ms(atoi(e));
   if (const char *e = getenv("GVTB200_TAIL_PREFETCH")) gvtb200_set_tail_prefetch(atoi(e));
+  if (const char *e = getenv("GVTB200_TAIL_SPLIT")) gvtb200_set_tail_split(atoi(e));
   CU(cudaFree(0));
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { // keep up to 8 GiB of freed build scratch in the pool
@@ -503,6 +504,11 @@ int gvtb200_init(int device) {
 
 const char *gvtb200_last_error(void) { return t_err.c_str(); }
 int gvtb200_current_device(void) { return cur_device(); }
+int gvtb200_set_tail_split(int max_lanes) {
+  if (max_lanes < 0 || max_lanes > 32) return fail(GVTB200_ERR_INVALID, "lanes %d outside 0..32", max_lanes);
+  g_tune.split_below = max_lanes;
+  return GVTB200_OK;
+}
 int gvtb200_set_tail_prefetch(int max_lanes) {
   if (max_lanes < 0 || max_lanes > 32) return fail(GVTB200_ERR_INVALID, "lanes %d outside 0..32", max_lanes);
   g_tune.prefetch_below = max_lanes;

@@ -592,6 +592,8 @@ struct TraceTune {
   int node_burst;   // node visits a lane may make per lock-step iteration before the warp votes again (it stops at the
                     // first triangle group)
   int prefetch_below; // lanes: a warp with at most this many traversing lanes prefetches the siblings it pushes (0 = never)
+  int split_below;    // persistent kernel: a warp with at most this many traversing lanes shares out the stacks of its rays
+                      // among its free lanes (0 = never)
 };
 
 struct CameraGen { // in-kernel camera-ray source (replaces reading a queue of camera rays back from HBM)
@@ -635,6 +637,10 @@ struct SmemStack {
   __device__ __forceinline__ uint2 pop(int &sp) {
     --sp;
     return sp < TRACE_SM_STACK ? s[sp * TRACE_THREADS] : l[sp - TRACE_SM_STACK];
+  }
+  __device__ __forceinline__ uint2 get(int k) const { return k < TRACE_SM_STACK ? s[k * TRACE_THREADS] : l[k - TRACE_SM_STACK]; }
+  __device__ __forceinline__ void set(int k, uint2 v) {
+    if (k < TRACE_SM_STACK) s[k * TRACE_THREADS] = v; else l[k - TRACE_SM_STACK] = v;
   }
 };
 
@@ -1408,7 +1414,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
   // GPUs); (B) regenerate the ray (cheaper than keeping it) and store it into its slot.
   long long pc0 = COUNT ? clock64() : 0;
   {
-    constexpr int CAM_CHUNK = 8;
+    constexpr int CAM_CHUNK = 4;
     __shared__ unsigned s_cnt[TRACE_THREADS / 32][GVT_P2P_MAX], s_base[TRACE_THREADS / 32][GVT_P2P_MAX];
     const unsigned warp = threadIdx.x >> 5;
     const bool enter_inside = (fp.flags & FLAG_ENTER_INSIDE) != 0;
@@ -1419,11 +1425,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       const size_t bb = lr / pp.tiles.tile_rows, k = lr - bb * pp.tiles.tile_rows;
       return ((size_t)pp.tiles.row0 + (bb * pp.tiles.stride + pp.tiles.index) * pp.tiles.tile_rows + k) * per_row + within;
     };
-    // per-lane notes of a chunk live in the traversal stack's shared memory (unused until phase 2): entry j = {first
-    // instance, destination | position in the warp's reservation << 8}, entries CAM_CHUNK.. = the routing distances
+    // per-lane notes of a chunk live in the traversal stack's shared memory (unused until phase 2), three 8-byte entries per
+    // ray: {first instance, destination | position in the warp's reservation << 8}, {d.x, d.y}, {d.z, routing distance}
     uint2 *note = s_stack + threadIdx.x;
-    float *note_t = reinterpret_cast<float *>(s_stack + CAM_CHUNK * TRACE_THREADS);
-    static_assert(CAM_CHUNK + CAM_CHUNK / 2 <= TRACE_SM_STACK, "camera notes must fit the shared stack");
+    static_assert(3 * CAM_CHUNK <= TRACE_SM_STACK, "camera notes must fit the shared stack");
     for (size_t it0 = 0; (it0 * n_warps) * 32 < pp.cam_count; it0 += CAM_CHUNK) {
       if (lane < GVT_P2P_MAX) s_cnt[warp][lane] = 0u;
       __syncwarp();
@@ -1431,20 +1436,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       for (int j = 0; j < CAM_CHUNK; ++j) {
         const size_t i = ((it0 + j) * n_warps + wg) * 32 + lane;
         uint2 nt = make_uint2(0xFFFFFFFFu, 0u); // background / beyond the shard
-        float t = 0.f;
         if (i < pp.cam_count) {
           Ray r;
           camera_ray(fp.cam, cam_index(i), r);
+          float t;
           const int next = tlas_route(sd.tlas, r.o, r.d, r.t_max, -1, enter_inside, t);
           if (next >= 0) {
             c_routed++;
             const int dest = multi ? pick_server(pp.servers, next, sd.inst[next].owner, r.d) : me;
             if (dest != me) c_exp++;
             nt = make_uint2((unsigned)next, (unsigned)dest | (atomicAdd(&s_cnt[warp][dest], 1u) << 8));
+            note[(3 * j + 1) * TRACE_THREADS] = make_uint2(f2u(r.d.x), f2u(r.d.y));
+            note[(3 * j + 2) * TRACE_THREADS] = make_uint2(f2u(r.d.z), f2u(t));
           }
         }
-        note[j * TRACE_THREADS] = nt;
-        note_t[j * TRACE_THREADS + threadIdx.x] = t;
+        note[3 * j * TRACE_THREADS] = nt;
       }
       __syncwarp();
       if ((int)lane < pp.world) {
@@ -1454,12 +1460,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       __syncwarp();
 #pragma unroll 1
       for (int j = 0; j < CAM_CHUNK; ++j) {
-        uint2 nt = note[j * TRACE_THREADS];
+        const uint2 nt = note[3 * j * TRACE_THREADS];
         if (nt.x == 0xFFFFFFFFu) continue;
         const size_t i = ((it0 + j) * n_warps + wg) * 32 + lane;
-        Ray r;
-        camera_ray(fp.cam, cam_index(i), r);
-        r.o = xadd(r.o, xmul(r.d, xmul(note_t[j * TRACE_THREADS + threadIdx.x], 0.95f))); // TracerBase.h:394
+        const uint2 n1 = note[(3 * j + 1) * TRACE_THREADS], n2 = note[(3 * j + 2) * TRACE_THREADS];
+        Ray r; // gvtPerspectiveCamera::generateRays' record (gvtCamera.cpp:279-300) around the direction pass A computed
+        r.d = v3(u2f(n1.x), u2f(n1.y), u2f(n2.x));
+        r.o = xadd(fp.cam.eye, xmul(r.d, xmul(u2f(n2.y), 0.95f))); // TracerBase.h:394
+        r.t_min = GVT_RAY_EPSILON, r.t_max = FLT_MAX, r.color = v3(0.f, 0.f, 0.f), r.t = FLT_MAX, r.w = fp.cam.contri;
+        r.type = RAY_PRIMARY, r.depth = fp.cam.depth, r.id = (int)(cam_index(i) / (size_t)(fp.cam.samples * fp.cam.samples));
         const int dest = (int)(nt.y & 0xFFu);
         const RayQueue q = dest == me ? pp.inbox : pp.peer_inbox[dest];
         const unsigned pos = s_base[warp][dest] + (nt.y >> 8);
@@ -1470,13 +1479,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
           c_qovf++;
           atomicOr(&ctl->err, 2u);
           if (dest == me) atomicAdd(&ctl->consumed, 1u); else atomicAdd_system(&pp.mail.m[dest]->pc.consumed, 1u);
-          note[j * TRACE_THREADS] = make_uint2(0xFFFFFFFFu, 0u);
+          note[3 * j * TRACE_THREADS] = make_uint2(0xFFFFFFFFu, 0u);
         }
       }
       __syncwarp();
 #pragma unroll 1
       for (int j = 0; j < CAM_CHUNK; ++j) { // the first release waits for this lane's payload stores, the others find nothing outstanding
-        const uint2 nt = note[j * TRACE_THREADS];
+        const uint2 nt = note[3 * j * TRACE_THREADS];
         if (nt.x == 0xFFFFFFFFu) continue;
         const int dest = (int)(nt.y & 0xFFu);
         const RayQueue q = dest == me ? pp.inbox : pp.peer_inbox[dest];
@@ -1499,7 +1508,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
   unsigned iter = 0;
   unsigned long long t_idle0 = 0;
   const unsigned long long t_start = global_ns();
-  enum { L_IDLE = 0, L_WAIT = 1, L_ACTIVE = 2, L_DEAD = 3 };
+  enum { L_IDLE = 0, L_WAIT = 1, L_ACTIVE = 2, L_DEAD = 3, L_HELP = 4, L_JOIN = 5 };
   int st = L_IDLE;
   unsigned idx = 0; // the lane's ticket: inbox slot (tracer) or hit-queue slot (shader)
 
@@ -1591,6 +1600,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
     stack.overflow = false;
     bool first = true, any = false;
     int inst = 0, type = 0;
+    int team = -1; // helper lanes: the owner's lane | the lane's own state << 8
     V3 o = v3(0.f, 0.f, 0.f), d = o;
     float t_min = 0.f, t_max = 0.f, tfar = FLT_MAX;
     const float4 *nodes = nullptr, *tris = nullptr;
@@ -1630,7 +1640,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       if (__any_sync(FULL, pend0 != nullptr)) publish(); // what the previous iteration stored: its payload has arrived by now
       // ---- idle lanes draw inbox tickets ---------------------------------------------------------------------------
       const unsigned idle = __ballot_sync(FULL, st == L_IDLE);
-      const unsigned tracing = __ballot_sync(FULL, st == L_ACTIVE);
+      const unsigned tracing = __ballot_sync(FULL, st == L_ACTIVE || st == L_HELP);
       const bool starved = 32 - __popc(tracing) >= tune.exit_at; // the traversal loop would come straight back
       // (a ticket is drawn without looking whether its ray exists yet: a lane keeps its ticket until the ray lands, so at most
       // one ticket per lane is ever ahead of `tail`, arriving rays find a lane waiting, and a refill costs one L2 round trip)
@@ -1666,7 +1676,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       };
       if (tracing == 0u) start_landed(); // nothing to overlap with
       // ---- nothing to trace in this warp ----------------------------------------------------------------------------------
-      if (__ballot_sync(FULL, st == L_ACTIVE) == 0u) {
+      if (__ballot_sync(FULL, st == L_ACTIVE || st == L_HELP || st == L_JOIN) == 0u) {
         flush();
         unsigned stop = 0;
         if (lane == 0) stop = ld_volatile_u32(&ctl->stop) == seq ? 1u : 0u;
@@ -1688,12 +1698,96 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       if (COUNT) pc1 = clock64(), p_poll += pc1 - pc0;
       // ---- traverse in lock step (comes back after PERSIST_TRIPS iterations at the latest: tickets get polled and new
       // arrivals get lanes; whether the inbox holds rays is not known without asking, so it never leaves early for a refill)
-      const unsigned resting = __ballot_sync(FULL, st != L_ACTIVE);
-      const bool done = warp_traverse<COUNT, PERSIST_TRIPS>(st == L_ACTIVE, resting, false, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
+      // ---- a nearly empty warp (the tail of the frame: a few long rays, each a chain of hundreds of dependent node visits)
+      // shares its rays out: a free lane takes the bottom half of a traversing lane's stack -- the oldest, largest subtrees
+      // -- and traverses it as a HELPER with a copy of the ray; hits are merged into the owner when a helper is done (smaller
+      // t, then smaller primitive id: the result does not depend on who found what; any hit ends a shadow ray for the whole
+      // team).  The chain of a long ray shrinks with the number of lanes working on it; nothing else changes: helpers never
+      // touch the frame's counters, the owner finishes the ray when its team is done.
+      {
+        const unsigned tm0 = __ballot_sync(FULL, st == L_ACTIVE || st == L_HELP);
+        if (tune.split_below > 0 && __popc(tm0) <= tune.split_below) {
+          const unsigned donors = __ballot_sync(FULL, (st == L_ACTIVE || st == L_HELP) && tv.sp >= 2);
+          const unsigned frees = __ballot_sync(FULL, st == L_IDLE || st == L_DEAD || (st == L_WAIT && landed != seq));
+          const int n = min(__popc(donors), __popc(frees));
+          if (n > 0) {
+            const bool isD = ((donors >> lane) & 1u) && __popc(donors & ltmask) < n;
+            const bool isF = ((frees >> lane) & 1u) && __popc(frees & ltmask) < n;
+            // partner lane: the r-th donor pairs with the r-th free lane
+            int partner = (int)lane;
+            if (isD) partner = (int)__fns(frees, 0, __popc(donors & ltmask) + 1);
+            if (isF) partner = (int)__fns(donors, 0, __popc(frees & ltmask) + 1);
+            const int src = isF ? partner : (int)lane;
+            // the ray, as the donor holds it
+            const float ox = __shfl_sync(FULL, rl.o.x, src), oy = __shfl_sync(FULL, rl.o.y, src), oz = __shfl_sync(FULL, rl.o.z, src);
+            const float dx = __shfl_sync(FULL, rl.d.x, src), dy = __shfl_sync(FULL, rl.d.y, src), dz = __shfl_sync(FULL, rl.d.z, src);
+            const float rx = __shfl_sync(FULL, rl.rdx, src), ry = __shfl_sync(FULL, rl.rdy, src), rz = __shfl_sync(FULL, rl.rdz, src);
+            const unsigned oc = __shfl_sync(FULL, rl.octinv, src);
+            const unsigned long long np = __shfl_sync(FULL, (unsigned long long)nodes, src), tp = __shfl_sync(FULL, (unsigned long long)tris, src);
+            const float tf = __shfl_sync(FULL, tfar, src), tmx = __shfl_sync(FULL, tv.tmax, src), ht = __shfl_sync(FULL, tv.hit.t, src);
+            const int an = __shfl_sync(FULL, (int)any, src), dsp = __shfl_sync(FULL, tv.sp, src);
+            const int own = __shfl_sync(FULL, st == L_HELP ? (team & 0xFF) : (int)lane, src);
+            const int h = min(dsp / 2, TRACE_SM_STACK); // entries the helper takes: the bottom of the donor's stack (all in shared memory)
+            if (isF) {
+              const uint2 *dcol = s_stack + (threadIdx.x - lane + (unsigned)partner);
+              for (int k = 0; k < h; ++k) stack.s[k * TRACE_THREADS] = dcol[k * TRACE_THREADS];
+            }
+            __syncwarp();
+            if (isD) {
+              const int hh = min(tv.sp / 2, TRACE_SM_STACK);
+              for (int k = hh; k < tv.sp; ++k) stack.set(k - hh, stack.get(k));
+              tv.sp -= hh;
+            }
+            if (isF) {
+              rl.o = v3(ox, oy, oz), rl.d = v3(dx, dy, dz), rl.rdx = rx, rl.rdy = ry, rl.rdz = rz, rl.octinv = oc;
+              nodes = (const float4 *)np, tris = (const float4 *)tp, tfar = tf, any = an != 0;
+              tv.sp = h, tv.tmax = tmx;
+              tv.ng = make_uint2(0u, 0u), tv.tg = make_uint2(GVT_TRI_TAG, 0u);
+              tv.hit.prim = -1, tv.hit.slot = -1, tv.hit.t = ht, tv.hit.u = 0.f, tv.hit.v = 0.f;
+              team = own | (st << 8); // what the lane was doing comes back when it is done helping
+              st = L_HELP;
+            }
+            __syncwarp();
+          }
+        }
+      }
+      const unsigned resting = __ballot_sync(FULL, st != L_ACTIVE && st != L_HELP);
+      const bool done = warp_traverse<COUNT, PERSIST_TRIPS>(st == L_ACTIVE || st == L_HELP, resting, false, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
       long long pc2 = 0;
       if (COUNT) pc2 = clock64(), p_trav += pc2 - pc1;
+      // ---- helpers that are done hand their hit to the ray's owner; owners wait for their team --------------------------------
+      bool fin = st == L_ACTIVE && done;
+      if (__ballot_sync(FULL, st == L_HELP || st == L_JOIN) != 0u) {
+        unsigned hm = __ballot_sync(FULL, st == L_HELP && done);
+        while (hm) {
+          const int f = __ffs((int)hm) - 1;
+          hm &= hm - 1u;
+          const int own = __shfl_sync(FULL, team & 0xFF, f);
+          const int hp = __shfl_sync(FULL, tv.hit.prim, f), hs = __shfl_sync(FULL, tv.hit.slot, f);
+          const float ht = __shfl_sync(FULL, tv.hit.t, f), hu = __shfl_sync(FULL, tv.hit.u, f), hv = __shfl_sync(FULL, tv.hit.v, f);
+          if ((int)lane == own && hp >= 0 && (ht < tv.hit.t || (ht == tv.hit.t && (tv.hit.prim < 0 || hp < tv.hit.prim)))) {
+            tv.hit.prim = hp, tv.hit.slot = hs, tv.hit.t = ht, tv.hit.u = hu, tv.hit.v = hv;
+            tv.tmax = ht;
+          }
+          if ((int)lane == f) st = team >> 8, team = -1;
+        }
+        // a shadow ray with a hit is over for its whole team
+        const unsigned over = __ballot_sync(FULL, (st == L_ACTIVE || st == L_JOIN) && any && tv.hit.prim >= 0);
+        if (st == L_HELP && ((over >> (team & 0xFF)) & 1u)) st = team >> 8, team = -1;
+        if (st == L_ACTIVE && ((over >> lane) & 1u)) fin = true;
+        // owners whose own stack is empty wait for their helpers
+        unsigned helpers = __ballot_sync(FULL, st == L_HELP);
+        bool has_helpers = false;
+        while (helpers) {
+          const int f = __ffs((int)helpers) - 1;
+          helpers &= helpers - 1u;
+          if (__shfl_sync(FULL, team & 0xFF, f) == (int)lane) has_helpers = true;
+        }
+        if (fin && has_helpers) st = L_JOIN, fin = false;
+        else if (st == L_JOIN && !has_helpers) st = L_ACTIVE, fin = true;
+      }
       // ---- rays that finished their instance -------------------------------------------------------------------------
-      if (st == L_ACTIVE && done) {
+      if (fin) {
         if (COUNT && pp.inst_load) atomicAdd(pp.inst_load + inst, (unsigned long long)(tc.nodes - nodes0));
         if (tv.hit.prim >= 0) {
           if (type != RAY_SHADOW) { // closest hit -> the shader SMs; an occluded shadow ray is dropped (:487-489)

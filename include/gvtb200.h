@@ -99,6 +99,11 @@ GVTB200_API int gvtb200_set_tuning(int refill_at, int exit_at, int postpone_num,
  * each a chain of dependent node fetches) requests the sibling nodes it pushes onto its stack into L2 (0 = off; also
  * GVTB200_TAIL_PREFETCH).  Results do not depend on it. */
 GVTB200_API int gvtb200_set_tail_prefetch(int max_lanes);
+/* tail splitting (persistent kernel): a warp with at most max_lanes traversing rays shares their traversal stacks out among
+ * its free lanes, which traverse the donated subtrees as helpers and hand their hits back (the frame's last rays are chains
+ * of hundreds of dependent node visits; the chain shrinks with the lanes working on it).  0 = off, default 16; also
+ * GVTB200_TAIL_SPLIT.  Results do not depend on it (closest hit: smaller t, then smaller primitive id). */
+GVTB200_API int gvtb200_set_tail_split(int max_lanes);
 /* how long a kernel of the NVLink peer path waits for another GPU before it gives up and flags the frame (default 4000 ms;
  * also GVTB200_PEER_TIMEOUT_MS).  The reference blocks in MPI_Wait for ever (DomainTracer.h:480-486). */
 GVTB200_API int gvtb200_set_peer_timeout_ms(int ms);

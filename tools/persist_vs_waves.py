@@ -38,8 +38,9 @@ for name in names:
     build_s = time.perf_counter() - t0
     out = {"workload": name, "film": [d.width, d.height], "build_s": round(build_s, 2)}
     fbs = {}
-    for mode in ("waves", "persist", "waves_pf8", "persist_pf4", "persist_pf8", "persist_pf16"):
-        g.check(g.lib().gvtb200_set_tail_prefetch(int(mode.split("_pf")[1]) if "_pf" in mode else 0))
+    modes = next((x[8:].split(",") for x in sys.argv[1:] if x.startswith("--modes=")), ["waves", "persist", "persist_sp0", "persist_sp32"])
+    for mode in modes:
+        g.check(g.lib().gvtb200_set_tail_split(int(mode.split("_sp")[1]) if "_sp" in mode else 8))
         for shade_at in ((8,) if mode.startswith("waves") else ((8, 14) if mode == "persist" else (8,))):
             if mode.startswith("persist"):
                 e.domain_persist_config(0, shade_at)
@@ -59,8 +60,9 @@ for name in names:
             out[key + "_ms"] = round(statistics.median(ms), 4)
             out["rays"] = c["camera_rays"] + c["shadow_generated"] + c["secondary_generated"]
             fbs[mode.split("_")[0]] = e.fb_read(d.width, d.height)
-    out["max_abs_diff"] = float(np.abs(fbs["waves"] - fbs["persist"]).max())
-    g.check(g.lib().gvtb200_set_tail_prefetch(0))
+    if "waves" in fbs and "persist" in fbs:
+        out["max_abs_diff"] = float(np.abs(fbs["waves"] - fbs["persist"]).max())
+    g.check(g.lib().gvtb200_set_tail_split(8))
     e.profile_counters(True)
     e.domain_frame_persist(0, 8)
     e.sync()
