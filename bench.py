@@ -500,6 +500,17 @@ def main():
             b, r = b.tolist(), r.tolist()
             return {"busy_ms_per_rank": [round(x, 3) for x in b], "imbalance_max_over_mean": round(max(b) / max(1e-9, sum(b) / len(b)), 3), "inbox_rays_per_rank": [int(x) for x in r]}
 
+        def progress_curve():
+            """The root's progress samples of the last persistent frame, thinned: [ms, fraction of the rays retired]."""
+            if rank != 0:
+                return None
+            p = e.domain_persist_progress()
+            if not len(p):
+                return []
+            total = float(p[-1, 2]) or 1.0
+            keep = p[:: max(1, len(p) // 24)]
+            return [[round(float(us) * 1e-3, 3), round(float(c) / total, 4)] for us, c, _ in keep] + [[round(float(p[-1, 0]) * 1e-3, 3), round(float(p[-1, 1]) / total, 4)]]
+
         def measure(label, step):
             ms, _ = timed(step, steps, warmup)
             e.sync()
@@ -516,6 +527,7 @@ def main():
         # (1) the persistent scheduler, every brick served by its owner alone
         base, ctr_all = measure("persistent kernel, brick served by its owner", persist)
         base.update(persist_stats())
+        base["progress_ms_vs_fraction_retired"] = progress_curve()
         if world == 1:
             e.profile_counters(True)
             persist()
@@ -545,6 +557,7 @@ def main():
                 barrier()
                 shared, _ = measure(f"persistent kernel, <= {a.replicas} BLAS replica(s) of other ranks' bricks per rank (copied from the owner over NVLink)", persist)
                 shared.update(persist_stats())
+                shared["progress_ms_vs_fraction_retired"] = progress_curve()
                 e.profile_counters(True)
                 persist()
                 e.sync()

@@ -59,7 +59,7 @@ C_ABI_SYMBOLS = (
     "gvtb200_framebuffer_clamp gvtb200_scene_last_timing gvtb200_domain_set_owner gvtb200_domain_begin_frame "
     "gvtb200_domain_drain_local gvtb200_domain_export gvtb200_domain_import gvtb200_domain_pending "
     "gvtb200_p2p_export gvtb200_p2p_attach gvtb200_p2p_detach gvtb200_image_frame_p2p gvtb200_domain_round_p2p gvtb200_domain_composite_p2p "
-    "gvtb200_domain_frame_persist gvtb200_domain_persist_config gvtb200_domain_persist_stats gvtb200_domain_persist_profile gvtb200_domain_set_servers "
+    "gvtb200_domain_frame_persist gvtb200_domain_persist_config gvtb200_domain_persist_stats gvtb200_domain_persist_profile gvtb200_domain_persist_progress gvtb200_domain_set_servers "
     "gvtb200_scene_set_instance_mesh gvtb200_mesh_export gvtb200_mesh_import"
 ).split()
 PEER_DESC_BYTES = 64 * 4 + 8 * 4 + 8 + 8 + 8 + 4 + 4  # sizeof(gvtb200_peer_desc)
@@ -163,6 +163,7 @@ def lib():
         L.gvtb200_domain_persist_stats.argtypes = [vp, vp, vp, vp, i32]
         L.gvtb200_domain_set_servers.argtypes = [vp, vp, vp, i32]
         L.gvtb200_domain_persist_profile.argtypes = [vp, vp]
+        L.gvtb200_domain_persist_progress.argtypes = [vp, vp, i32, vp]
         L.gvtb200_scene_set_instance_mesh.argtypes = [vp, i32, vp]
         L.gvtb200_mesh_export.argtypes = [vp, vp]
         L.gvtb200_mesh_import.argtypes = [vp, i32, vp]
@@ -568,6 +569,12 @@ class EngineScene:
         load = np.zeros(n_instances, np.uint64) if n_instances else None
         check(lib().gvtb200_domain_persist_stats(self.h, C.byref(busy), C.byref(rays), _fp(load), n_instances))
         return busy.value, int(rays.value), load
+
+    def domain_persist_progress(self):
+        """[(us since the start barrier, rays retired, rays handed out)] as the root's control warp sampled them."""
+        buf, n = np.zeros((256, 3), np.uint32), C.c_int(0)
+        check(lib().gvtb200_domain_persist_progress(self.h, _fp(buf), 256, C.byref(n)))
+        return buf[: n.value].copy()
 
     def domain_persist_profile(self):
         """Cycle breakdown of a counted persistent frame (gvtb200_domain_persist_profile), as fractions per role."""

@@ -1983,6 +1983,18 @@ int gvtb200_domain_persist_profile(gvtb200_scene s, uint64_t prof[16]) {
   CU(cudaMemcpy(prof, s->p2p.d_mail->pc.prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return GVTB200_OK;
 }
+int gvtb200_domain_persist_progress(gvtb200_scene s, uint32_t *samples, int cap, int *n) {
+  NEED_SCENE();
+  if (!s->p2p.d_mail || !samples || !n) return fail(GVTB200_ERR_INVALID, "no persistent frame has run / NULL argument");
+  CU(cudaStreamSynchronize(s->stream));
+  PersistCtl *pc = &s->p2p.d_mail->pc;
+  unsigned k = 0;
+  CU(cudaMemcpy(&k, &pc->n_progress, 4, cudaMemcpyDeviceToHost));
+  k = std::min<unsigned>(std::min<unsigned>(k, 256u), (unsigned)std::max(0, cap));
+  if (k) CU(cudaMemcpy(samples, pc->progress, (size_t)k * 12, cudaMemcpyDeviceToHost));
+  *n = (int)k;
+  return GVTB200_OK;
+}
 int gvtb200_domain_persist_stats(gvtb200_scene s, double *busy_ms, uint64_t *inbox_rays, uint64_t *instance_load, int n_instances) {
   NEED_SCENE();
   if (!s->p2p.d_mail) return fail(GVTB200_ERR_INVALID, "no persistent frame has run");

@@ -1061,13 +1061,18 @@ struct PersistCtl {
   // rays, [2] in the traversal loop, [3] finishing rays (routing, sends, hit records), [4] drawing / polling tickets;
   // shader warps: [5] shading, [6] waiting for hits; [7] warps counted
   unsigned long long prof[16];
+  // the root's control warp samples the job's progress while it polls for termination: [k] = {microseconds since the start
+  // barrier, rays retired on all ranks, rays handed out on all ranks}, one sample every GVT_PROGRESS_US
+  unsigned progress[3 * 256];
+  unsigned n_progress, pad5[31];
   // ---- not reset between frames: values are frame sequence numbers ----
   unsigned cam_done; // every camera ray of this rank's shard has been handed out
   unsigned go, stop, done_seq;
   unsigned long long t_go, t_last; // globaltimer at the start barrier / at the last retire flush (per-rank busy time)
   unsigned arrive[GVT_P2P_MAX];    // start barrier: arrive[r] = frame number, written by rank r
 };
-#define GVT_PERSIST_RESET_BYTES 768 /* tail .. prof */
+#define GVT_PERSIST_RESET_BYTES (768 + 3 * 256 * 4 + 128) /* tail .. pad5 */
+#define GVT_PROGRESS_US 16
 struct Mailbox {
   unsigned go, err, cta_done, pad;
   unsigned done[GVT_P2P_MAX];
@@ -1195,7 +1200,7 @@ __global__ void k_fb_accumulate_root(const float4 *src, float *dst, size_t npix,
 #define PERSIST_MIN_BLOCKS 6
 #endif
 #ifndef PERSIST_TRIPS
-#define PERSIST_TRIPS 16
+#define PERSIST_TRIPS 24
 #endif
 struct PersistParams {
   RayQueue inbox;             // this rank's inbound slots (count unused: PersistCtl::tail / head)
@@ -1302,7 +1307,12 @@ __device__ __noinline__ void persist_control(const PersistParams &pp, PersistCtl
       const unsigned cs = __reduce_add_sync(FULL, c), es = __reduce_or_sync(FULL, e), all_started = __reduce_and_sync(FULL, started);
       const unsigned t = (peer && cs != 0xFFFFFFFFu) ? ld_volatile_u32(&theirs->tail) + ld_volatile_u32(&theirs->hit_tail) : 0u;
       const unsigned ts = __reduce_add_sync(FULL, t);
-      const bool late = global_ns() - t0 > pp.timeout_ns;
+      const unsigned long long now = global_ns();
+      const bool late = now - t0 > pp.timeout_ns;
+      if (r == 0) { // progress curve of the whole job (read back by gvtb200_domain_persist_progress)
+        const unsigned us = (unsigned)((now - ctl->t_go) / 1000ull), k = ctl->n_progress;
+        if (k < 256u && us >= k * GVT_PROGRESS_US) ctl->progress[3 * k] = us, ctl->progress[3 * k + 1] = cs, ctl->progress[3 * k + 2] = ts, ctl->n_progress = k + 1u;
+      }
       if ((all_started && cs == ts) || es || late) {
         if ((es || late) && r == 0) atomicOr(&ctl->err, es ? es : 1u);
         break;
@@ -1409,14 +1419,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
 
   // ---- phase 1: gvtPerspectiveCamera::generateRays + FilterRaysLocally (first routing hop) for this rank's film shard ------
   // Two passes over chunks of CAM_CHUNK rays per lane: (A) generate, route, pick the serving rank, count per destination
-  // inside the warp; ONE slot reservation per warp and destination (same-address atomics on an inbox's `tail` serialise at
-  // about a nanosecond each -- over NVLink too -- and one per ray group made this phase 0.3 ms long whatever the number of
-  // GPUs); (B) regenerate the ray (cheaper than keeping it) and store it into its slot.
+  // inside the CTA; ONE slot reservation per CTA and destination (same-address atomics on an inbox's `tail` serialise at
+  // a few nanoseconds each over NVLink, and one per ray group made this phase 0.3 ms long whatever the number of GPUs); (B) regenerate the ray (cheaper than keeping it) and store it into its slot.
   long long pc0 = COUNT ? clock64() : 0;
   {
     constexpr int CAM_CHUNK = 4;
-    __shared__ unsigned s_cnt[TRACE_THREADS / 32][GVT_P2P_MAX], s_base[TRACE_THREADS / 32][GVT_P2P_MAX];
+    __shared__ unsigned s_cnt[GVT_P2P_MAX], s_base[GVT_P2P_MAX]; // per CTA: rays per destination in this chunk, where their slots start
     const unsigned warp = threadIdx.x >> 5;
+    const unsigned n_workers = blockIdx.x == 0 ? TRACE_THREADS - 32 : TRACE_THREADS, first_worker = blockIdx.x == 0 ? 32u : 0u;
+    auto cta_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(n_workers) : "memory"); }; // the control warp is not part of it
     const bool enter_inside = (fp.flags & FLAG_ENTER_INSIDE) != 0;
     const size_t per_row = (size_t)fp.cam.W * fp.cam.samples * fp.cam.samples;
     const size_t n_warps = (size_t)gridDim.x * (TRACE_THREADS / 32) - 1, wg = (size_t)blockIdx.x * (TRACE_THREADS / 32) + warp - 1; // workers only
@@ -1430,8 +1441,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
     uint2 *note = s_stack + threadIdx.x;
     static_assert(3 * CAM_CHUNK <= TRACE_SM_STACK, "camera notes must fit the shared stack");
     for (size_t it0 = 0; (it0 * n_warps) * 32 < pp.cam_count; it0 += CAM_CHUNK) {
-      if (lane < GVT_P2P_MAX) s_cnt[warp][lane] = 0u;
-      __syncwarp();
+      if (threadIdx.x - first_worker < GVT_P2P_MAX) s_cnt[threadIdx.x - first_worker] = 0u;
+      cta_sync();
 #pragma unroll 1
       for (int j = 0; j < CAM_CHUNK; ++j) {
         const size_t i = ((it0 + j) * n_warps + wg) * 32 + lane;
@@ -1445,19 +1456,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
             c_routed++;
             const int dest = multi ? pick_server(pp.servers, next, sd.inst[next].owner, r.d) : me;
             if (dest != me) c_exp++;
-            nt = make_uint2((unsigned)next, (unsigned)dest | (atomicAdd(&s_cnt[warp][dest], 1u) << 8));
+            nt = make_uint2((unsigned)next, (unsigned)dest | (atomicAdd(&s_cnt[dest], 1u) << 8));
             note[(3 * j + 1) * TRACE_THREADS] = make_uint2(f2u(r.d.x), f2u(r.d.y));
             note[(3 * j + 2) * TRACE_THREADS] = make_uint2(f2u(r.d.z), f2u(t));
           }
         }
         note[3 * j * TRACE_THREADS] = nt;
       }
-      __syncwarp();
-      if ((int)lane < pp.world) {
-        const unsigned n = s_cnt[warp][lane];
-        if (n) s_base[warp][lane] = (int)lane == me ? atomicAdd(&ctl->tail, n) : atomicAdd_system(&pp.mail.m[lane]->pc.tail, n);
+      cta_sync();
+      if ((int)(threadIdx.x - first_worker) < pp.world) { // ONE reservation per CTA, chunk and destination
+        const int dst = (int)(threadIdx.x - first_worker);
+        const unsigned n = s_cnt[dst];
+        if (n) s_base[dst] = dst == me ? atomicAdd(&ctl->tail, n) : atomicAdd_system(&pp.mail.m[dst]->pc.tail, n);
       }
-      __syncwarp();
+      cta_sync();
 #pragma unroll 1
       for (int j = 0; j < CAM_CHUNK; ++j) {
         const uint2 nt = note[3 * j * TRACE_THREADS];
@@ -1471,7 +1483,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         r.type = RAY_PRIMARY, r.depth = fp.cam.depth, r.id = (int)(cam_index(i) / (size_t)(fp.cam.samples * fp.cam.samples));
         const int dest = (int)(nt.y & 0xFFu);
         const RayQueue q = dest == me ? pp.inbox : pp.peer_inbox[dest];
-        const unsigned pos = s_base[warp][dest] + (nt.y >> 8);
+        const unsigned pos = s_base[dest] + (nt.y >> 8);
         if (pos < q.cap) {
           queue_store(q, pos, r, (int)nt.x);
           if (dest != me) dirty = true;
@@ -1489,9 +1501,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         if (nt.x == 0xFFFFFFFFu) continue;
         const int dest = (int)(nt.y & 0xFFu);
         const RayQueue q = dest == me ? pp.inbox : pp.peer_inbox[dest];
-        st_release_sys(q.ready + s_base[warp][dest] + (nt.y >> 8), seq);
+        st_release_sys(q.ready + s_base[dest] + (nt.y >> 8), seq);
       }
-      __syncwarp();
+      cta_sync(); // s_cnt / s_base are rewritten by the next chunk
     }
     __syncwarp();
     // (the warp count below only tells the root that no more camera rays will be handed out by this rank)
@@ -1662,13 +1674,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
           const float4 c0 = ld_strong_f4(pp.inbox.c0 + idx), c1 = ld_strong_f4(pp.inbox.c1 + idx);
           type = ld_strong_i32(&pp.inbox.c3[idx].w);
           inst = ld_strong_i32(pp.inbox.inst + idx);
-#ifdef GVT_DEBUG_PERSIST
-          if ((unsigned)inst >= (unsigned)sd.tlas.n_inst) {
-            printf("BAD inst %d at idx %u type %d landed %u seq %u tail %u head %u o %f %f %f blk %d thr %d iter %u\n", inst, idx, type, landed, seq, ld_volatile_u32(&ctl->tail), ld_volatile_u32(&ctl->head), c0.x, c0.y, c0.z, blockIdx.x, threadIdx.x, iter);
-            st = L_DEAD;
-            return;
-          }
-#endif
           o = v3(c0.x, c0.y, c0.z), t_min = c0.w, d = v3(c1.x, c1.y, c1.z), t_max = c1.w;
           any = (type == RAY_SHADOW), first = true, st = L_ACTIVE;
           begin_instance();
@@ -1846,7 +1851,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         }
       }
       start_landed();
-      if ((iter & 63u) == 0u) flush();
+      if ((iter & 15u) == 0u) flush();
       if (COUNT) p_post += clock64() - pc2;
     }
     publish();

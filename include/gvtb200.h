@@ -318,6 +318,10 @@ GVTB200_API int gvtb200_domain_persist_stats(gvtb200_scene scene, double *busy_m
  * [0] camera phase; tracer warps: [1] waiting for rays, [2] traversal loop, [3] finishing rays (routing, sends, hit records),
  * [4] drawing / polling tickets; shader warps: [5] shading, [6] waiting for hits; [7] warps, [8] shader warps, [9] tracer warps */
 GVTB200_API int gvtb200_domain_persist_profile(gvtb200_scene scene, uint64_t prof[16]);
+/* the root's view of the last persistent frame, sampled every 16 us by its control warp while it polled for termination:
+ * samples[3*k] = microseconds since the start barrier, [3*k+1] = rays retired on all ranks, [3*k+2] = rays handed out on
+ * all ranks (up to 256 samples; *n receives the count).  Shows whether a frame is throughput or latency-chain bound. */
+GVTB200_API int gvtb200_domain_persist_progress(gvtb200_scene scene, uint32_t *samples, int cap, int *n);
 /* Which ranks serve an instance (persistent scheduler only; default: its owner).  ranks[4*i+j], j < 4, are the ranks that
  * hold a BLAS for instance i (-1 = unused), weights[4*i+j] their shares (NULL = equal); a ray bound for the instance picks
  * one by a hash of its direction bits, so the choice is reproducible.  This is how the work of a hot domain is spread:
