@@ -334,6 +334,74 @@ def test_full_size_properties(gpu):
     assert 0.05 < c["primary_hits"] / c["camera_rays"] < 0.5
 
 
+def test_incoherent_config4_reduced_film(gpu):
+    """BASELINE configs[4] at a reduced film: sibenik, samples = 3 (W*H*samples^2 camera rays, gvtCamera.cpp:205), rayMaxDepth 5
+    (the bounce loop of EmbreeMeshAdapter.cpp:584-598 run four times).  The random numbers of a bounce are a function of (ray id,
+    depth) on both sides (the reference's per-TBB-chunk RandEngine, core/math/RandEngine.h:43-81, is not reproducible and is
+    replaced on both sides: a documented deviation), so the counters agree to 1e-3 and the image to >= 50 dB."""
+    d = library.incoherent_scene(240, 135)
+    assert d.depth == 5 and d.samples == 3
+    o, s, e = _pair(gpu, d)
+    ref, st = o.render(threads=8)
+    fb = s.render()
+    ctr = e.counters()
+    assert ctr["camera_rays"] == st["camera_rays"] == 240 * 135 * 9
+    assert st["secondary_generated"] > 0.05 * st["camera_rays"]  # the bounces are really there
+    for k in ("primary_hits", "shadow_generated", "shadow_unoccluded", "secondary_generated", "fb_adds"):
+        assert abs(ctr[k] - st[k]) <= 1e-3 * st[k] + 2, (k, ctr[k], st[k])
+    assert ctr["queue_overflows"] == 0 and ctr["stack_overflows"] == 0
+    assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref)) >= 50.0
+    assert np.allclose(fb, ref, atol=2e-3)
+
+
+def test_instanced_grid_frame_bit_identical(gpu):
+    """BASELINE configs[2] in small: a 9x9 grid of bunny.obj instances (two-level BVH: 81 instance boxes over one BLAS, rays
+    that miss one instance are routed on to the next, TracerBase.h:392-401).  Depth 1, one light: one add per pixel, so the
+    framebuffer is bit-identical to the oracle's, and so are the routing / hit / shadow counters."""
+    a = np.load(os.path.join(library.ASSETS, "bunny_obj.npz"))
+    d = library.SceneDesc("grid9", width=480, height=360)
+    d.meshes = [library.MeshDesc(a["verts"], a["faces"], False, None)]
+    n, pitch = 9, 0.2
+    for j in range(n):
+        for i in range(n):
+            d.instances.append((0, library.translate_scale((i * pitch, j * pitch, 0.0), 1.0)))
+    c = (n - 1) * pitch * 0.5
+    d.eye, d.focus, d.up = (c + 0.3, c + 0.1, 2.2), (c, c + 0.1, 0.0), (0.0, 1.0, 0.0)  # slightly oblique: rays cross several boxes
+    d.lights = [(d.eye, (1.0, 1.0, 1.0))]
+    o, s, e = _pair(gpu, d, 1)
+    ref, st = o.render(threads=8)
+    fb = s.render()
+    ctr = e.counters()
+    for k in ("camera_rays", "routed_initial", "primary_hits", "shadow_generated", "shadow_unoccluded", "fb_adds"):
+        assert ctr[k] == st[k], (k, ctr[k], st[k])
+    assert ctr["instance_visits"] == st["rays_traced"] + st["shadow_generated"] > ctr["routed_initial"] + ctr["shadow_generated"]  # rays did move on
+    assert np.array_equal(fb, ref)
+    # the persistent scheduler renders the same frame
+    e.domain_frame_persist(0, 8)
+    e.sync()
+    assert np.array_equal(e.fb_read(d.width, d.height), ref)
+
+
+@pytest.mark.parametrize("name", ["bunny", "sibenik"])
+def test_full_1080p_frames_against_the_oracle(gpu, name):
+    """The 1080p frames of the north-star target (bunny, primary + shadow: bit-identical) and of BASELINE configs[1] (sibenik,
+    shadow + 1 bounce: >= 50 dB, counters to 1e-3) against the CPU oracle at FULL size, once."""
+    d = library.bunny_scene(1920, 1080) if name == "bunny" else library.sibenik_scene(1920, 1080, depth=2)
+    o, s, e = _pair(gpu, d, 0 if name == "bunny" else None)
+    ref, st = o.render(threads=os.cpu_count() or 8)
+    fb = s.render()
+    ctr = e.counters()
+    assert ctr["camera_rays"] == st["camera_rays"] == 1920 * 1080
+    if name == "bunny":
+        for k in ("routed_initial", "primary_hits", "shadow_generated", "shadow_unoccluded", "fb_adds"):
+            assert ctr[k] == st[k], (k, ctr[k], st[k])
+        assert np.array_equal(fb, ref)
+    else:
+        for k in ("primary_hits", "shadow_generated", "shadow_unoccluded", "secondary_generated", "fb_adds"):
+            assert abs(ctr[k] - st[k]) <= 1e-3 * st[k] + 2, (k, ctr[k], st[k])
+        assert po.psnr(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref)) >= 50.0
+
+
 def _standalone_ranks(g, d, flags, world):
     """One engine scene per simulated rank on the same GPU: rank r holds only the meshes of the instances it owns."""
     from gravit_b200 import schedulers
@@ -439,6 +507,23 @@ def test_image_scheduler_peer_gather_bit_identical(gpu, world):
     for tile_rows in (3, 8, 8):  # consecutive frames: the go / done flags carry frame sequence numbers
         assert np.array_equal(frame(tile_rows, 0), ref)
     assert np.array_equal(frame(8, 1), ref)  # a non-zero root works the same way
+    # parallel read-back (gvtb200_framebuffer_read_rows): every rank renders its row tiles and copies them to their place in ONE
+    # host image; then every rank copies its share of the ROOT's gathered image (over the peer mapping) instead
+    for tile_rows in (5, 8):
+        host = np.zeros((d.height, d.width, 4), np.float32)
+        for r, e in enumerate(ranks):
+            e.render_tiles(d.height, tile_rows, r, world)
+            e.fb_read_rows(host.ctypes.data, tile_rows, r, world)
+        for e in ranks:
+            e.sync()
+        assert np.array_equal(host, ref)
+    frame(8, 0)
+    host = np.zeros((d.height, d.width, 4), np.float32)
+    for r, e in enumerate(ranks):
+        e.fb_read_rows(host.ctypes.data, 8, r, world, src_rank=0)
+    for e in ranks:
+        e.sync()
+    assert np.array_equal(host, ref)
     for e in ranks:
         e.close()
 
