@@ -205,6 +205,7 @@ def api():
         A.gvtapi_add_renderer_volume.argtypes = [s, i32, i32, s, s, i32]
         A.gvtapi_modify_camera_pose.argtypes = [s, vp, vp, vp, f]
         A.gvtapi_render.argtypes = [s]
+        A.gvtapi_set_gpus.argtypes = [i32]
         A.gvtapi_writeimage.argtypes = [s, s]
         A.gvtapi_set_engine_flags.argtypes = [u32, u32]
         A.gvtapi_framebuffer.argtypes = [vp, C.c_size_t, vp, vp]
@@ -710,6 +711,14 @@ class GvtScene:
         if not h:
             raise EngineError(self.A.gvtapi_last_error().decode())
         return EngineScene(h)
+
+    def set_gpus(self, n):
+        """api::setGpus: api::render drives n GPUs of this process (one host thread per GPU)."""
+        acheck(self.A.gvtapi_set_gpus(n))
+
+    def set_schedule(self, schedule):
+        """scheduler::Image (0) / Domain (1) / AsyncImage (2) / AsyncDomain (3) for the renderer (api::modifyRenderer)."""
+        acheck(self.A.gvtapi_modify_renderer(b"Renderer", ADAPTER_B200, schedule, b"Camera", b"Film"))
 
     def render(self):
         """api::render + the framebuffer (H, W, 4) float32."""

@@ -477,6 +477,11 @@ int gvtb200_init(int device) {
   }
   if (device < 0 || device >= n || device >= GVT_MAX_DEVICES) return fail(GVTB200_ERR_INVALID, "device %d out of range (0..%d)", device, std::min(n, GVT_MAX_DEVICES) - 1);
   CU(cudaSetDevice(device));
+  if (g_dev[device].ready) { // another thread (or an earlier call) has set this device up: select it for this thread
+    t_device = device;
+    g_device = device;
+    return GVTB200_OK;
+  }
   cudaDeviceProp p;
   CU(cudaGetDeviceProperties(&p, device));
   if (p.major < 10) return fail(GVTB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
@@ -932,8 +937,8 @@ int gvtb200_trace(gvtb200_mesh m, gvtb200_ray *rays, size_t n_rays, size_t begin
   CU(cudaSetDevice(m->device));
   if (int rc = mesh_adapter_ctx(m)) return rc;
   cudaStream_t st = m->stream;
-  int max_depth = 1;
-  for (size_t i = begin; i < end; ++i) max_depth = std::max(max_depth, rays[i].depth);
+  int max_depth = 1; // waves to run; a ray's depth is caller input: bounded (Russian roulette ends real paths long before)
+  for (size_t i = begin; i < end; ++i) max_depth = std::max(max_depth, std::min(rays[i].depth, 64));
   Instance in;
   pack_instance(in, minv, normi, 0, 0);
   CU(cudaMemcpyAsync(m->d_inst, &in, sizeof(in), cudaMemcpyHostToDevice, st));

@@ -12,7 +12,11 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <condition_variable>
+#include <algorithm>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -127,6 +131,23 @@ struct Context {
   // device scene
   gvtb200_scene scene = nullptr;
   bool instances_dirty = true;
+  // several GPUs in this process (api::setGpus): per GPU its own BLAS handles and scene; the tracers of algorithm/*.h run
+  // as one host thread per GPU (render_multi below)
+  int gpus = 1;
+  struct Multi {
+    int n = 0, schedule = -1, w = 0, h = 0;
+    bool attached = false;
+    std::vector<std::vector<gvtb200_mesh> > meshes; // [gpu][mesh in map order], nullptr = not resident
+    std::vector<gvtb200_scene> scenes;
+  } multi;
+  void drop_multi() {
+    for (size_t g = 0; g < multi.scenes.size(); ++g)
+      if (multi.scenes[g]) gvtb200_scene_destroy(multi.scenes[g]);
+    for (auto &v : multi.meshes)
+      for (auto m : v)
+        if (m) gvtb200_mesh_destroy(m);
+    multi = Multi();
+  }
   std::vector<float> fb;
   int fbw = 0, fbh = 0;
 
@@ -138,6 +159,7 @@ struct Context {
     if (scene) gvtb200_scene_destroy(scene);
     scene = nullptr;
     instances_dirty = true;
+    drop_multi();
   }
   ~Context() { drop_scene(); }
 };
@@ -272,6 +294,185 @@ gvtb200_scene device_scene(const RendererRec &r) {
   const unsigned flags = c.flags | (r.adapter == gvt::render::adapter::EmbreeStream ? (unsigned)GVTB200_FLAG_SMOOTH : 0u);
   if (gvtb200_scene_set_flags(c.scene, flags, c.seed) != GVTB200_OK) engine_error("flags");
   return c.scene;
+}
+
+
+// ---- Tracer<ImageScheduler> / Tracer<DomainScheduler> on several GPUs of this process -------------------------------------
+// Renderer.cpp:71-96 picks the tracer from the schedule type; here the tracer is one host thread per GPU (no MPI, no IPC: the
+// devices map each other's memory with cudaDeviceEnablePeerAccess) driving the same C ABI calls the one-process-per-GPU
+// drivers use:
+//   Image / AsyncImage   geometry replicated (ImageTracer.h:111-125 slices the film), every GPU renders its row tiles and
+//                        brings them to their place in the host image over its own PCIe link;
+//   Domain               instance k lives on GPU k % n (DomainTracer.h:140); exchange rounds with rays stored into the owner's
+//                        queue over NVLink, the termination sum (:339-349) formed by the host threads between two barriers;
+//   AsyncDomain          the persistent scheduler: one kernel per GPU and frame, no rounds, termination on the device.
+// The composited image (root GPU 0) is read back in parallel as well.
+struct Barrier { // the threads of one frame meet here (what MPI_Barrier / the gather of DomainTracer.h:339-349 were for)
+  std::mutex m;
+  std::condition_variable cv;
+  int n, waiting = 0, phase = 0;
+  explicit Barrier(int n) : n(n) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    const int ph = phase;
+    if (++waiting == n) {
+      waiting = 0, ++phase;
+      cv.notify_all();
+    } else
+      cv.wait(lk, [&] { return phase != ph; });
+  }
+};
+
+void multi_build(const RendererRec &r, int n) {
+  Context &c = db();
+  const CameraRec &cr = c.cameras.at(r.camera);
+  const FilmRec &fr = c.films.at(r.film);
+  const bool domain = r.schedule == gvt::render::scheduler::Domain || r.schedule == gvt::render::scheduler::AsyncDomain;
+  bool mesh_dirty = false;
+  for (auto &kv : c.meshes) mesh_dirty |= kv.second->dirty;
+  Context::Multi &M = c.multi;
+  if (M.n != n || M.schedule != r.schedule || M.w != fr.w || M.h != fr.h || mesh_dirty || c.instances_dirty) {
+    c.drop_multi();
+    M.n = n, M.schedule = r.schedule, M.w = fr.w, M.h = fr.h;
+    M.meshes.assign(n, std::vector<gvtb200_mesh>(c.meshes.size(), nullptr));
+    M.scenes.assign(n, nullptr);
+    std::vector<std::string> mesh_names;
+    for (auto &kv : c.meshes) kv.second->generateNormals(), mesh_names.push_back(kv.first);
+    std::vector<int32_t> owner(c.instances.size());
+    for (size_t k = 0; k < owner.size(); ++k) owner[k] = domain ? (int32_t)(k % (size_t)n) : 0; // mpiInstanceMap, DomainTracer.h:140
+    std::vector<std::string> errs(n);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n; ++g)
+      th.emplace_back([&, g] {
+        auto bad = [&](const char *what) { errs[g] = std::string(what) + ": " + gvtb200_last_error(); };
+        if (gvtb200_init(g) != GVTB200_OK) return bad("gvtb200_init");
+        for (size_t mi = 0; mi < mesh_names.size(); ++mi) { // ImageScheduler: every mesh; DomainScheduler: the meshes of owned instances
+          bool need = !domain;
+          for (size_t k = 0; k < c.instances.size() && !need; ++k) need = owner[k] == g && c.instances[k].mesh == mesh_names[mi];
+          if (!need) continue;
+          Mesh &m = *c.meshes[mesh_names[mi]];
+          gvtb200_material mm;
+          mm.type = m.mat.type, memcpy(mm.kd, m.mat.kd, 12), memcpy(mm.ks, m.mat.ks, 12), mm.alpha = m.mat.alpha;
+          std::vector<gvtb200_material> fm(m.faces_to_materials.size());
+          const size_t nf = m.faces.size() / 3;
+          std::vector<int32_t> fidx;
+          for (size_t i = 0; i < fm.size(); ++i) {
+            const Material &q = m.faces_to_materials[i];
+            fm[i].type = q.type, memcpy(fm[i].kd, q.kd, 12), memcpy(fm[i].ks, q.ks, 12), fm[i].alpha = q.alpha;
+          }
+          if (!fm.empty()) {
+            fidx.resize(nf);
+            for (size_t i = 0; i < nf; ++i) fidx[i] = i < fm.size() ? (int32_t)i : -1;
+          }
+          const bool vc = !m.vertex_colors.empty() && m.vertex_colors.size() == m.vertices.size();
+          if (gvtb200_mesh_create(&m.vertices[0].x, (uint32_t)m.vertices.size(), m.faces.data(), (uint32_t)nf,
+                                  m.normals.size() == m.vertices.size() ? &m.normals[0].x : nullptr, &mm, fm.empty() ? nullptr : fm.data(),
+                                  (uint32_t)fm.size(), fidx.empty() ? nullptr : fidx.data(), vc ? &m.vertex_colors[0].x : nullptr,
+                                  &M.meshes[g][mi]) != GVTB200_OK)
+            return bad("mesh build");
+        }
+        if (gvtb200_scene_create(&M.scenes[g]) != GVTB200_OK) return bad("scene");
+        for (const Instance &in : c.instances) {
+          const size_t mi = std::find(mesh_names.begin(), mesh_names.end(), in.mesh) - mesh_names.begin();
+          if (gvtb200_scene_add_instance(M.scenes[g], M.meshes[g][mi], in.m, in.minv, in.normi, in.lo, in.hi) < 0) return bad("instance");
+        }
+        if (domain && gvtb200_domain_set_owner(M.scenes[g], owner.data(), (int)owner.size(), g, n) != GVTB200_OK) return bad("owner");
+      });
+    for (auto &t : th) t.join();
+    for (auto &e : errs)
+      if (!e.empty()) throw std::runtime_error("multi-GPU setup: " + e);
+    for (auto &kv : c.meshes) kv.second->dirty = false;
+    c.instances_dirty = false;
+    if (c.scene) gvtb200_scene_destroy(c.scene), c.scene = nullptr; // the single-GPU scene is rebuilt on demand
+    c.instances_dirty = false;
+  }
+  // per-frame parameters, then (first frame) the commit and the peer mapping
+  std::vector<gvtb200_light> ls;
+  for (auto &l : c.lights) ls.push_back(l.l);
+  const unsigned flags = c.flags | (r.adapter == gvt::render::adapter::EmbreeStream ? (unsigned)GVTB200_FLAG_SMOOTH : 0u);
+  for (int g = 0; g < n; ++g) {
+    gvtb200_scene sc = M.scenes[g];
+    if (gvtb200_scene_set_lights(sc, ls.data(), (int)ls.size()) != GVTB200_OK) engine_error("lights");
+    if (gvtb200_scene_set_camera(sc, cr.eye, cr.focus, cr.up, cr.fov, cr.depth, cr.samples, cr.jitter) != GVTB200_OK) engine_error("camera");
+    if (gvtb200_scene_set_film(sc, fr.w, fr.h) != GVTB200_OK) engine_error("film");
+    if (gvtb200_scene_set_flags(sc, flags, c.seed) != GVTB200_OK) engine_error("flags");
+  }
+  if (!M.attached) {
+    std::vector<gvtb200_peer_desc> descs(n);
+    for (int g = 0; g < n; ++g) {
+      if (gvtb200_scene_commit(M.scenes[g]) != GVTB200_OK) engine_error("commit");
+      if (gvtb200_p2p_export(M.scenes[g], n, &descs[g]) != GVTB200_OK) engine_error("p2p export");
+    }
+    for (int g = 0; g < n; ++g)
+      if (gvtb200_p2p_attach(M.scenes[g], g, n, descs.data()) != GVTB200_OK) engine_error("p2p attach");
+    M.attached = true;
+  }
+}
+
+void render_multi(const RendererRec &r, int n) {
+  Context &c = db();
+  multi_build(r, n);
+  Context::Multi &M = c.multi;
+  const FilmRec &fr = c.films.at(r.film);
+  c.fb.assign((size_t)fr.w * fr.h * 4, 0.f);
+  c.fbw = fr.w, c.fbh = fr.h;
+  const int tile_rows = 8;
+  Barrier bar(n);
+  std::vector<unsigned long long> exported(n, 0);
+  std::vector<std::string> errs(n);
+  std::vector<std::thread> th;
+  for (int g = 0; g < n; ++g)
+    th.emplace_back([&, g] {
+      gvtb200_scene sc = M.scenes[g];
+      bool ok = true;
+      auto check = [&](int rc, const char *what) {
+        if (rc != GVTB200_OK && errs[g].empty()) errs[g] = std::string(what) + ": " + gvtb200_last_error(), ok = false;
+      };
+      switch (r.schedule) {
+      case gvt::render::scheduler::Domain: { // Tracer<DomainScheduler>::operator(), DomainTracer.h:185-368
+        check(gvtb200_domain_begin_frame(sc), "domain_begin_frame");
+        check(gvtb200_scene_sync(sc), "sync");
+        bar.wait();
+        unsigned long long before = 0;
+        for (int round = 0; round < 100000; ++round) {
+          void *d_total = nullptr;
+          check(gvtb200_domain_round_p2p(sc, round, &d_total), "domain_round_p2p");
+          check(gvtb200_scene_sync(sc), "sync");
+          gvtb200_counters ctr;
+          check(gvtb200_scene_counters(sc, &ctr), "counters");
+          exported[g] = ok ? ctr.rays_exported : ~0ull;
+          bar.wait(); // every rank's round is over: what it stored into its peers is visible
+          unsigned long long total = 0;
+          bool any_bad = false;
+          for (int k = 0; k < n; ++k) total += exported[k], any_bad |= exported[k] == ~0ull;
+          bar.wait(); // everybody has read the counts before anybody overwrites them
+          if (any_bad || total == before) break; // no ray changed rank in this round: nothing is in flight (DomainTracer.h:339-349)
+          before = total;
+        }
+        if (g != 0) check(gvtb200_domain_composite_p2p(sc, 0), "composite"); // peers first: the root's call waits for them
+        bar.wait();
+        if (g == 0) check(gvtb200_domain_composite_p2p(sc, 0), "composite");
+        check(gvtb200_scene_sync(sc), "sync");
+        bar.wait();
+        check(gvtb200_framebuffer_read_rows(sc, c.fb.data(), tile_rows, g, n, 0), "read_rows");
+        break;
+      }
+      case gvt::render::scheduler::AsyncDomain: // the persistent scheduler (tracer/Domain/DomainTracer.cpp:109-192 is its relative)
+        check(gvtb200_domain_frame_persist(sc, 0, tile_rows), "domain_frame_persist");
+        check(gvtb200_scene_sync(sc), "sync");
+        bar.wait(); // the root's image is complete (and clamped) when the root's kernel has ended
+        check(gvtb200_framebuffer_read_rows(sc, c.fb.data(), tile_rows, g, n, 0), "read_rows");
+        break;
+      default: // Image, AsyncImage: Tracer<ImageScheduler>::operator(), ImageTracer.h:127-269
+        check(gvtb200_render_frame_tiles(sc, 0, fr.h, tile_rows, g, n), "render_frame_tiles");
+        check(gvtb200_framebuffer_read_rows(sc, c.fb.data(), tile_rows, g, n, -1), "read_rows");
+        break;
+      }
+      check(gvtb200_scene_sync(sc), "sync");
+    });
+  for (auto &t : th) t.join();
+  for (auto &e : errs)
+    if (!e.empty()) throw std::runtime_error("multi-GPU render: " + e);
 }
 
 } // namespace
@@ -442,12 +643,13 @@ void *engineScene(std::string name) {
 }
 
 // gvtRenderer::render (Renderer.cpp:106-115): camera rays + Tracer<...>::operator() + composite, all on the device.
-// A single process owns every instance, so scheduler::Domain degenerates to the image path exactly as one MPI rank
-// does in the reference; multi-GPU domain frames are driven through gvtb200_domain_* (one process per GPU).
+// On one GPU a single rank owns every instance, so scheduler::Domain degenerates to the image path exactly as one MPI rank
+// does in the reference; with api::setGpus(n > 1) the schedule type picks the multi-GPU tracer (render_multi above).
 void render(std::string name) {
   auto it = db().renderers.find(name);
   if (it == db().renderers.end()) throw std::runtime_error("Suplied renderer " + name + " is not valid");
   if (it->second.volume) throw std::runtime_error("volume rendering is not supported by this engine");
+  if (db().gpus > 1) return render_multi(it->second, db().gpus);
   gvtb200_scene s = device_scene(it->second);
   Context &c = db();
   const FilmRec &f = c.films[it->second.film];
@@ -463,6 +665,11 @@ const std::vector<float> &framebuffer(int *width, int *height) {
   return db().fb;
 }
 void setEngineFlags(unsigned flags, unsigned seed) { db().flags = flags, db().seed = seed; }
+void setGpus(int n) {
+  if (n < 1 || n > 16) throw std::runtime_error("setGpus: 1..16 GPUs");
+  if (n != db().gpus) db().drop_multi();
+  db().gpus = n;
+}
 
 // IceTComposite::write (composite/IceTComposite.cpp:119-158): P6, rows bottom-to-top, (unsigned char)(c*255)
 void writeimage(std::string name, std::string output) {
@@ -559,6 +766,7 @@ GAPI int gvtapi_add_renderer(const char *n, int adapter, int schedule, const cha
   return guard([&] { api::addRenderer(n, adapter, schedule, cam, film); });
 }
 GAPI int gvtapi_render(const char *n) { return guard([&] { api::render(n); }); }
+GAPI int gvtapi_set_gpus(int n) { return guard([&] { api::setGpus(n); }); }
 GAPI int gvtapi_writeimage(const char *n, const char *out) { return guard([&] { api::writeimage(n, out); }); }
 GAPI int gvtapi_set_engine_flags(unsigned flags, unsigned seed) { return guard([&] { api::setEngineFlags(flags, seed); }); }
 GAPI int gvtapi_framebuffer(float *rgba, size_t n_floats, int *w, int *h) {

@@ -69,6 +69,11 @@ const std::vector<float> &framebuffer(int *width = nullptr, int *height = nullpt
 void gvtReset();
 // the ObjReader path (data/reader/ObjReader.cpp:192-194): 0-based faces pushed without addFace's filter
 void addMeshTriangles0(const std::string name, const unsigned &n, const unsigned *triangles0);
+// how many GPUs of this process api::render uses (default 1).  With n > 1 the renderer's schedule type selects the multi-GPU
+// tracer, as Renderer.cpp:71-96 selects Tracer<ImageScheduler> / Tracer<DomainScheduler>: Image / AsyncImage = film rows
+// dealt over the GPUs with the geometry replicated, Domain = instance k on GPU k % n with exchange rounds over NVLink,
+// AsyncDomain = the persistent scheduler.  One host thread per GPU; the image comes back over n PCIe links.
+void setGpus(int n);
 // handle of the device-side scene behind a renderer (for the multi-GPU drivers), built on first use
 void *engineScene(std::string renderer);
 

@@ -11,6 +11,7 @@
 #include <gvt/render/data/Primitives.h>
 #include <gvt/render/data/scene/Light.h>
 
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <tuple>
@@ -96,14 +97,25 @@ public:
       }
       ls.push_back(p);
     }
-    // every input ray can come back, plus one shadow ray per light per bounce level
+    // every input ray can come back, plus one shadow ray per light per bounce level (EmbreeMeshAdapter.cpp:584-601 loops while
+    // depth > 0): n * (1 + lights * max depth).  Should the estimate still be short, gvtb200_trace reports GVTB200_ERR_CAPACITY
+    // with rayList untouched and the call is repeated with a larger buffer.
     const size_t n = end - begin;
+    int max_depth = 1;
+    for (size_t i = begin; i < end; ++i) max_depth = std::max(max_depth, std::min(rayList[i].mice.depth, 64));
+    size_t cap = n * (1 + ls.size() * (size_t)max_depth) + 16;
+    std::vector<gvt::render::actor::Ray> out;
     size_t n_moved = 0;
-    std::vector<gvt::render::actor::Ray> out(n * (2 + 2 * ls.size()) + 16);
-    int rc = gvtb200_trace(handle, reinterpret_cast<gvtb200_ray *>(rayList.data()), rayList.size(), begin, end,
-                           reinterpret_cast<gvtb200_ray *>(out.data()), out.size(), &n_moved, &(*m)[0][0], &(*minv)[0][0],
-                           &(*normi)[0][0], ls.data(), (int)ls.size(), /*flags: HEAD = flat shading*/ 0u, /*seed*/ 0u);
-    if (rc != GVTB200_OK) throw std::runtime_error(gvtb200_last_error());
+    for (int attempt = 0;; ++attempt) {
+      out.resize(cap);
+      n_moved = 0;
+      int rc = gvtb200_trace(handle, reinterpret_cast<gvtb200_ray *>(rayList.data()), rayList.size(), begin, end,
+                             reinterpret_cast<gvtb200_ray *>(out.data()), out.size(), &n_moved, &(*m)[0][0], &(*minv)[0][0],
+                             &(*normi)[0][0], ls.data(), (int)ls.size(), /*flags: HEAD = flat shading*/ 0u, /*seed*/ 0u);
+      if (rc == GVTB200_OK) break;
+      if (rc != GVTB200_ERR_CAPACITY || attempt >= 4) throw std::runtime_error(gvtb200_last_error());
+      cap *= 2;
+    }
     std::lock_guard<std::mutex> lock(_outqueue); // EmbreeMeshAdapter.cpp:619-621
     moved_rays.insert(moved_rays.end(), out.begin(), out.begin() + n_moved);
   }

@@ -22,8 +22,16 @@ def built():
 
 
 @pytest.fixture(scope="session")
-def gpu(built):
+def gpu(built, request):
+    """The product library on a B200.  Under `-m gpu` (the GPU box) a missing device is a hard failure: GPU tests must never
+    pass on a fallback.  In an unfiltered run on a machine without a device the GPU tests are skipped instead."""
     import gravit_b200 as g
 
-    g.init(0)  # raises without a device: GPU tests must never pass on a fallback
+    try:
+        g.init(0)
+    except g.EngineError:
+        expr = request.config.getoption("-m") or ""
+        if "gpu" in expr and "not gpu" not in expr:
+            raise
+        pytest.skip("no CUDA device (run with -m gpu on a B200 box)")
     return g

@@ -218,6 +218,57 @@ def test_adapter_trace_queue_contents_bit_exact(gpu, name, flags):
     mesh.close()
 
 
+@pytest.mark.parametrize("name", ["simple", "bunny70k"])
+def test_reference_side_adapter_runs_for_real(gpu, name):
+    """INTEGRATION.md section 1 executed: gravit_b200/host/gvt_shim/B200MeshAdapter.h compiled against GraviT's OWN headers and
+    linked with GraviT's own Ray.cpp / Mesh.cpp / Light.cpp / Material.cpp / BBox.cpp (oracle/_ref, tests/ref_adapter/harness.cpp):
+    a real gvt::render::data::primitives::Mesh, a real RayVector and a real PointLight go through Adapter::trace
+    (Adapter.h:82-84, EmbreeMeshAdapter.cpp:625-660) on the GPU.  moved_rays and the in-place state of rayList equal the
+    oracle's byte for byte (64-byte payloads; moved_rays as a multiset: the reference's order is nondeterministic)."""
+    import ctypes as C
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libgvt_ref_adapter.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libgvt_ref_adapter.so not built (needs /root/reference at build time)")
+    H = C.CDLL(path)
+    H.refadapter_last_error.restype = C.c_char_p
+    H.refadapter_trace.restype = C.c_long
+    H.refadapter_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_long]
+    d = SCENES[name]()
+    o = oracle_scene(d, 0)  # HEAD's flat shading: what the binding asks for
+    rays = o.camera_rays()
+    nxt, t = o.route(rays, -1)
+    inst = int(np.bincount(nxt[nxt >= 0]).argmax())
+    q = rays[nxt == inst].copy()
+    q["origin"] = q["origin"] + q["direction"] * (t[nxt == inst] * np.float32(0.95))[:, None]
+    mi, m16 = d.instances[inst]
+    mesh = d.meshes[mi]
+    assert mesh.one_based  # the harness feeds Mesh::addFace (1-based, degenerate faces dropped)
+    ro, mo, _ = o.trace(inst, q)
+    verts = np.ascontiguousarray(mesh.verts, np.float32).reshape(-1, 3)
+    tris = np.ascontiguousarray(mesh.tris, np.uint32).reshape(-1, 3)
+    kd = np.asarray(mesh.kd or (0.5, 0.5, 0.5), np.float32)
+    lp = np.ascontiguousarray([p for p, _ in d.lights], np.float32)
+    lc = np.ascontiguousarray([c for _, c in d.lights], np.float32)
+    for begin, end in ((0, 0), (len(q) // 3, len(q))):  # end == 0 means "all" (EmbreeMeshAdapter.cpp:642); then a sub-range
+        rg = q.copy()
+        cap = 4 * len(q) + 16
+        mg = np.zeros(cap, gpu.RAY_DTYPE)
+        n = H.refadapter_trace(verts.ctypes.data, len(verts), tris.ctypes.data, len(tris), kd.ctypes.data, rg.ctypes.data, len(rg), begin, end,
+                               np.ascontiguousarray(m16, np.float32).ctypes.data, lp.ctypes.data, lc.ctypes.data, len(lp), mg.ctypes.data, cap)
+        assert n >= 0, H.refadapter_last_error()
+        mg = mg[:n]
+        if begin == 0:
+            assert n == len(mo) and np.array_equal(sorted_payload(mo), sorted_payload(mg))
+            assert np.array_equal(ro.view(np.uint8).reshape(-1, 80)[:, :64], rg.view(np.uint8).reshape(-1, 80)[:, :64])
+        else:
+            ro2, mo2, _ = o.trace(inst, q[begin:])
+            assert n == len(mo2) and np.array_equal(sorted_payload(mo2), sorted_payload(mg))
+            assert np.array_equal(rg[:begin], q[:begin])  # rays outside [begin, end) are not touched (HeterogeneousMeshAdapter.cpp:69-79)
+            assert np.array_equal(ro2.view(np.uint8).reshape(-1, 80)[:, :64], rg.view(np.uint8).reshape(-1, 80)[begin:, :64])
+
+
 @pytest.mark.parametrize("name,flags", [("simple", 1), ("simple", 0), ("bunny_obj", 1), ("bunny70k", 0)])
 def test_frame_matches_oracle_and_golden(gpu, name, flags):
     full = {"simple": lambda: library.simple_scene(), "bunny_obj": lambda: library.bunny_obj_scene(), "bunny70k": lambda: library.bunny_scene(512, 512)}
@@ -766,6 +817,38 @@ def test_queue_overflow_is_an_error(gpu):
     e.sync()
     assert po.psnr(po.fb_to_ppm_bytes(e.fb_read(d.width, d.height)), po.fb_to_ppm_bytes(ref1)) >= 50.0
     e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("schedule,name", [(0, "Image"), (1, "Domain"), (3, "AsyncDomain")])
+def test_cpp_multi_gpu_tracers_behind_api_render(gpu, schedule, name):
+    """Renderer.cpp:71-96: api::render picks Tracer<ImageScheduler> / Tracer<DomainScheduler> from the renderer's schedule
+    type.  With api::setGpus(n) the C++ host layer drives n GPUs of ONE process (one host thread per GPU, peer access
+    instead of IPC, no torch, no MPI): the 25-instance golden scene rendered on 2 (and, if present, 4) GPUs equals the oracle's
+    single-process image, for every schedule type.  Needs >= 2 GPUs (skipped on a single-GPU box)."""
+    import torch
+
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    g = gpu
+    d = library.simple_scene(256, 256)
+    o = oracle_scene(d, 1)
+    ref, st = o.render(schedule=0, world_size=1, threads=8)
+    s = library.apply(d, g.GvtScene(flags=1))
+    one = s.render()
+    assert np.array_equal(one, ref)
+    s.set_schedule(schedule)
+    try:
+        for n in sorted({2, min(4, n_dev)}):
+            s.set_gpus(n)
+            for frame in range(2):
+                fb = s.render()
+                assert np.allclose(fb, ref, atol=1e-6), (n, frame, float(np.abs(fb - ref).max()))
+                assert po.image_diff(po.fb_to_ppm_bytes(fb), po.fb_to_ppm_bytes(ref)) == 0
+    finally:
+        s.set_gpus(1)
+    assert np.array_equal(s.render(), ref)  # and back on one GPU
 
 
 @pytest.mark.gpu

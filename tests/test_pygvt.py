@@ -76,14 +76,12 @@ def _build_simple_with_pygvt(gvt, adapter, w, h):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("adapter,smooth", [("Embree", 0), ("EmbreeStream", 1), ("B200", 0)])
-def test_pygvt_simple_scene_adapter_types(adapter, smooth, tmp_path):
+def test_pygvt_simple_scene_adapter_types(gpu, adapter, smooth, tmp_path):
     """adapter::Embree is HEAD's FLAT_SHADING build (EmbreeMeshAdapter.cpp:75); adapter::EmbreeStream has no such define
     (EmbreeStreamMeshAdapter.cpp:931-946) and therefore reproduces the reference's golden image, which predates the
     define.  Both must equal the oracle bit for bit."""
-    import gravit_b200 as g
     import gravit_b200.pygvt as gvt
 
-    g.init(0)
     d = _build_simple_with_pygvt(gvt, getattr(gvt, adapter), 512, 512)
     gvt.render("Renderer")
     fb = gvt.framebuffer()
