@@ -277,6 +277,7 @@ def main():
     ap.add_argument("--owner", default="mod", choices=["mod", "balanced"], help="gyroid: brick k on rank k mod N (the reference's map) or the view-balanced placement")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1, ImageScheduler headline: weak = the film grows by sqrt(N) per axis so every rank keeps the N = 1 "
                     "ray count (same scene, camera and aspect); strong = the N = 1 film split over the ranks")
+    ap.add_argument("--replica-sweep", default="1,2,3,99", help="gyroid, persistent scheduler, local-first policy: replica counts per rank to time (99 = everything everywhere); '' = none")
     ap.add_argument("--replicas", type=int, default=1, help="gyroid, persistent scheduler: BLAS copies of other ranks' bricks a rank may hold (0 = the owner alone serves a brick)")
     ap.add_argument("--shade-sms", type=int, default=0, help="persistent scheduler: SMs that shade instead of tracing (0 = default)")
     ap.add_argument("--gyroid-res", type=int, default=library.GYROID_RES_100M, help="grid cells per axis of the gyroid volume (946 = 100 M triangles)")
@@ -483,7 +484,10 @@ def main():
         res = {"workload": f"gyroid isosurface {n_tris:,} tris in 2x2x2 bricks (res {a.gyroid_res}), 3840x2160, 1 point light, primary+shadow (configs[3])",
                "film": [W, H], "n_tris": n_tris, "owner": [int(x) for x in owner], "scene_build_s": round(build_s, 2), "geometry_generation_s": round(gen_s, 2),
                "blas_build_ms_per_brick_this_rank": [round(x, 1) for x in blas_ms],
-               "blas_build_Mtris_per_s_this_rank": round(n_tris / 8.0 * len(mine) / max(1e-9, sum(blas_ms) * 1e-3) / 1e6, 1)}
+               "blas_build_Mtris_per_s_this_rank": round(n_tris / 8.0 * len(mine) / max(1e-9, sum(blas_ms) * 1e-3) / 1e6, 1),
+               "blas_build_note": "the first build on a rank also grows the stream-ordered memory pool (several GB of scratch) and loads the kernels; the later ones show the build itself"}
+        if len(blas_ms) > 1:
+            res["blas_build_Mtris_per_s_warm_median"] = round(n_tris / 8.0 / (statistics.median(blas_ms[1:]) * 1e-3) / 1e6, 1)
 
         def persist():
             schedulers.render_domain_persist(e, 0, a.tile_rows)
@@ -524,7 +528,16 @@ def main():
                    "queue_overflows": ctr_all["queue_overflows"]}
             return out, ctr_all
 
+        def calibrate(label):
+            """How many SMs shade instead of tracing is a property of the scene (hits per ray, cost of a ray): a few frames per
+            candidate, the fastest stays (a scene-setup step like the server plan; --shade-sms fixes it instead)."""
+            if a.shade_sms:
+                return {"shade_sms": a.shade_sms, "fixed_by": "--shade-sms"}
+            best, tried = schedulers.calibrate_shader_sms(e, persist, lambda f: timed(f, 3, 1)[0])
+            return {"shade_sms": best, "schedule": label, "ms_per_frame_by_shade_sms": {str(k): round(v, 3) for k, v in tried.items()}}
+
         # (1) the persistent scheduler, every brick served by its owner alone
+        res["shader_sm_calibration"] = [calibrate("owner only")]
         base, ctr_all = measure("persistent kernel, brick served by its owner", persist)
         base.update(persist_stats())
         base["progress_ms_vs_fraction_retired"] = progress_curve()
@@ -537,6 +550,30 @@ def main():
         res["persistent_owner_only"] = base
         headline = base
         descs = None
+        install = lambda: e.domain_set_servers(None)  # noqa: E731  (re-installs the headline schedule's server table)
+        ref_img = [None]
+
+        def parity(label):
+            """The N-rank image (root's framebuffer) of the schedule installed now against ONE rank tracing every brick (the
+            others' BLAS mapped over NVLink; rendered once)."""
+            persist()
+            e.sync()
+            barrier()
+            out = None
+            if rank == 0:
+                img = e.fb_read(W, H)
+                if ref_img[0] is None:
+                    full, imported_ref = schedulers.whole_scene_on_one_rank(e, descs, owner, rank, mode=g.IMPORT_MAP)
+                    t1 = time.perf_counter()
+                    ref_img[0], _ = full.render(W, H)
+                    res["parity_reference"] = {"what": "rank 0 alone renders the whole scene through the wave path, the other ranks' bricks traversed through NVLink-mapped BLAS",
+                                               "frame_s": round(time.perf_counter() - t1, 3), "lit_pixels": int((ref_img[0][..., 3] > 0).sum())}
+                    full.close()
+                    del imported_ref
+                out = {"schedule": label, "max_abs_err": float(np.abs(img - ref_img[0]).max())}
+            barrier()
+            return out
+
         if world > 1:
             # (2) shared BLAS: a counted frame gives the load per brick, the plan spreads the hot bricks over idle ranks
             e.profile_counters(True)
@@ -548,45 +585,88 @@ def main():
             res["cycle_profile_owner_only_counted_frame"] = prof
             e.profile_counters(False)
             load = np.array(allsum(load))
+            res["node_visits_per_brick"] = [int(x) for x in load]
             descs = schedulers.exchange_mesh_descs(dist, e._keep, e.recipe["inst"], owner, rank, world, dev)
-            if a.replicas > 0:
-                tab_r, tab_w = schedulers.plan_servers(load, owner, world, max_replicas=a.replicas)
-                t1 = time.perf_counter()
-                keep = schedulers.apply_server_plan(e, tab_r, tab_w, descs, rank, mode=g.IMPORT_COPY)
-                torch.cuda.synchronize()
-                barrier()
-                shared, _ = measure(f"persistent kernel, <= {a.replicas} BLAS replica(s) of other ranks' bricks per rank (copied from the owner over NVLink)", persist)
-                shared.update(persist_stats())
-                shared["progress_ms_vs_fraction_retired"] = progress_curve()
+            parities = [parity("owner only")]
+            imported = {}
+            brick_bytes = [0.0]
+
+            def counted_profile():
                 e.profile_counters(True)
                 persist()
                 e.sync()
                 prof = [None] * world
                 dist.all_gather_object(prof, e.domain_persist_profile())
-                shared["cycle_profile_counted_frame"] = prof
                 e.profile_counters(False)
+                return prof
+
+            if a.replicas > 0:
+                tab_r, tab_w = schedulers.plan_servers(load, owner, world, max_replicas=a.replicas)
+                t1 = time.perf_counter()
+                free0 = torch.cuda.mem_get_info()[0]
+                imported.update(schedulers.apply_server_plan(e, tab_r, tab_w, descs, rank, mode=g.IMPORT_COPY))
+                torch.cuda.synchronize()
+                if imported:
+                    brick_bytes[0] = (free0 - torch.cuda.mem_get_info()[0]) / len(imported)
+                barrier()
+                res["shader_sm_calibration"].append(calibrate("shared BLAS, by hash"))
+                shared, _ = measure(f"persistent kernel, <= {a.replicas} BLAS replica(s) of other ranks' bricks per rank (copied from the owner over NVLink), every ray of a brick goes to one of its servers by hash", persist)
+                shared.update(persist_stats())
+                shared["progress_ms_vs_fraction_retired"] = progress_curve()
+                shared["cycle_profile_counted_frame"] = counted_profile()
                 shared.update(servers=[[int(x) for x in row if x >= 0] for row in tab_r], shares=[[round(float(w), 3) for w, x in zip(wr, row) if x >= 0] for wr, row in zip(tab_w, tab_r)],
-                              node_visits_per_brick=[int(x) for x in load], replica_setup_s=round(time.perf_counter() - t1, 3))
+                              replica_setup_s=round(time.perf_counter() - t1, 3))
                 res["persistent_shared_blas"] = shared
+                parities.append(parity("shared BLAS, by hash"))
                 if shared["ms_per_frame"] < headline["ms_per_frame"]:
                     headline = shared
-        # parity: the N-rank image (root's framebuffer) against ONE rank tracing every brick (the others' BLAS mapped over NVLink)
-        persist()
-        e.sync()
-        barrier()
-        if world > 1:
-            if rank == 0:
-                img = e.fb_read(W, H)
-                full, imported = schedulers.whole_scene_on_one_rank(e, descs, owner, rank, mode=g.IMPORT_MAP)
+                    install = lambda: e.domain_set_servers(tab_r, tab_w)  # noqa: E731
+            # (2b) local first: a rank that holds a brick keeps the rays that meet it there; replicas per rank swept up to
+            # "everything everywhere" (no ray leaves its rank: the ImageScheduler's data layout under the DomainScheduler)
+            full_r = 8 - min(int((np.asarray(owner) == r).sum()) for r in range(world))
+            sweep = sorted({min(int(x), full_r) for x in a.replica_sweep.split(",") if x.strip()}) if a.replica_sweep else []
+            res["replication_sweep"] = []
+            per_brick = allsum([brick_bytes[0]], dist.ReduceOp.MAX)[0]
+            for R in sweep:
+                if R <= 0:
+                    continue
+                holders, share = schedulers.plan_holders(load, owner, world, max_replicas=R)
                 t1 = time.perf_counter()
-                ref, _ = full.render(W, H)
-                res["parity"] = {"max_abs_err": float(np.abs(img - ref).max()), "lit_pixels": int((ref[..., 3] > 0).sum()),
-                                 "reference": "rank 0 alone renders the whole scene through the wave path, the other ranks' bricks traversed through NVLink-mapped BLAS",
-                                 "reference_frame_s": round(time.perf_counter() - t1, 3)}
-                full.close()
-                del imported
-            barrier()
+                free0 = torch.cuda.mem_get_info()[0]
+                n0 = len(imported)
+                imported = schedulers.apply_holder_plan(e, holders, share, descs, rank, owner, mode=g.IMPORT_COPY, imported=imported)
+                torch.cuda.synchronize()
+                if len(imported) > n0 and not per_brick:
+                    per_brick = (free0 - torch.cuda.mem_get_info()[0]) / (len(imported) - n0)
+                barrier()
+                setup_s = time.perf_counter() - t1
+                rl, moved = schedulers.planned_rank_load_local(load, holders, share, world)
+                m, _ = measure(f"persistent kernel, local first, <= {R} BLAS replica(s) of other ranks' bricks per rank", persist)
+                m.update(persist_stats())
+                held = [sum(1 for h in holders if r in h) for r in range(world)]
+                m.update(replicas_per_rank=R, bricks_held_per_rank=held, everything_everywhere=all(len(h) == world for h in holders),
+                         holders=[[int(x) for x in h] for h in holders], planned_max_rank_load_over_mean=round(float(rl.max() * world), 3),
+                         planned_fraction_of_brick_visits_that_start_with_a_transfer=round(float(moved), 3), replica_setup_s=round(setup_s, 3))
+                if R == sweep[-1] or R == a.replicas:
+                    m["progress_ms_vs_fraction_retired"] = progress_curve()
+                    m["cycle_profile_counted_frame"] = counted_profile()
+                p_ = parity(f"local first, {R} replica(s)")
+                parities.append(p_)
+                m["parity_max_abs_err"] = p_["max_abs_err"] if p_ else None
+                res["replication_sweep"].append(m)
+                # the headline stays a PARTITIONED scene: at most --replicas copies per rank
+                if R <= a.replicas and m["ms_per_frame"] < headline["ms_per_frame"]:
+                    headline = m
+                    install = (lambda hh, ss: (lambda: e.domain_set_servers(*schedulers.server_table_for_rank(hh, ss, rank))))(holders, share)
+            per_brick = allsum([per_brick], dist.ReduceOp.MAX)[0]
+            res["blas_GB_per_brick"] = round(per_brick / 1e9, 3)
+            if rank == 0:
+                res["parity"] = {"max_abs_err": max(p_["max_abs_err"] for p_ in parities), "per_schedule": parities, **res.get("parity_reference", {})}
+                ref = ref_img[0]
         else:
+            persist()
+            e.sync()
+            barrier()
             img = e.fb_read(W, H)
             ref, _ = e.render(W, H)  # the wave path on the same scene
             res["parity"] = {"max_abs_err": float(np.abs(img - ref).max()), "lit_pixels": int((ref[..., 3] > 0).sum()), "reference": "the wave path (k_trace / k_shade launches) on the same scene"}
@@ -635,8 +715,8 @@ def main():
             else:
                 res["roofline"] = {"frac": None, "note": "no ncu capture of these kernel sources for this workload (" + str(cap_src) + ")"}
         # ---- end to end: frame + parallel read-back of the root's image ---------------------------------------------------
-        if world > 1 and a.replicas > 0 and headline is res.get("persistent_shared_blas"):
-            e.domain_set_servers(tab_r, tab_w)
+        if world > 1:
+            install()
         host, host_np, cleanup, pinned = shared_host_image(dist, rank, world, H, W)
         use_waves = world == 1 and headline is res.get("waves")
         e2e_ms = []

@@ -85,7 +85,8 @@ GVT_HD float fastmin(float a, float b) { return (a < b) ? a : b; }
 GVT_HD float fastmax(float a, float b) { return (a > b) ? a : b; }
 
 #define GVT_RAY_EPSILON 1.e-6f /* actor/Ray.cpp:33 */
-enum { RAY_PRIMARY = 0, RAY_SHADOW = 1, RAY_SECONDARY = 2 };
+enum { RAY_PRIMARY = 0, RAY_SHADOW = 1, RAY_SECONDARY = 2,
+       RAY_CAMERA_REF = 3 }; // (inbound queues of the persistent DomainScheduler only: a camera ray sent as its index, see k_persist)
 enum { FLAG_SMOOTH = 1, FLAG_ENTER_INSIDE = 2, FLAG_SHADOW_TO_LIGHT = 8 };
 
 // ---- the ray, as held in registers -----------------------------------------------------------------------

@@ -269,7 +269,7 @@ int scan_inplace(unsigned *d, size_t n, std::vector<unsigned *> &levels, size_t 
   return 0;
 }
 
-TraceTune g_tune = { 16, 20, 2, 2, 0, 16 };
+TraceTune g_tune = { 16, 20, 2, 2, 0, 16, 24 };
 
 int trace_grid(int dev, bool count) {
   DevState &D = g_dev[dev];
@@ -495,6 +495,7 @@ int gvtb200_init(int device) {
   if (const char *e = getenv("GVTB200_PEER_TIMEOUT_MS")) gvtb200_set_peer_timeout_ms(atoi(e));
   if (const char *e = getenv("GVTB200_TAIL_PREFETCH")) gvtb200_set_tail_prefetch(atoi(e));
   if (const char *e = getenv("GVTB200_TAIL_SPLIT")) gvtb200_set_tail_split(atoi(e));
+  if (const char *e = getenv("GVTB200_PERSIST_TRIPS")) g_tune.persist_trips = std::max(1, atoi(e)); // (measurement hook)
   CU(cudaFree(0));
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { // keep up to 8 GiB of freed build scratch in the pool

@@ -594,6 +594,7 @@ struct TraceTune {
   int prefetch_below; // lanes: a warp with at most this many traversing lanes prefetches the siblings it pushes (0 = never)
   int split_below;    // persistent kernel: a warp with at most this many traversing lanes shares out the stacks of its rays
                       // among its free lanes (0 = never)
+  int persist_trips;  // persistent kernel: lock-step iterations after which a warp looks at its inbox again at the latest
 };
 
 struct CameraGen { // in-kernel camera-ray source (replaces reading a queue of camera rays back from HBM)
@@ -649,9 +650,9 @@ struct SmemStack {
 // should go back to its caller: all lanes are finished, or at least tune.exit_at lanes are not traversing and there is
 // something better to do for them (`resting` = lanes that had no ray on entry; a lane outside `resting` that stopped
 // traversing has a finished ray to hand over; more_input = the caller can refill).  Returns this lane's `done`.
-// BUDGET > 0: return after that many iterations at the latest (the persistent kernel must look at its inbox now and then).
-template <bool COUNT, int BUDGET, class Stack>
-__device__ __forceinline__ bool warp_traverse(bool active, unsigned resting, bool more_input, const TraceTune &tune, const float4 *nodes,
+// BUDGETED: return after `budget` iterations at the latest (the persistent kernel must look at its inbox now and then).
+template <bool COUNT, bool BUDGETED, class Stack>
+__device__ __forceinline__ bool warp_traverse(bool active, unsigned resting, bool more_input, int budget, const TraceTune &tune, const float4 *nodes,
                                               const float4 *tris, const RayLocal &rl, float tfar, bool any, Trav &tv, Stack &stack,
                                               TravCounters &tc, const unsigned char *s_lut) {
   const unsigned FULL = 0xffffffffu;
@@ -663,8 +664,8 @@ __device__ __forceinline__ bool warp_traverse(bool active, unsigned resting, boo
     if (tm == 0u) break;
     const unsigned waiting = 32u - (unsigned)__popc(tm);
     // (the persistent kernel always advances one step per call: its callers' lanes can rest in states a refill cannot end)
-    if ((BUDGET == 0 || trips > 0) && waiting >= (unsigned)tune.exit_at && ((~tm & ~resting) != 0u || more_input)) break;
-    if (BUDGET > 0 && ++trips > BUDGET) break;
+    if ((!BUDGETED || trips > 0) && waiting >= (unsigned)tune.exit_at && ((~tm & ~resting) != 0u || more_input)) break;
+    if (BUDGETED && ++trips > budget) break;
     const bool pf = __popc(tm) <= tune.prefetch_below;
     if (trav) {
 #pragma unroll 1
@@ -807,7 +808,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
       continue;
     }
     // ---- traverse in lock step ---------------------------------------------------------------------------
-    const bool done = warp_traverse<COUNT, 0>(active, idle, !exhausted, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
+    const bool done = warp_traverse<COUNT, false>(active, idle, !exhausted, 0, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
     // ---- rays that finished their instance -------------------------------------------------------------------
     if (active && done) {
       if (tv.hit.prim >= 0) {
@@ -895,9 +896,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
   }
 }
 
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 4
+#endif
 // k_shade: one thread per closest hit.  Surface data, Shade() per light -> shadow rays into `shq`, the bounce decision ->
 // the secondary ray into `nxq` (EmbreeMeshAdapter.cpp:491-601).  Fully coherent: every lane of a warp shades.
-__global__ void __launch_bounds__(256) k_shade(FrameParams fp, SceneDev sd, ShadeQueues q, int mode) {
+__global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(FrameParams fp, SceneDev sd, ShadeQueues q, int mode) {
   const unsigned n = min(*q.hq.count, q.hq.cap);
   const bool to_light = (fp.flags & FLAG_SHADOW_TO_LIGHT) != 0;
   unsigned long long c_hits = 0, c_shgen = 0, c_sec = 0, c_qovf = 0;
@@ -1199,9 +1203,6 @@ __global__ void k_fb_accumulate_root(const float4 *src, float *dst, size_t npix,
 #ifndef PERSIST_MIN_BLOCKS
 #define PERSIST_MIN_BLOCKS 6
 #endif
-#ifndef PERSIST_TRIPS
-#define PERSIST_TRIPS 24
-#endif
 struct PersistParams {
   RayQueue inbox;             // this rank's inbound slots (count unused: PersistCtl::tail / head)
   RayQueue hitq;              // this rank's closest hits: ray + hit column, ticketed like the inbox (hit_tail / hit_head)
@@ -1252,6 +1253,12 @@ __device__ __forceinline__ int ld_strong_i32(const int *p) {
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// release as ONE fence and any number of relaxed stores (st.release is MEMBAR + store, once per flag)
+__device__ __forceinline__ void fence_release(bool far) {
+  if (far) asm volatile("fence.acq_rel.sys;" ::: "memory"); else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned *p, unsigned v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_relaxed_gpu(unsigned *p, unsigned v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_release_sys_add(unsigned *p, unsigned v) { asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -1371,12 +1378,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
   bool far0 = false, far1 = false;
   auto publish = [&]() {
     if (pend0) {
-      if (far0) st_release_sys(pend0, seq); else st_release_gpu(pend0, seq);
+      fence_release(far0 || (pend1 && far1)); // one fence orders the payload of both
+      if (far0) st_relaxed_sys(pend0, seq); else st_relaxed_gpu(pend0, seq);
       pend0 = nullptr;
-    }
-    if (pend1) {
-      if (far1) st_release_sys(pend1, seq); else st_release_gpu(pend1, seq);
-      pend1 = nullptr;
+      if (pend1) {
+        if (far1) st_relaxed_sys(pend1, seq); else st_relaxed_gpu(pend1, seq);
+        pend1 = nullptr;
+      }
     }
   };
   auto pend_add = [&](unsigned *flag, bool far) {
@@ -1440,6 +1448,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
     // ray: {first instance, destination | position in the warp's reservation << 8}, {d.x, d.y}, {d.z, routing distance}
     uint2 *note = s_stack + threadIdx.x;
     static_assert(3 * CAM_CHUNK <= TRACE_SM_STACK, "camera notes must fit the shared stack");
+    // A camera ray is a function of its index and the camera every rank holds: another rank gets the index, not the record --
+    // the first hop of 7/8 of the primary rays is what fills the NVLink ports at the start of a frame
+    const bool cam_ref = pp.fb_pix * (size_t)(fp.cam.samples * fp.cam.samples) < 0x7FFFFFFFull;
     for (size_t it0 = 0; (it0 * n_warps) * 32 < pp.cam_count; it0 += CAM_CHUNK) {
       if (threadIdx.x - first_worker < GVT_P2P_MAX) s_cnt[threadIdx.x - first_worker] = 0u;
       cta_sync();
@@ -1485,7 +1496,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         const RayQueue q = dest == me ? pp.inbox : pp.peer_inbox[dest];
         const unsigned pos = s_base[dest] + (nt.y >> 8);
         if (pos < q.cap) {
-          queue_store(q, pos, r, (int)nt.x);
+          if (dest == me || !cam_ref) {
+            queue_store(q, pos, r, (int)nt.x);
+          } else { // 20 bytes over NVLink instead of 68: the index, the routing distance and the instance (see start_landed)
+            q.c3[pos] = make_int4((int)(unsigned)cam_index(i), (int)n2.y, 0, RAY_CAMERA_REF);
+            q.inst[pos] = (int)nt.x;
+          }
           if (dest != me) dirty = true;
         } else { // the frame fails with GVTB200_ERR_CAPACITY; the count stays balanced so that it still ends
           c_qovf++;
@@ -1495,13 +1511,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         }
       }
       __syncwarp();
+      fence_release(dirty); // one fence per chunk waits for this lane's payload stores; the flags are relaxed stores after it
 #pragma unroll 1
-      for (int j = 0; j < CAM_CHUNK; ++j) { // the first release waits for this lane's payload stores, the others find nothing outstanding
+      for (int j = 0; j < CAM_CHUNK; ++j) {
         const uint2 nt = note[3 * j * TRACE_THREADS];
         if (nt.x == 0xFFFFFFFFu) continue;
         const int dest = (int)(nt.y & 0xFFu);
-        const RayQueue q = dest == me ? pp.inbox : pp.peer_inbox[dest];
-        st_release_sys(q.ready + s_base[dest] + (nt.y >> 8), seq);
+        if (dest == me) st_relaxed_gpu(pp.inbox.ready + s_base[dest] + (nt.y >> 8), seq);
+        else st_relaxed_sys(pp.peer_inbox[dest].ready + s_base[dest] + (nt.y >> 8), seq);
       }
       cta_sync(); // s_cnt / s_base are rewritten by the next chunk
     }
@@ -1520,7 +1537,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
   unsigned iter = 0;
   unsigned long long t_idle0 = 0;
   const unsigned long long t_start = global_ns();
-  enum { L_IDLE = 0, L_WAIT = 1, L_ACTIVE = 2, L_DEAD = 3, L_HELP = 4, L_JOIN = 5 };
+  enum { L_IDLE = 0, L_WAIT = 1, L_ACTIVE = 2, L_DEAD = 3, L_HELP = 4, L_JOIN = 5, L_SEND = 6 };
   int st = L_IDLE;
   unsigned idx = 0; // the lane's ticket: inbox slot (tracer) or hit-queue slot (shader)
 
@@ -1639,6 +1656,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       r.id = c3.x, r.depth = c3.y, r.w = u2f((uint32_t)c3.z), r.type = c3.w;
       r.o = o, r.t_min = t_min, r.d = d, r.t_max = t_max;
     };
+    unsigned landed = 0u; // L_WAIT: the `ready` word of the lane's ticket; L_SEND (group leader): the reserved position
     for (;;) {
       ++iter;
       if ((iter & 4095u) == 0u) { // watchdog: a frame never runs this long (decided by lane 0: the warp leaves together)
@@ -1650,6 +1668,28 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       }
       if (COUNT) pc0 = clock64();
       if (__any_sync(FULL, pend0 != nullptr)) publish(); // what the previous iteration stored: its payload has arrived by now
+      // ---- SendRays, second half: the slots reserved in other ranks' inboxes one iteration ago (see below) have come back
+      if (__any_sync(FULL, st == L_SEND)) {
+        const unsigned base = __shfl_sync(FULL, landed, (team >> 8) & 31);
+        if (st == L_SEND) {
+          const int dest = team & 0xFF;
+          const unsigned pos = base + ((unsigned)team >> 16);
+          const RayQueue q = pp.peer_inbox[dest];
+          if (pos < q.cap) {
+            Ray r;
+            reload(r);
+            queue_store(q, pos, r, inst);
+            pend_add(q.ready + pos, true);
+          } else { // never silently: the frame fails with GVTB200_ERR_CAPACITY; the count stays balanced so that it still ends
+            c_qovf++;
+            atomicOr(&ctl->err, 2u);
+            atomicAdd_system(&pp.mail.m[dest]->pc.consumed, 1u);
+          }
+          dirty = true;
+          c_exp++, c_cons++;
+          st = L_IDLE, team = -1;
+        }
+      }
       // ---- idle lanes draw inbox tickets ---------------------------------------------------------------------------
       const unsigned idle = __ballot_sync(FULL, st == L_IDLE);
       const unsigned tracing = __ballot_sync(FULL, st == L_ACTIVE || st == L_HELP);
@@ -1664,7 +1704,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       }
       // ---- lanes that hold a ticket: has the ray landed?  While other lanes of the warp trace, the question is asked now
       // and the answer is looked at after the traversal burst (an L2 round trip the whole warp would otherwise wait for)
-      unsigned landed = 0u;
+      landed = 0u;
       if (st == L_WAIT) {
         if (idx >= pp.inbox.cap) st = L_DEAD; // beyond the inbox: no ray will ever land there (a producer that finds the inbox full flags the frame)
         else landed = ld_volatile_u32(pp.inbox.ready + idx);
@@ -1672,9 +1712,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       auto start_landed = [&]() {
         if (st == L_WAIT && landed == seq) {
           const float4 c0 = ld_strong_f4(pp.inbox.c0 + idx), c1 = ld_strong_f4(pp.inbox.c1 + idx);
-          type = ld_strong_i32(&pp.inbox.c3[idx].w);
+          const int4 c3 = ld_strong_i4(pp.inbox.c3 + idx);
           inst = ld_strong_i32(pp.inbox.inst + idx);
-          o = v3(c0.x, c0.y, c0.z), t_min = c0.w, d = v3(c1.x, c1.y, c1.z), t_max = c1.w;
+          type = c3.w;
+          if (type == RAY_CAMERA_REF) { // a camera ray of another rank's film shard, sent as (index, routing distance): the
+            Ray r;                      // record is rebuilt here, bit for bit what the sender had, and written into the slot
+            camera_ray(fp.cam, (size_t)(unsigned)c3.x, r);
+            r.o = xadd(fp.cam.eye, xmul(r.d, xmul(u2f((uint32_t)c3.y), 0.95f))); // TracerBase.h:394
+            queue_store(pp.inbox, idx, r, inst);
+            o = r.o, t_min = r.t_min, d = r.d, t_max = r.t_max, type = RAY_PRIMARY;
+          } else {
+            o = v3(c0.x, c0.y, c0.z), t_min = c0.w, d = v3(c1.x, c1.y, c1.z), t_max = c1.w;
+          }
           any = (type == RAY_SHADOW), first = true, st = L_ACTIVE;
           begin_instance();
         }
@@ -1701,7 +1750,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
       t_idle0 = 0;
       long long pc1 = 0;
       if (COUNT) pc1 = clock64(), p_poll += pc1 - pc0;
-      // ---- traverse in lock step (comes back after PERSIST_TRIPS iterations at the latest: tickets get polled and new
+      // ---- traverse in lock step (comes back after tune.persist_trips iterations at the latest: tickets get polled and new
       // arrivals get lanes; whether the inbox holds rays is not known without asking, so it never leaves early for a refill)
       // ---- a nearly empty warp (the tail of the frame: a few long rays, each a chain of hundreds of dependent node visits)
       // shares its rays out: a free lane takes the bottom half of a traversing lane's stack -- the oldest, largest subtrees
@@ -1757,7 +1806,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
         }
       }
       const unsigned resting = __ballot_sync(FULL, st != L_ACTIVE && st != L_HELP);
-      const bool done = warp_traverse<COUNT, PERSIST_TRIPS>(st == L_ACTIVE || st == L_HELP, resting, false, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
+      const bool done = warp_traverse<COUNT, true>(st == L_ACTIVE || st == L_HELP, resting, false, tune.persist_trips, tune, nodes, tris, rl, tfar, any, tv, stack, tc, s_lut);
       long long pc2 = 0;
       if (COUNT) pc2 = clock64(), p_trav += pc2 - pc1;
       // ---- helpers that are done hand their hit to the ray's owner; owners wait for their team --------------------------------
@@ -1841,11 +1890,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, PERSIST_MIN_BLOCKS) k_persist(F
               inst = next;
               begin_instance();
             } else {
-              Ray r;
-              reload(r);
-              send(r, next, dest);
-              c_exp++, c_cons++;
-              st = L_IDLE;
+              // SendRays, first half: the slot in the destination's inbox is reserved now -- one system-scope atomic per
+              // destination and warp, an NVLink round trip -- and used at the top of the next iteration: the answer
+              // travels while the warp traverses instead of stalling it here
+              cg::coalesced_group grp = cg::labeled_partition(cg::coalesced_threads(), dest);
+              const unsigned leader = grp.shfl(lane, 0);
+              if (grp.thread_rank() == 0) landed = atomicAdd_system(&pp.mail.m[dest]->pc.tail, grp.size());
+              team = dest | (int)(leader << 8) | (int)(grp.thread_rank() << 16);
+              inst = next;
+              st = L_SEND;
             }
           }
         }

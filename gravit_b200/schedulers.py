@@ -140,6 +140,21 @@ def render_domain_persist(engine, root=0, tile_rows=8):
     engine.domain_frame_persist(root, tile_rows)
 
 
+def calibrate_shader_sms(engine, frame, time_frames, candidates=(2, 3, 4, 6, 8, 10, 14, 20)):
+    """How many SMs of the persistent kernel shade instead of tracing is a property of the scene (hits per ray against the
+    cost of tracing one): a few frames per candidate, the fastest stays.  A scene-setup step like the server plan.
+    frame(): renders one frame (asynchronous); time_frames(frame) -> ms per frame, the same number on every rank (the
+    caller's max over ranks).  Returns (best, {candidate: ms})."""
+    tried = {}
+    for sm in candidates:
+        engine.domain_persist_config(0, sm)
+        tried[sm] = float(time_frames(frame))
+        engine.sync()
+    best = min(tried, key=tried.get)
+    engine.domain_persist_config(0, best)
+    return best, tried
+
+
 def plan_servers(load, owner, world, max_replicas=1, max_servers=4, slack=1.02):
     """Which ranks serve which instance, and with what share, so that the ranks' loads even out.
 
@@ -219,6 +234,140 @@ def planned_rank_load(load, ranks, weights, world):
             if ranks[k, j] >= 0:
                 rl[ranks[k, j]] += load[k] * w[j]
     return rl
+
+
+def plan_holders(load, owner, world, max_replicas=1, slack=1.02, candidates=8):
+    """Replica placement for the *local first* policy: a rank that holds a copy of a domain traces every ray that meets that
+    domain on this rank itself; only rays that meet a domain the rank does not hold are sent away, to one of the domain's
+    holders chosen by `share`.  Every replica therefore removes ray traffic as well as load from the owner -- with a copy
+    of everything on every rank the DomainScheduler degenerates into the ImageScheduler (no ray leaves its rank), which is
+    what 180 GB of HBM per GPU allow for scenes of a few GB; `max_replicas` (copies of other ranks' domains per rank) is the
+    memory knob in between.  GraviT's `Locations` list (DomainTracer.h:115-144) and its hybrid schedulers ("load the hot
+    domain where the rays are") are the reference's form of this.
+
+    Load model: the demand for domain k arises uniformly over the ranks (camera rays are sharded by interleaved row tiles);
+    rank r gets load[k]/world of it if it holds k, and share[k][r] of the (world - holders)/world part that arises elsewhere.
+    Greedy: the step (rank with room, domain it does not hold) that gives the smallest predicted maximum rank load is taken,
+    ties -- everything within `slack` of the mean counts as balanced -- go to the heaviest domain (most traffic removed);
+    after every step the shares are re-balanced by water-filling.
+    Returns (holders, share): holders[k] = ranks holding k, owner first; share[k] = {rank: share of the non-local demand}."""
+    load = np.asarray(load, np.float64)
+    n = len(load)
+    total = float(load.sum())
+    holders = [[int(owner[k])] for k in range(n)]
+    share = [{int(owner[k]): 1.0} for k in range(n)]
+    if total <= 0 or world < 2:
+        return holders, share
+    L = load / total
+
+    def away(k):  # the part of k's demand that arises on ranks which do not hold it
+        return L[k] * (world - len(holders[k])) / world
+
+    def rank_load():
+        rl = np.zeros(world)
+        for k in range(n):
+            for r in holders[k]:
+                rl[r] += L[k] / world + away(k) * share[k][r]
+        return rl
+
+    def rebalance(sweeps=20):
+        rl = rank_load()
+        for _ in range(sweeps):
+            for k in range(n):
+                a = away(k)
+                if len(holders[k]) < 2 or a <= 0:
+                    continue
+                others = {r: rl[r] - a * share[k][r] for r in holders[k]}
+                lv = sorted(others.values())
+                level = lv[0] + a
+                for m in range(len(lv), 0, -1):  # water level: sum(max(0, level - others)) == a
+                    cand = (a + sum(lv[:m])) / m
+                    if cand >= lv[m - 1]:
+                        level = cand
+                        break
+                for r in holders[k]:
+                    new = max(0.0, level - others[r]) / a
+                    rl[r] += a * (new - share[k][r])
+                    share[k][r] = new
+        return rl
+
+    held = [0] * world
+    heavy = sorted(range(n), key=lambda k: -load[k])
+    floor = slack / world
+    for _ in range(world * max_replicas):
+        best = None
+        for r in range(world):
+            if held[r] >= max_replicas:
+                continue
+            for k in [k for k in heavy if r not in holders[k] and load[k] > 0][:candidates]:
+                saved = [list(holders[j]) for j in range(n)], [dict(share[j]) for j in range(n)]
+                holders[k].append(r)
+                share[k][r] = 0.0
+                worst = max(float(rebalance().max()), floor)
+                key = (round(worst, 6), -load[k], r)
+                if best is None or key < best[0]:
+                    best = (key, r, k)
+                holders[:], share[:] = saved
+        if best is None:
+            break
+        _, r, k = best
+        holders[k].append(r)
+        share[k][r] = 0.0
+        held[r] += 1
+        rebalance()
+    return holders, share
+
+
+def planned_rank_load_local(load, holders, share, world):
+    """Per-rank load (fraction of the frame's) and the fraction of instance visits that start with a ray transfer, as
+    plan_holders' model predicts them."""
+    load = np.asarray(load, np.float64)
+    L = load / max(load.sum(), 1e-30)
+    rl = np.zeros(world)
+    moved = 0.0
+    for k in range(len(load)):
+        a = L[k] * (world - len(holders[k])) / world
+        moved += a
+        for r in holders[k]:
+            rl[r] += L[k] / world + a * share[k].get(r, 0.0)
+    return rl, moved
+
+
+def server_table_for_rank(holders, share, rank, max_servers=4):
+    """The server table rank `rank` installs under the local-first policy (every rank's table is different): a domain the
+    rank holds is served by the rank itself; any other domain by up to `max_servers` of its holders, by share."""
+    n = len(holders)
+    ranks = np.full((n, 4), -1, np.int32)
+    weights = np.zeros((n, 4), np.float32)
+    for k in range(n):
+        if rank in holders[k]:
+            ranks[k, 0], weights[k, 0] = rank, 1.0
+            continue
+        top = sorted(holders[k], key=lambda r: -share[k].get(r, 0.0))[:max_servers]
+        live = [r for r in top if share[k].get(r, 0.0) > 1e-4] or [holders[k][0]]
+        s = sum(share[k].get(r, 0.0) for r in live) or 1.0
+        for j, r in enumerate(live):
+            ranks[k, j], weights[k, j] = r, max(share[k].get(r, 0.0) / s, 1e-4)
+    return ranks, weights
+
+
+def apply_holder_plan(engine, holders, share, descs, rank, owner, mode=0, imported=None):
+    """Import the BLAS of every domain this rank holds without owning it (what is already in `imported` is kept), attach
+    it, re-commit and install this rank's local-first server table.  Returns the dict of imported meshes (keep it alive)."""
+    import gravit_b200 as g
+
+    imported = {} if imported is None else imported
+    fresh = False
+    for k in range(len(holders)):
+        if rank in holders[k] and int(owner[k]) != rank and k not in imported:
+            m = g.Mesh.from_desc(descs[k], mode)
+            engine.set_instance_mesh(k, m)
+            imported[k] = m
+            fresh = True
+    if fresh:
+        engine.commit()
+    engine.domain_set_servers(*server_table_for_rank(holders, share, rank))
+    return imported
 
 
 def exchange_mesh_descs(dist, scene_meshes, instances, owner, rank, world, device="cpu"):

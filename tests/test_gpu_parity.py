@@ -715,6 +715,50 @@ def test_domain_scheduler_persistent_shared_blas(gpu, mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("replicas", [1, 99])
+def test_domain_scheduler_persistent_local_first(gpu, replicas):
+    """Local-first replica plan (schedulers.plan_holders): every rank installs its OWN server table -- itself for the domains
+    it holds, the holders by share for the others.  With a copy of everything everywhere no ray leaves its rank; with one
+    replica per rank fewer do than with the owner alone.  Same image, same counters either way."""
+    from gravit_b200 import schedulers
+
+    g = gpu
+    g.check(g.lib().gvtb200_set_peer_timeout_ms(3000))
+    world = 3
+    d = library.gyroid_scene(48, 2, 320, 240)
+    o = oracle_scene(d, d.flags)
+    ref1, st = o.render(schedule=0, world_size=1, threads=8)
+    ranks, owner = _standalone_ranks(g, d, d.flags, world)
+    _connect(ranks)
+    for e in ranks:
+        e.profile_counters(True)
+    _persist_frame(ranks)
+    load = sum(e.domain_persist_stats(len(d.instances))[2].astype(np.float64) for e in ranks)
+    exported0 = sum(e.counters()["rays_exported"] for e in ranks)
+    for e in ranks:
+        e.profile_counters(False)
+    holders, share = schedulers.plan_holders(load, owner, world, max_replicas=replicas)
+    descs = [ranks[owner[k]]._keep[d.instances[k][0]].export() for k in range(len(d.instances))]
+    keep = [schedulers.apply_holder_plan(e, holders, share, descs, r, owner, mode=g.IMPORT_COPY) for r, e in enumerate(ranks)]
+    assert any(keep)
+    for frame in range(2):
+        _persist_frame(ranks)
+        fb = ranks[0].fb_read(d.width, d.height)
+        assert np.allclose(fb, ref1, atol=1e-6)
+        c = [e.counters() for e in ranks]
+        for k in ("primary_hits", "shadow_generated", "fb_adds"):
+            assert sum(x[k] for x in c) == st[k]
+        exported = sum(x["rays_exported"] for x in c)
+        if replicas == 99:
+            assert all(len(h) == world for h in holders) and exported == 0
+        else:
+            assert 0 < exported < exported0
+    for e in ranks:
+        e.close()
+    del keep
+
+
+@pytest.mark.gpu
 def test_domain_scheduler_persistent_with_bounces_and_lights(gpu):
     """rayMaxDepth 3, two lights, 3 simulated ranks: bounces continue in the lane, extra shadow rays go through the rank's own
     inbound queue, secondary rays migrate.  Random numbers are a function of (ray id, depth), not of who traces the ray, so the

@@ -213,3 +213,39 @@ def test_server_plan_and_mesh_descriptors_world2():
         assert p.exitcode == 0
     assert res[0][1:] == res[1][1:]
     assert any(row[1] >= 0 for row in res[0][1])
+
+
+def test_local_first_replica_plan():
+    """plan_holders: more replicas never move more rays, the predicted load stays near the mean, everything everywhere
+    means no transfer at all, and every rank's table serves the domains it holds itself."""
+    from gravit_b200 import schedulers as s
+
+    load = [550148, 7170928, 6964897, 24289854, 7175614, 18528249, 24262832, 62267103]  # the 100M gyroid's bricks (node visits)
+    for world, owner in ((8, list(range(8))), (4, [0, 1, 2, 1, 3, 2, 3, 0]), (2, [0, 0, 0, 1, 0, 1, 1, 0])):
+        own = max(owner.count(r) for r in range(world))
+        moved_prev = 1.0
+        for R in (0, 1, 2, 3, 8):
+            holders, share = s.plan_holders(load, owner, world, max_replicas=R)
+            rl, moved = s.planned_rank_load_local(load, holders, share, world)
+            assert abs(rl.sum() - 1.0) < 1e-9
+            assert moved <= moved_prev + 1e-12
+            moved_prev = moved
+            for k, h in enumerate(holders):
+                assert h[0] == owner[k] and len(set(h)) == len(h)
+                assert abs(sum(share[k].values()) - 1.0) < 1e-9
+            for r in range(world):
+                assert sum(1 for k, h in enumerate(holders) if r in h and owner[k] != r) <= R
+                tr, tw = s.server_table_for_rank(holders, share, r)
+                for k, h in enumerate(holders):
+                    live = [int(x) for x in tr[k] if x >= 0]
+                    assert live and set(live) <= set(h)
+                    if r in h:
+                        assert live == [r]
+                    assert abs(sum(float(w) for w, x in zip(tw[k], tr[k]) if x >= 0) - 1.0) < 1e-3
+            if R == 0:
+                assert all(len(h) == 1 for h in holders)
+            if R == 1 and world == 8:
+                assert rl.max() * world < 1.1  # one replica per rank is enough to balance the eight bricks
+            if R == 8:
+                assert moved == 0.0 and all(len(h) == world for h in holders) and abs(rl.max() * world - 1.0) < 1e-9
+        assert own >= 1

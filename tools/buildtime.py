@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""BLAS build time / size for the bench meshes and a large gyroid brick.  python tools/buildtime.py [res]"""
+"""BLAS build time / size for the bench meshes and a large gyroid brick.  python tools/buildtime.py [res] [only] [reps]
+`only`: just the gyroid brick (the target of an ncu launch list of one big build)."""
 import os
 import sys
 import time
@@ -13,7 +14,9 @@ from scenes import library  # noqa: E402
 
 g.init(0)
 res = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-cases = [("bunny70k", library.bunny70k_mesh()), ("sibenik", library.sibenik_scene(64, 36).meshes[0])]
+only = len(sys.argv) > 2 and sys.argv[2] == "only"
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+cases = [] if only else [("bunny70k", library.bunny70k_mesh()), ("sibenik", library.sibenik_scene(64, 36).meshes[0])]
 t0 = time.time()
 v, t = library.gyroid_brick(res, (0, 0, 0), 1)
 print(f"gyroid res {res}: {len(t)} tris generated in {time.time()-t0:.1f} s", flush=True)
@@ -21,11 +24,11 @@ cases.append((f"gyroid{res}", library.MeshDesc(v, t, True, None)))
 for name, m in cases:
     verts = np.asarray(m.verts, np.float32).reshape(-1, 3)
     faces = np.asarray(m.tris, np.uint32).reshape(-1, 3) - (1 if m.one_based else 0)
-    for rep in range(2):
+    for rep in range(reps):
         t0 = time.time()
         mesh = g.Mesh(verts, faces)
         wall = time.time() - t0
         st = mesh.stats()
-        if rep == 1:
+        if rep == reps - 1:
             print(name, "tris", len(faces), st, f"wall {wall*1e3:.1f} ms", flush=True)
         mesh.close()
