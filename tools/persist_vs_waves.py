@@ -41,7 +41,8 @@ for name in names:
     modes = next((x[8:].split(",") for x in sys.argv[1:] if x.startswith("--modes=")), ["waves", "persist", "persist_sp0", "persist_sp32"])
     for mode in modes:
         g.check(g.lib().gvtb200_set_tail_split(int(mode.split("_sp")[1]) if "_sp" in mode else 8))
-        for shade_at in ((8,) if mode.startswith("waves") else ((8, 14) if mode == "persist" else (8,))):
+        shade_list = next((tuple(int(v) for v in x[8:].split(",")) for x in sys.argv[1:] if x.startswith("--shade=")), (8, 14))
+        for shade_at in ((8,) if mode.startswith("waves") else (shade_list if mode == "persist" else (8,))):
             if mode.startswith("persist"):
                 e.domain_persist_config(0, shade_at)
             frame = (lambda: e.render_async(d.height)) if mode.startswith("waves") else (lambda: e.domain_frame_persist(0, 8))
