@@ -140,11 +140,17 @@ def render_domain_persist(engine, root=0, tile_rows=8):
     engine.domain_frame_persist(root, tile_rows)
 
 
-def calibrate_shader_sms(engine, frame, time_frames, candidates=(2, 3, 4, 6, 8, 10, 14, 20)):
-    """How many SMs of the persistent kernel shade instead of tracing is a property of the scene (hits per ray against the
-    cost of tracing one): a few frames per candidate, the fastest stays.  A scene-setup step like the server plan.
+def calibrate_shader_sms(engine, frame, time_frames, candidates=(2, 3, 4, 6, 8, 10, 14, 20), splits=(16, 32)):
+    """Two knobs of the persistent kernel are properties of the scene and of how many rays a GPU gets per frame, and are
+    set by timing a few frames per candidate (a scene-setup step like the server plan):
+      * how many SMs shade instead of tracing (hits per ray against the cost of tracing one);
+      * up to how many traversing lanes a warp shares its rays' stacks out to its free lanes (gvtb200_set_tail_split): with
+        rays to spare a free lane is better off waiting for the next refill (16), with few rays per lane -- small films,
+        many GPUs -- every free lane should help (32).
     frame(): renders one frame (asynchronous); time_frames(frame) -> ms per frame, the same number on every rank (the
-    caller's max over ranks).  Returns (best, {candidate: ms})."""
+    caller's max over ranks).  Returns (best shader SMs, {candidate: ms}, best split, {candidate: ms})."""
+    import gravit_b200 as g
+
     tried = {}
     for sm in candidates:
         engine.domain_persist_config(0, sm)
@@ -152,7 +158,14 @@ def calibrate_shader_sms(engine, frame, time_frames, candidates=(2, 3, 4, 6, 8, 
         engine.sync()
     best = min(tried, key=tried.get)
     engine.domain_persist_config(0, best)
-    return best, tried
+    tried_split = {}
+    for sp in splits:
+        g.check(g.lib().gvtb200_set_tail_split(sp))
+        tried_split[sp] = float(time_frames(frame))
+        engine.sync()
+    best_split = min(tried_split, key=tried_split.get)
+    g.check(g.lib().gvtb200_set_tail_split(best_split))
+    return best, tried, best_split, tried_split
 
 
 def plan_servers(load, owner, world, max_replicas=1, max_servers=4, slack=1.02):
