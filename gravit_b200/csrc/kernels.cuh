@@ -896,8 +896,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Frame
   }
 }
 
+// (4 CTAs per SM = 64 registers: sibenik's two k_shade launches 0.22 -> 0.19 ms, but the incoherent 4K / 9 spp frame, where k_shade
+// streams 50 M hits per wave from HBM, 23.7 -> 26.2 ms: 3 it is)
 #ifndef SHADE_MIN_BLOCKS
-#define SHADE_MIN_BLOCKS 4
+#define SHADE_MIN_BLOCKS 3
 #endif
 // k_shade: one thread per closest hit.  Surface data, Shade() per light -> shadow rays into `shq`, the bounce decision ->
 // the secondary ray into `nxq` (EmbreeMeshAdapter.cpp:491-601).  Fully coherent: every lane of a warp shades.

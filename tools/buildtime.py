@@ -24,11 +24,14 @@ cases.append((f"gyroid{res}", library.MeshDesc(v, t, True, None)))
 for name, m in cases:
     verts = np.asarray(m.verts, np.float32).reshape(-1, 3)
     faces = np.asarray(m.tris, np.uint32).reshape(-1, 3) - (1 if m.one_based else 0)
+    us, walls = [], []
     for rep in range(reps):
         t0 = time.time()
         mesh = g.Mesh(verts, faces)
-        wall = time.time() - t0
+        walls.append((time.time() - t0) * 1e3)
         st = mesh.stats()
-        if rep == reps - 1:
-            print(name, "tris", len(faces), st, f"wall {wall*1e3:.1f} ms", flush=True)
+        us.append(st["build_us"])
         mesh.close()
+    warm = sorted(us[1:]) or us
+    print(name, "tris", len(faces), {k: st[k] for k in ("wide_nodes", "depth")}, f"build_us first {us[0]} warm min {warm[0]} median {warm[len(warm)//2]}",
+          f"-> {len(faces) / warm[len(warm)//2]:.1f} Mtris/s; wall median {sorted(walls)[len(walls)//2]:.1f} ms", flush=True)
