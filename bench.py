@@ -533,7 +533,7 @@ def main():
             candidate, the fastest stays (a scene-setup step like the server plan; --shade-sms fixes it instead)."""
             if a.shade_sms:
                 return {"shade_sms": a.shade_sms, "fixed_by": "--shade-sms"}
-            best, tried, split, tried_split = schedulers.calibrate_shader_sms(e, persist, lambda f: timed(f, 3, 1)[0])
+            best, tried, split, tried_split = schedulers.calibrate_shader_sms(e, persist, lambda f: timed(f, 6, 2)[0])
             return {"shade_sms": best, "schedule": label, "ms_per_frame_by_shade_sms": {str(k): round(v, 3) for k, v in tried.items()},
                     "tail_split": split, "ms_per_frame_by_tail_split": {str(k): round(v, 3) for k, v in tried_split.items()}}
 

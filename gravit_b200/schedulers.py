@@ -164,6 +164,8 @@ def calibrate_shader_sms(engine, frame, time_frames, candidates=(2, 3, 4, 6, 8, 
         tried_split[sp] = float(time_frames(frame))
         engine.sync()
     best_split = min(tried_split, key=tried_split.get)
+    if splits and tried_split[best_split] > 0.98 * tried_split[splits[0]]:
+        best_split = splits[0]  # within the noise of a few frames: stay with the first (the default)
     g.check(g.lib().gvtb200_set_tail_split(best_split))
     return best, tried, best_split, tried_split
 
