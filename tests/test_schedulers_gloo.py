@@ -249,3 +249,41 @@ def test_local_first_replica_plan():
             if R == 8:
                 assert moved == 0.0 and all(len(h) == world for h in holders) and abs(rl.max() * world - 1.0) < 1e-9
         assert own >= 1
+
+
+def test_persistent_kernel_calibration_picks_the_fastest():
+    """calibrate_shader_sms: the fastest shader-SM count stays; the stack-sharing width only moves off its default for a
+    gain beyond the noise of a few frames.  (Host logic only: a stand-in engine, no GPU.)"""
+    import gravit_b200 as g
+    from gravit_b200 import schedulers as s
+
+    class Lib:
+        def __init__(self):
+            self.split = None
+
+        def gvtb200_set_tail_split(self, n):
+            self.split = n
+            return 0
+
+    class Engine:
+        def __init__(self):
+            self.sms = None
+
+        def domain_persist_config(self, grid, sms):
+            self.sms = sms
+
+        def sync(self):
+            pass
+
+    lib, e = Lib(), Engine()
+    old_lib, old_check = g.lib, g.check
+    g.lib, g.check = (lambda: lib), (lambda rc: None)
+    try:
+        for gain, want_split in ((0.995, 16), (0.9, 32)):
+            cost = lambda: (abs(e.sms - 6) * 0.1 + 3.0) * (gain if lib.split == 32 else 1.0)  # noqa: E731
+            best, tried, split, tried_split = s.calibrate_shader_sms(e, lambda: None, lambda f: cost())
+            assert best == 6 and e.sms == 6 and set(tried) == {2, 3, 4, 6, 8, 10, 14, 20}
+            assert split == want_split and lib.split == want_split and set(tried_split) == {16, 32}
+            lib.split = None
+    finally:
+        g.lib, g.check = old_lib, old_check
