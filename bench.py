@@ -278,6 +278,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1, ImageScheduler headline: weak = the film grows by sqrt(N) per axis so every rank keeps the N = 1 "
                     "ray count (same scene, camera and aspect); strong = the N = 1 film split over the ranks")
     ap.add_argument("--replica-sweep", default="1,2,3,99", help="gyroid, persistent scheduler, local-first policy: replica counts per rank to time (99 = everything everywhere); '' = none")
+    ap.add_argument("--gyroid-samples", type=int, default=2, help="gyroid: also time the same scene and film with samples^2 rays per pixel (the frame of a GPU at N = 8 holds "
+                    "15 rays per lane at 1 spp: the latency of the longest ray chain, not throughput, is what is measured there); 1 = skip")
     ap.add_argument("--replicas", type=int, default=1, help="gyroid, persistent scheduler: BLAS copies of other ranks' bricks a rank may hold (0 = the owner alone serves a brick)")
     ap.add_argument("--shade-sms", type=int, default=0, help="persistent scheduler: SMs that shade instead of tracing (0 = default)")
     ap.add_argument("--gyroid-res", type=int, default=library.GYROID_RES_100M, help="grid cells per axis of the gyroid volume (946 = 100 M triangles)")
@@ -515,15 +517,17 @@ def main():
             keep = p[:: max(1, len(p) // 24)]
             return [[round(float(us) * 1e-3, 3), round(float(c) / total, 4)] for us, c, _ in keep] + [[round(float(p[-1, 0]) * 1e-3, 3), round(float(p[-1, 1]) / total, 4)]]
 
+        spp = [1]  # rays per pixel of the camera installed now
+
         def measure(label, step):
             ms, _ = timed(step, steps, warmup)
             e.sync()
             _, ctr_all = frame_rays(e)
             # persistent scheduler: every rank generates its own shard of the camera rays; round-synchronous: every rank
             # generates all of them and keeps its own (DomainTracer.h:148-181) -- the film's rays are counted once either way
-            assert ctr_all["camera_rays"] in (W * H, W * H * world), ctr_all
-            ctr_all["camera_rays"] = W * H
-            rays = W * H + ctr_all["shadow_generated"] + ctr_all["secondary_generated"]
+            assert ctr_all["camera_rays"] in (W * H * spp[0], W * H * spp[0] * world), ctr_all
+            ctr_all["camera_rays"] = W * H * spp[0]
+            rays = W * H * spp[0] + ctr_all["shadow_generated"] + ctr_all["secondary_generated"]
             out = {"schedule": label, "ms_per_frame": ms, "rays_per_frame": rays, "Mrays_per_s": rays / (ms * 1e-3) / 1e6, "rays_exported": ctr_all["rays_exported"],
                    "queue_overflows": ctr_all["queue_overflows"]}
             return out, ctr_all
@@ -747,6 +751,42 @@ def main():
             barrier()
             e.p2p_detach()
             barrier()
+        # ---- the same scene, film and schedule with samples^2 rays per pixel: a frame with enough rays per lane to show the
+        # scheduler's throughput (at 1 spp and 8 GPUs a lane sees ~15 rays and the frame is as long as its longest ray chain)
+        if a.gyroid_samples > 1:
+            ns = a.gyroid_samples
+            eye, focus, up, fov, depth, _, jitter = e.recipe["cam"]
+            g.check(g.lib().gvtb200_scene_set_camera(e.h, g._fp(g.f32(eye)), g._fp(g.f32(focus)), g._fp(g.f32(up)), fov, depth, ns, jitter))
+            spp[0] = ns * ns
+            if world > 1:
+                schedulers.p2p_connect(e, dist, rank, world, dev)
+                install()
+            more, _ = measure(headline["schedule"], persist)
+            more["samples_per_pixel"] = ns * ns
+            if world > 1:
+                more.update(persist_stats())
+                persist()
+                e.sync()
+                barrier()
+                if rank == 0:
+                    img = e.fb_read(W, H)
+                    e.recipe["cam"] = (eye, focus, up, fov, depth, ns, jitter)
+                    full, imported_ref = schedulers.whole_scene_on_one_rank(e, descs, owner, rank, mode=g.IMPORT_MAP)
+                    ref4, _ = full.render(W, H)
+                    more["parity_max_abs_err"] = float(np.abs(img - ref4).max())
+                    full.close()
+                    del imported_ref
+                barrier()
+                e.p2p_detach()
+                barrier()
+            else:
+                def wave4():
+                    e.render_async(H)
+
+                w4, _ = measure("wave path", wave4)
+                more["wave_path_ms_per_frame"] = w4["ms_per_frame"]
+                more["one_gpu_ms_per_frame"] = min(w4["ms_per_frame"], more["ms_per_frame"])
+            res["more_rays_per_pixel"] = more
         return res, e, d
 
     # ================= the headline workload ========================================================================================
