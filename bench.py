@@ -761,7 +761,7 @@ def main():
             if world > 1:
                 schedulers.p2p_connect(e, dist, rank, world, dev)
                 install()
-            more, _ = measure(headline["schedule"], persist)
+            more, _ = measure(headline["schedule"] if world > 1 else "persistent kernel, all bricks on one GPU", persist)
             more["samples_per_pixel"] = ns * ns
             if world > 1:
                 more.update(persist_stats())

@@ -28,6 +28,7 @@ for name in names:
     if name.startswith("gyroid"):
         res = int(name.split(":")[1]) if ":" in name else library.GYROID_RES_100M
         d = library.gyroid_scene(res, 2, *(film or (3840, 2160)), brick_fn=lambda *a: library.gyroid_brick_torch(*a, device=dev))
+        d.samples = next((int(x[10:]) for x in sys.argv[1:] if x.startswith("--samples=")), d.samples)  # samples^2 rays per pixel
         e, _ = schedulers.build_domain_rank(d, 0, 1)
         for m in d.meshes:
             m.verts = m.tris = None
