@@ -326,7 +326,10 @@ GVTB200_API int gvtb200_domain_persist_progress(gvtb200_scene scene, uint32_t *s
  * hold a BLAS for instance i (-1 = unused), weights[4*i+j] their shares (NULL = equal); a ray bound for the instance picks
  * one by a hash of its direction bits, so the choice is reproducible.  This is how the work of a hot domain is spread:
  * GraviT's hybrid schedulers load a copy of a busy domain on idle ranks (the `Locations` list of a mesh,
- * DomainTracer.h:115-144); here a rank gets its copy from the owner over NVLink (gvtb200_mesh_import). */
+ * DomainTracer.h:115-144); here a rank gets its copy from the owner over NVLink (gvtb200_mesh_import).
+ * The table belongs to the calling rank and the ranks' tables may differ: a rank that holds a copy of a domain can list
+ * itself alone for it ("local first": what meets the domain on this rank is traced on this rank) while ranks that do not
+ * hold it list its holders; with a copy of everything everywhere no ray ever leaves its rank. */
 GVTB200_API int gvtb200_domain_set_servers(gvtb200_scene scene, const int32_t *ranks, const float *weights, int n_instances);
 /* swap the mesh of an instance (NULL = not resident); gvtb200_scene_commit afterwards */
 GVTB200_API int gvtb200_scene_set_instance_mesh(gvtb200_scene scene, int instance, gvtb200_mesh mesh);
