@@ -192,7 +192,13 @@ def _plan_worker(rank, world, port, out):
         meshes = [_FakeMesh(100 + k) if owner[k] == rank else None for k in range(n)]
         descs = schedulers.exchange_mesh_descs(dist, meshes, [(k,) for k in range(n)], owner, rank, world)
         assert all(d[0] == 100 + k for k, d in enumerate(descs))  # every instance's descriptor came from its owner
-        out.put((rank, ranks_tab.tolist(), np.round(weights, 4).tolist()))
+        # local first: the same holders on every rank, but a table of its own per rank
+        holders, share = schedulers.plan_holders(t.numpy(), owner, world, max_replicas=2)
+        tab_r, tab_w = schedulers.server_table_for_rank(holders, share, rank)
+        for k, h in enumerate(holders):
+            live = [int(x) for x in tab_r[k] if x >= 0]
+            assert live == [rank] if rank in h else (live and rank not in live and set(live) <= set(h))
+        out.put((rank, ranks_tab.tolist(), np.round(weights, 4).tolist(), [list(map(int, h)) for h in holders]))
     finally:
         dist.destroy_process_group()
 
@@ -211,8 +217,9 @@ def test_server_plan_and_mesh_descriptors_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert res[0][1:] == res[1][1:]
+    assert res[0][1:] == res[1][1:]  # the hash plan and the holders are the same on both ranks
     assert any(row[1] >= 0 for row in res[0][1])
+    assert any(len(h) == 2 for h in res[0][3])  # somebody holds a replica
 
 
 def test_local_first_replica_plan():
